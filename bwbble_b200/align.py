@@ -1,0 +1,265 @@
+"""Host-side mirror of the reference's operator interface for the hot path.
+
+Reference interface                      -> here
+  load_bwt (bwt.c:90-125)                -> Aligner.load_index / Aligner.upload_index
+  O / O_alphabet (bwt.c:348-438)         -> Aligner.occ / Aligner.occ_alphabet           (K1)
+  exact_match (exact_match.c:58-60)      -> Aligner.exact_match                          (K2)
+  calculate_d (inexact_match.c:171-254)  -> Aligner.calculate_d                          (K3)
+  align_reads_inexact{,_parallel}        -> Aligner.align -> AlignResult.aln_bytes()     (K4+K5)
+     (inexact_match.c:25-168)               (= the bytes alns2alnf_bin appends to the .aln file)
+  align_reads (align.c:40-87)            -> align_reads(fasta, fastq, aln_out, params)
+
+Everything runs through the C ABI of libbwbble_b200.so; there is no Python compute path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+from ._lib import Hit, Params
+from .index import BwtIndex, load_bwt
+from .params import default_params
+
+
+def _u8(a) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=np.uint8)
+
+
+def _u64(a) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=np.uint64)
+
+
+class AlignResult:
+    """Owner of a bwb_results*."""
+
+    def __init__(self, aligner: "Aligner", handle: int):
+        self._a = aligner
+        self._h = C.c_void_p(handle)
+
+    def close(self):
+        if self._h:
+            _lib.lib().bwb_results_free(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def fetch(self):
+        _lib.check(_lib.lib().bwb_results_fetch(self._h), self._a._ctx)
+        return self
+
+    @property
+    def num_reads(self) -> int:
+        return int(_lib.lib().bwb_results_num_reads(self._h))
+
+    @property
+    def num_hits(self) -> int:
+        return int(_lib.lib().bwb_results_num_hits(self._h))
+
+    def counts(self) -> np.ndarray:
+        p = _lib.lib().bwb_results_counts(self._h)
+        n = self.num_reads
+        if not p or n == 0:
+            return np.zeros(n, dtype=np.uint32)
+        return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint32)), shape=(n,)).copy()
+
+    def hits(self) -> np.ndarray:
+        """Structured array view of the bwb_hit records (copied)."""
+        n = self.num_hits
+        dt = np.dtype([("L", "<u8"), ("U", "<u8"), ("score", "<i4"), ("num_mm", "u1"), ("num_gapo", "u1"),
+                       ("num_gape", "u1"), ("aln_length", "u1"), ("n_runs", "u1"), ("pad", "u1", 3),
+                       ("read_id", "<u4"), ("runs", "u1", 16)])
+        assert dt.itemsize == C.sizeof(Hit)
+        p = _lib.lib().bwb_results_hits(self._h)
+        if not p or n == 0:
+            return np.zeros(0, dtype=dt)
+        raw = C.string_at(p, n * dt.itemsize)
+        return np.frombuffer(raw, dtype=dt).copy()
+
+    def counters(self) -> dict:
+        arr = (C.c_uint64 * 8)()
+        _lib.check(_lib.lib().bwb_results_counters(self._h, C.byref(arr)), self._a._ctx)
+        names = ["pops", "pushes", "exact_tails", "rank_queries", "max_heap", "max_list"]
+        return {k: int(arr[i]) for i, k in enumerate(names)}
+
+    def aln_bytes(self) -> bytes:
+        buf = C.c_void_p()
+        ln = C.c_uint64()
+        _lib.check(_lib.lib().bwb_results_aln_bytes(self._h, C.byref(buf), C.byref(ln)), self._a._ctx)
+        try:
+            return C.string_at(buf, ln.value)
+        finally:
+            _lib.lib().bwb_free(buf)
+
+    def write_aln(self, path: str, append: bool = False):
+        _lib.check(_lib.lib().bwb_results_write_aln(self._h, os.fsencode(path), int(append)), self._a._ctx)
+
+
+class DeviceReads:
+    """Owner of a bwb_reads* (reads resident in HBM)."""
+
+    def __init__(self, aligner: "Aligner", handle: int, n: int):
+        self._a = aligner
+        self._h = C.c_void_p(handle)
+        self.n = n
+
+    def close(self):
+        if self._h:
+            _lib.lib().bwb_reads_free(self._h)
+            self._h = None
+
+    __del__ = close
+
+
+class Aligner:
+    """A bwb_ctx: devices + replicated index + search scratch."""
+
+    def __init__(self, devices: Optional[Sequence[int]] = None, **options):
+        L = _lib.lib()
+        if devices is None:
+            self._ctx = L.bwb_create(None, 0)
+        else:
+            arr = (C.c_int * len(devices))(*devices)
+            self._ctx = L.bwb_create(arr, len(devices))
+        if not self._ctx:
+            msg = L.bwb_last_error(None)
+            raise _lib.BwbError(-2, msg.decode() if msg else "bwb_create failed")
+        self._ctx = C.c_void_p(self._ctx)
+        for k, v in options.items():
+            self.set_option(k, v)
+        self.index: Optional[BwtIndex] = None
+
+    def close(self):
+        if getattr(self, "_ctx", None):
+            _lib.lib().bwb_destroy(self._ctx)
+            self._ctx = None
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def set_option(self, key: str, value: int):
+        _lib.check(_lib.lib().bwb_set_option(self._ctx, key.encode(), int(value)), self._ctx)
+
+    def set_stream(self, cuda_stream: int, dev_slot: int = 0):
+        """Launch on a caller-owned stream, e.g. torch.cuda.current_stream().cuda_stream."""
+        _lib.check(_lib.lib().bwb_set_stream(self._ctx, dev_slot, C.c_void_p(cuda_stream)), self._ctx)
+
+    # ---- index -----------------------------------------------------------------------------
+    def upload_index(self, ix: BwtIndex):
+        C17 = _u64(ix.C)
+        bwt = np.ascontiguousarray(ix.bwt, dtype=np.uint32)
+        O = _u64(ix.O)
+        _lib.check(_lib.lib().bwb_index_upload(self._ctx, ix.length, ix.sa0_index, C17.ctypes.data, bwt.ctypes.data,
+                                               len(bwt), O.ctypes.data, len(O) // 16), self._ctx)
+        self.index = ix
+
+    def load_index(self, bwt_path: str):
+        self.upload_index(load_bwt(bwt_path))
+
+    def download_blocks(self) -> np.ndarray:
+        n = int(_lib.lib().bwb_index_num_blocks(self._ctx))
+        out = np.zeros((n, 32), dtype=np.uint32)
+        _lib.check(_lib.lib().bwb_index_download_blocks(self._ctx, out.ctypes.data), self._ctx)
+        return out
+
+    # ---- K1 ----------------------------------------------------------------------------------
+    def occ(self, codes, pos) -> np.ndarray:
+        codes, pos = _u8(codes), _u64(pos)
+        out = np.zeros(len(pos), dtype=np.uint64)
+        _lib.check(_lib.lib().bwb_occ(self._ctx, codes.ctypes.data, pos.ctypes.data, len(pos), out.ctypes.data), self._ctx)
+        return out
+
+    def occ_alphabet(self, pos, inc: int) -> np.ndarray:
+        pos = _u64(pos)
+        out = np.zeros((len(pos), 16), dtype=np.uint64)
+        _lib.check(_lib.lib().bwb_occ_alphabet(self._ctx, pos.ctypes.data, len(pos), inc, out.ctypes.data), self._ctx)
+        return out
+
+    def occ_bench(self, n: int, seed: int = 1, mode: int = 0, iters: int = 10):
+        ms = C.c_float()
+        ck = C.c_uint64()
+        _lib.check(_lib.lib().bwb_occ_bench(self._ctx, n, seed, mode, iters, C.byref(ms), C.byref(ck)), self._ctx)
+        return float(ms.value), int(ck.value)
+
+    # ---- K2 / K3 -------------------------------------------------------------------------------
+    def exact_match(self, seq, offsets) -> List[np.ndarray]:
+        seq, offsets = _u8(seq), _u64(offsets)
+        n = len(offsets) - 1
+        counts = np.zeros(n, dtype=np.uint32)
+        buf = C.c_void_p()
+        tot = C.c_uint64()
+        _lib.check(_lib.lib().bwb_exact_match(self._ctx, seq.ctypes.data, offsets.ctypes.data, n, counts.ctypes.data,
+                                              C.byref(buf), C.byref(tot)), self._ctx)
+        try:
+            flat = np.frombuffer(C.string_at(buf, tot.value * 16), dtype=np.uint64).reshape(-1, 2).copy()
+        finally:
+            _lib.lib().bwb_free(buf)
+        ends = np.cumsum(counts)
+        return [flat[e - c:e] for c, e in zip(counts, ends)]
+
+    def calculate_d(self, seq, offsets, use_len: int = 0) -> List[np.ndarray]:
+        seq, offsets = _u8(seq), _u64(offsets)
+        n = len(offsets) - 1
+        total = int(offsets[-1] - offsets[0])
+        out = np.zeros(2 * (total + n), dtype=np.int32)
+        _lib.check(_lib.lib().bwb_calculate_d(self._ctx, seq.ctypes.data, offsets.ctypes.data, n, use_len,
+                                              out.ctypes.data), self._ctx)
+        res = []
+        base = int(offsets[0])
+        for r in range(n):
+            ln = int(offsets[r + 1] - offsets[r])
+            dl = min(use_len, ln) if use_len > 0 else ln
+            o = 2 * (int(offsets[r]) - base + r)
+            res.append(out[o:o + 2 * (dl + 1)].reshape(-1, 2).copy())
+        return res
+
+    # ---- K4 + K5 --------------------------------------------------------------------------------
+    def align(self, seq, offsets, params: Optional[Params] = None) -> AlignResult:
+        """Host buffers in, host-readable results out (H2D + kernels + D2H)."""
+        seq, offsets = _u8(seq), _u64(offsets)
+        params = params or default_params()
+        h = C.c_void_p()
+        _lib.check(_lib.lib().bwb_align(self._ctx, C.byref(params), seq.ctypes.data, offsets.ctypes.data,
+                                        len(offsets) - 1, C.byref(h)), self._ctx)
+        return AlignResult(self, h.value)
+
+    def upload_reads(self, seq, offsets) -> DeviceReads:
+        seq, offsets = _u8(seq), _u64(offsets)
+        h = C.c_void_p()
+        _lib.check(_lib.lib().bwb_reads_upload(self._ctx, seq.ctypes.data, offsets.ctypes.data, len(offsets) - 1,
+                                               C.byref(h)), self._ctx)
+        return DeviceReads(self, h.value, len(offsets) - 1)
+
+    def align_resident(self, reads: DeviceReads, params: Optional[Params] = None, fetch: bool = False) -> AlignResult:
+        params = params or default_params()
+        h = C.c_void_p()
+        _lib.check(_lib.lib().bwb_align_resident(self._ctx, C.byref(params), reads._h, int(fetch), C.byref(h)), self._ctx)
+        return AlignResult(self, h.value)
+
+
+def align_reads(fasta_path: str, fastq_path: str, aln_path: str, params: Optional[Params] = None,
+                devices: Optional[Sequence[int]] = None, batch: int = 0x40000 * 4) -> int:
+    """`bwbble align` (align_reads, align.c:40-87): loads <fasta>.bwt, maps every read of the FASTQ
+    and writes the binary .aln file, in batches (READ_BATCH_SIZE x 4 reads by default)."""
+    from .fastx import read_fastq
+    params = params or default_params()
+    if os.path.exists(aln_path):
+        os.remove(aln_path)                       # align.c:48
+    reads = read_fastq(fastq_path)
+    with Aligner(devices) as al:
+        al.load_index(fasta_path + ".bwt")
+        open(aln_path, "wb").close()
+        for lo in range(0, reads.n, batch):
+            sub = reads.slice(lo, min(reads.n, lo + batch))
+            res = al.align(sub.seq, sub.offsets, params)
+            res.write_aln(aln_path, append=True)
+            res.close()
+    return reads.n

@@ -1,0 +1,760 @@
+// bwb_abi.cu -- host side of the C ABI declared in include/bwbble_b200.h.
+//
+// One bwb_ctx owns one or more CUDA devices.  The index is replicated per device; reads of one
+// bwb_align call are sharded in contiguous ranges (static chunks, like the reference's OpenMP
+// driver, inexact_match.c:115-116) and every shard runs K4 -> scan -> K5 on its device's stream.
+// There is no CPU fallback: every entry point that needs the device fails with BWB_ERR_CUDA when
+// CUDA is unusable.
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "bwb_kernels.cuh"
+#include "bwbble_b200.h"
+#include "host_common.h"
+
+using namespace bwb;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t bytes = 0;
+};
+
+struct Device {
+    int id = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    int sm_count = 0;
+    // index
+    uint4 *blocks = nullptr;
+    // search scratch (sized for n_warps)
+    int n_warps = 0, grid = 0, wpb = 0;
+    size_t smem_bytes = 0;
+    DevBuf glists, chunks, chunk_link, stage;
+    uint32_t chunks_per_warp = 0, n_chunks = 0;
+    // per-call buffers
+    DevBuf seq, offsets, read_off, read_cnt, ordered_off, unordered, ordered, cub_tmp, small;
+    // pinned staging for small D2H
+    unsigned long long *h_small = nullptr;
+};
+
+}  // namespace
+
+struct bwb_ctx {
+    std::vector<Device> dev;
+    std::string err;
+    // index meta
+    bool have_index = false;
+    uint64_t length = 0, num_blocks = 0, sa0 = 0;
+    uint64_t C[17] = {0};
+    // options
+    long long heap_pool_mb = 8192;
+    int list_cap = 8192;
+    int hits_per_read = 1024;
+    int warps_per_block = 8;
+    int blocks_per_sm = 0;
+};
+
+struct bwb_reads {
+    bwb_ctx *ctx = nullptr;
+    uint64_t n_reads = 0;
+    int max_len = 0;
+    std::vector<uint64_t> shard_lo;      // per device, n_dev+1 entries
+    std::vector<void *> d_seq, d_off;    // per device
+};
+
+struct bwb_results {
+    bwb_ctx *ctx = nullptr;
+    uint64_t n_reads = 0;
+    std::vector<uint32_t> counts;
+    std::vector<bwb_hit> hits;
+    uint64_t counters[8] = {0};
+    // pending (device-resident) state
+    bool fetched = false;
+    std::vector<uint64_t> shard_lo;
+    std::vector<uint64_t> shard_total;
+    int status = 0;
+};
+
+namespace {
+
+int fail(bwb_ctx *ctx, int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    if (ctx) ctx->err = buf;
+    return code;
+}
+
+#define CU(call)                                                                                     \
+    do {                                                                                             \
+        cudaError_t e_ = (call);                                                                     \
+        if (e_ != cudaSuccess)                                                                       \
+            return fail(ctx, BWB_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_),   \
+                        __FILE__, __LINE__);                                                         \
+    } while (0)
+
+int ensure(bwb_ctx *ctx, DevBuf &b, size_t bytes, bool slack = true) {
+    if (b.bytes >= bytes && b.p) return BWB_OK;
+    if (b.p) CU(cudaFree(b.p));
+    b.p = nullptr;
+    b.bytes = 0;
+    size_t want = slack ? bytes + bytes / 4 + 256 : bytes + 256;
+    CU(cudaMalloc(&b.p, want));
+    b.bytes = want;
+    return BWB_OK;
+}
+
+void release(DevBuf &b) {
+    if (b.p) cudaFree(b.p);
+    b.p = nullptr;
+    b.bytes = 0;
+}
+
+IndexView make_view(const bwb_ctx *ctx, const Device &d) {
+    IndexView v;
+    v.blocks = d.blocks;
+    v.length = ctx->length;
+    v.num_blocks = ctx->num_blocks;
+    for (int i = 0; i < 17; i++) v.C[i] = ctx->C[i];
+    return v;
+}
+
+int check_reads(bwb_ctx *ctx, const uint64_t *offsets, uint64_t n_reads, int &max_len) {
+    max_len = 0;
+    if (n_reads >= 0xffffffffull) return fail(ctx, BWB_ERR_ARG, "too many reads in one call");
+    for (uint64_t r = 0; r < n_reads; r++) {
+        if (offsets[r + 1] < offsets[r]) return fail(ctx, BWB_ERR_ARG, "offsets not monotone at read %llu", (unsigned long long)r);
+        uint64_t l = offsets[r + 1] - offsets[r];
+        if (l > 255) return fail(ctx, BWB_ERR_ARG, "read %llu is %llu bases; positions are 8-bit (align.h:104)", (unsigned long long)r, (unsigned long long)l);
+        if ((int)l > max_len) max_len = (int)l;
+    }
+    return BWB_OK;
+}
+
+// per-warp shared-memory layout of K4 (must match k_align)
+struct SmemLayout {
+    int per_warp, off_D, off_Ds, off_bk, off_seq;
+};
+SmemLayout k4_layout(int max_len, int seed_len, int nb) {
+    SmemLayout L;
+    int o = 2 * SL * (int)sizeof(ulonglong2);
+    L.off_D = o;
+    o += ((max_len + 1) * 8 + 15) & ~15;
+    L.off_Ds = o;
+    o += ((seed_len + 1) * 8 + 15) & ~15;
+    L.off_bk = o;
+    o += (nb * 12 + 15) & ~15;
+    L.off_seq = o;
+    o += (max_len + 15) & ~15;
+    L.per_warp = o;
+    return L;
+}
+
+// size the persistent grid and the per-warp scratch for K4
+int prepare_search(bwb_ctx *ctx, Device &d, const SmemLayout &L) {
+    CU(cudaSetDevice(d.id));
+    const int wpb = ctx->warps_per_block;
+    const size_t smem = (size_t)wpb * L.per_warp;
+    if (smem > 227 * 1024) return fail(ctx, BWB_ERR_ARG, "shared memory per block %zu exceeds 227 KB", smem);
+    CU(cudaFuncSetAttribute(k_align, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int bps = ctx->blocks_per_sm;
+    if (bps <= 0) {
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_align, wpb * 32, smem));
+        if (bps <= 0) return fail(ctx, BWB_ERR_CUDA, "k_align does not fit on an SM");
+    }
+    const int grid = bps * d.sm_count;
+    const int n_warps = grid * wpb;
+    d.smem_bytes = smem;
+    if (n_warps != d.n_warps || wpb != d.wpb) {
+        release(d.glists); release(d.chunks); release(d.chunk_link); release(d.stage);
+        d.n_warps = n_warps; d.grid = grid; d.wpb = wpb;
+    }
+    d.grid = grid;
+    int rc;
+    if ((rc = ensure(ctx, d.glists, (size_t)n_warps * 2 * ctx->list_cap * sizeof(ulonglong2), false))) return rc;
+    if ((rc = ensure(ctx, d.stage, (size_t)n_warps * ctx->hits_per_read * sizeof(bwb_hit), false))) return rc;
+    if (!d.chunks.p) {
+        const size_t chunk_bytes = (size_t)CHUNK_ENTRIES * 32;
+        uint64_t n_chunks = ((uint64_t)ctx->heap_pool_mb << 20) / chunk_bytes;
+        if (n_chunks < (uint64_t)n_warps * 8) n_chunks = (uint64_t)n_warps * 8;
+        if (n_chunks > 0xfffffff0ull) n_chunks = 0xfffffff0ull;
+        d.n_chunks = (uint32_t)n_chunks;
+        d.chunks_per_warp = (uint32_t)((n_chunks - n_chunks / 4) / n_warps);   // 3/4 private, 1/4 shared overflow
+        if ((rc = ensure(ctx, d.chunks, (size_t)n_chunks * chunk_bytes, false))) return rc;
+        if ((rc = ensure(ctx, d.chunk_link, (size_t)n_chunks * 4, false))) return rc;
+    }
+    return BWB_OK;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+extern "C" {
+
+void bwb_default_params(bwb_params *p) {   // align.c:22-38
+    memset(p, 0, sizeof *p);
+    p->gape_score = 4; p->gapo_score = 11; p->mm_score = 3;
+    p->max_diff = 0; p->max_gape = 6; p->max_gapo = 1;
+    p->seed_length = 32; p->max_diff_seed = 2; p->max_entries = 3000000;
+    p->use_precalc = 0; p->matched_Ncontig = 0; p->is_multiref = 1;
+    p->max_best = 30; p->no_indel_length = 5; p->n_threads = 1;
+}
+
+const char *bwb_last_error(const bwb_ctx *ctx) { return ctx ? ctx->err.c_str() : g_last_error.c_str(); }
+
+bwb_ctx *bwb_create(const int *devices, int ndev) {
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        fail(nullptr, BWB_ERR_CUDA, "no usable CUDA device: %s (this library has no CPU fallback)",
+             e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+        return nullptr;
+    }
+    bwb_ctx *ctx = new bwb_ctx();
+    std::vector<int> ids;
+    if (!devices || ndev <= 0) ids.push_back(0);
+    else ids.assign(devices, devices + ndev);
+    for (int id : ids) {
+        if (id < 0 || id >= count) {
+            fail(nullptr, BWB_ERR_ARG, "device %d out of range (%d visible)", id, count);
+            delete ctx;
+            return nullptr;
+        }
+        Device d;
+        d.id = id;
+        cudaDeviceProp prop;
+        if (cudaSetDevice(id) != cudaSuccess || cudaGetDeviceProperties(&prop, id) != cudaSuccess ||
+            cudaStreamCreateWithFlags(&d.own_stream, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaMallocHost((void **)&d.h_small, 64 * sizeof(unsigned long long)) != cudaSuccess) {
+            fail(nullptr, BWB_ERR_CUDA, "cannot initialise device %d: %s", id, cudaGetErrorString(cudaGetLastError()));
+            delete ctx;
+            return nullptr;
+        }
+        d.stream = d.own_stream;
+        d.sm_count = prop.multiProcessorCount;
+        ctx->dev.push_back(d);
+    }
+    return ctx;
+}
+
+void bwb_destroy(bwb_ctx *ctx) {
+    if (!ctx) return;
+    for (auto &d : ctx->dev) {
+        cudaSetDevice(d.id);
+        cudaDeviceSynchronize();
+        if (d.blocks) cudaFree(d.blocks);
+        DevBuf *bufs[] = {&d.glists, &d.chunks, &d.chunk_link, &d.stage, &d.seq, &d.offsets, &d.read_off, &d.read_cnt,
+                          &d.ordered_off, &d.unordered, &d.ordered, &d.cub_tmp, &d.small};
+        for (DevBuf *b : bufs) release(*b);
+        if (d.h_small) cudaFreeHost(d.h_small);
+        if (d.own_stream) cudaStreamDestroy(d.own_stream);
+    }
+    delete ctx;
+}
+
+int bwb_device_count(const bwb_ctx *ctx) { return ctx ? (int)ctx->dev.size() : 0; }
+
+int bwb_set_option(bwb_ctx *ctx, const char *key, long long value) {
+    if (!ctx || !key) return BWB_ERR_ARG;
+    std::string k(key);
+    if (value <= 0 && k != "blocks_per_sm") return fail(ctx, BWB_ERR_ARG, "option %s needs a positive value", key);
+    if (k == "heap_pool_mb") ctx->heap_pool_mb = value;
+    else if (k == "list_cap") ctx->list_cap = (int)(value < SL + 4 ? SL + 4 : value);
+    else if (k == "hits_per_read") ctx->hits_per_read = (int)value;
+    else if (k == "warps_per_block") {
+        if (value > 8) return fail(ctx, BWB_ERR_ARG, "warps_per_block must be 1..8");
+        ctx->warps_per_block = (int)value;
+    } else if (k == "blocks_per_sm") ctx->blocks_per_sm = (int)value;
+    else return fail(ctx, BWB_ERR_ARG, "unknown option %s", key);
+    for (auto &d : ctx->dev) {       // scratch is re-sized lazily
+        cudaSetDevice(d.id);
+        cudaDeviceSynchronize();
+        release(d.glists); release(d.chunks); release(d.chunk_link); release(d.stage);
+        d.n_warps = 0;
+    }
+    return BWB_OK;
+}
+
+int bwb_set_stream(bwb_ctx *ctx, int dev_slot, void *cuda_stream) {
+    if (!ctx || dev_slot < 0 || dev_slot >= (int)ctx->dev.size()) return BWB_ERR_ARG;
+    ctx->dev[dev_slot].stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->dev[dev_slot].own_stream;
+    return BWB_OK;
+}
+
+// ---- index ------------------------------------------------------------------------------------
+int bwb_index_upload(bwb_ctx *ctx, uint64_t length, uint64_t sa0_index, const uint64_t C[17], const uint32_t *bwt,
+                     uint64_t num_words, const uint64_t *O, uint64_t num_occ) {
+    if (!ctx || !C || !bwt || !O || length < 2) return fail(ctx, BWB_ERR_ARG, "bwb_index_upload: bad argument");
+    if (num_words < (length + 7) / 8 || num_occ < (length + 127) / 128)
+        return fail(ctx, BWB_ERR_ARG, "bwb_index_upload: arrays shorter than length implies");
+    if (length >= (1ull << 40)) return fail(ctx, BWB_ERR_ARG, "index longer than 2^40 rows");
+    ctx->length = length;
+    ctx->sa0 = sa0_index;
+    ctx->num_blocks = (length + 127) / 128;
+    memcpy(ctx->C, C, sizeof ctx->C);
+    for (auto &d : ctx->dev) {
+        CU(cudaSetDevice(d.id));
+        if (d.blocks) { CU(cudaFree(d.blocks)); d.blocks = nullptr; }
+        uint32_t *d_bwt = nullptr, *d_err = nullptr;
+        uint64_t *d_O = nullptr;
+        CU(cudaMalloc(&d.blocks, ctx->num_blocks * 128));
+        CU(cudaMalloc(&d_bwt, num_words * 4));
+        CU(cudaMalloc(&d_O, num_occ * 16 * 8));
+        CU(cudaMalloc(&d_err, 4));
+        CU(cudaMemcpyAsync(d_bwt, bwt, num_words * 4, cudaMemcpyHostToDevice, d.stream));
+        CU(cudaMemcpyAsync(d_O, O, num_occ * 16 * 8, cudaMemcpyHostToDevice, d.stream));
+        CU(cudaMemsetAsync(d_err, 0, 4, d.stream));
+        const unsigned tpb = 128;
+        const unsigned grid = (unsigned)((ctx->num_blocks + tpb - 1) / tpb);
+        k_relayout<<<grid, tpb, 0, d.stream>>>(d_bwt, num_words, d_O, num_occ, sa0_index,
+                                              reinterpret_cast<uint32_t *>(d.blocks), ctx->num_blocks, d_err);
+        CU(cudaGetLastError());
+        uint32_t herr = 0;
+        CU(cudaMemcpyAsync(&herr, d_err, 4, cudaMemcpyDeviceToHost, d.stream));
+        CU(cudaStreamSynchronize(d.stream));
+        CU(cudaFree(d_bwt)); CU(cudaFree(d_O)); CU(cudaFree(d_err));
+        if (herr) return fail(ctx, BWB_ERR_ARG, "a per-code rank counter exceeds 2^32 (index too large for u32 checkpoints)");
+    }
+    ctx->have_index = true;
+    return BWB_OK;
+}
+
+int bwb_index_load_file(bwb_ctx *ctx, const char *bwt_path) {
+    if (!ctx || !bwt_path) return BWB_ERR_ARG;
+    bwb_host::HostIndex ix;
+    if (bwb_host::read_bwt_file(bwt_path, ix, false)) return fail(ctx, BWB_ERR_IO, "cannot read %s", bwt_path);
+    return bwb_index_upload(ctx, ix.length, ix.sa0_index, ix.C, ix.bwt.data(), ix.num_words, ix.O.data(), ix.num_occ);
+}
+
+uint64_t bwb_index_num_blocks(const bwb_ctx *ctx) { return ctx && ctx->have_index ? ctx->num_blocks : 0; }
+
+int bwb_index_download_blocks(bwb_ctx *ctx, void *out) {
+    if (!ctx || !out) return BWB_ERR_ARG;
+    if (!ctx->have_index) return fail(ctx, BWB_ERR_NO_INDEX, "no index uploaded");
+    Device &d = ctx->dev[0];
+    CU(cudaSetDevice(d.id));
+    CU(cudaMemcpy(out, d.blocks, ctx->num_blocks * 128, cudaMemcpyDeviceToHost));
+    return BWB_OK;
+}
+
+// ---- K1 ---------------------------------------------------------------------------------------
+int bwb_occ(bwb_ctx *ctx, const uint8_t *code, const uint64_t *pos, uint64_t n, uint64_t *out) {
+    if (!ctx || !code || !pos || !out) return BWB_ERR_ARG;
+    if (!ctx->have_index) return fail(ctx, BWB_ERR_NO_INDEX, "no index uploaded");
+    if (n == 0) return BWB_OK;
+    Device &d = ctx->dev[0];
+    CU(cudaSetDevice(d.id));
+    uint8_t *dc; uint64_t *dp, *dout;
+    CU(cudaMalloc(&dc, n)); CU(cudaMalloc(&dp, n * 8)); CU(cudaMalloc(&dout, n * 8));
+    CU(cudaMemcpyAsync(dc, code, n, cudaMemcpyHostToDevice, d.stream));
+    CU(cudaMemcpyAsync(dp, pos, n * 8, cudaMemcpyHostToDevice, d.stream));
+    k_occ<<<(unsigned)((n + 255) / 256), 256, 0, d.stream>>>(make_view(ctx, d), dc, dp, n, dout);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(out, dout, n * 8, cudaMemcpyDeviceToHost, d.stream));
+    CU(cudaStreamSynchronize(d.stream));
+    cudaFree(dc); cudaFree(dp); cudaFree(dout);
+    return BWB_OK;
+}
+
+int bwb_occ_alphabet(bwb_ctx *ctx, const uint64_t *pos, uint64_t n, int inc, uint64_t *out) {
+    if (!ctx || !pos || !out) return BWB_ERR_ARG;
+    if (!ctx->have_index) return fail(ctx, BWB_ERR_NO_INDEX, "no index uploaded");
+    if (n == 0) return BWB_OK;
+    Device &d = ctx->dev[0];
+    CU(cudaSetDevice(d.id));
+    uint64_t *dp, *dout;
+    CU(cudaMalloc(&dp, n * 8)); CU(cudaMalloc(&dout, n * 16 * 8));
+    CU(cudaMemcpyAsync(dp, pos, n * 8, cudaMemcpyHostToDevice, d.stream));
+    k_occ_alphabet<<<(unsigned)((n * 16 + 255) / 256), 256, 0, d.stream>>>(make_view(ctx, d), dp, n, (uint32_t)inc, dout);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(out, dout, n * 16 * 8, cudaMemcpyDeviceToHost, d.stream));
+    CU(cudaStreamSynchronize(d.stream));
+    cudaFree(dp); cudaFree(dout);
+    return BWB_OK;
+}
+
+int bwb_occ_bench(bwb_ctx *ctx, uint64_t n, uint64_t seed, int mode, int iters, float *ms_per_launch, uint64_t *checksum) {
+    if (!ctx || n == 0 || iters <= 0) return BWB_ERR_ARG;
+    if (!ctx->have_index) return fail(ctx, BWB_ERR_NO_INDEX, "no index uploaded");
+    Device &d = ctx->dev[0];
+    CU(cudaSetDevice(d.id));
+    unsigned long long *dsink;
+    CU(cudaMalloc(&dsink, 8));
+    CU(cudaMemsetAsync(dsink, 0, 8, d.stream));
+    const int chain = mode >= 2 ? 8 : 1;          // modes 2/3 = modes 0/1 with 8 dependent queries per thread
+    const int m = mode & 1;
+    const uint64_t threads = m ? n * 16 : n;
+    const unsigned grid = (unsigned)((threads + 255) / 256);
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+    for (int it = -2; it < iters; it++) {          // two warm-up launches
+        if (it == 0) CU(cudaEventRecord(e0, d.stream));
+        if (m) k_occ_bench<1><<<grid, 256, 0, d.stream>>>(make_view(ctx, d), n, seed + it, chain, dsink);
+        else k_occ_bench<0><<<grid, 256, 0, d.stream>>>(make_view(ctx, d), n, seed + it, chain, dsink);
+    }
+    CU(cudaEventRecord(e1, d.stream));
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(d.stream));
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, e0, e1));
+    if (ms_per_launch) *ms_per_launch = ms / iters;
+    unsigned long long h = 0;
+    CU(cudaMemcpy(&h, dsink, 8, cudaMemcpyDeviceToHost));
+    if (checksum) *checksum = h;
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(dsink);
+    return BWB_OK;
+}
+
+// ---- K2 / K3 ----------------------------------------------------------------------------------
+static int run_list_kernel(bwb_ctx *ctx, int which, const uint8_t *seq, const uint64_t *offsets, uint64_t n_reads,
+                           int use_len, uint32_t *counts, uint64_t **intervals, uint64_t *n_intervals, int32_t *out_d) {
+    if (!ctx || !seq || !offsets) return BWB_ERR_ARG;
+    if (!ctx->have_index) return fail(ctx, BWB_ERR_NO_INDEX, "no index uploaded");
+    int max_len, rc;
+    if ((rc = check_reads(ctx, offsets, n_reads, max_len))) return rc;
+    if (n_reads == 0) { if (n_intervals) *n_intervals = 0; if (intervals) *intervals = nullptr; return BWB_OK; }
+    Device &d = ctx->dev[0];
+    CU(cudaSetDevice(d.id));
+    const int wpb = 4;
+    const int grid = d.sm_count * 4;
+    const int n_warps = grid * wpb;
+    const uint64_t total = offsets[n_reads] - offsets[0];
+    ListArgs a;
+    memset(&a, 0, sizeof a);
+    a.ix = make_view(ctx, d);
+    a.n_reads = (uint32_t)n_reads;
+    a.list_cap = ctx->list_cap;
+    a.max_len = max_len;
+    a.use_len = use_len;
+    uint8_t *dseq; uint64_t *doff; ulonglong2 *gl; uint32_t *dstatus;
+    CU(cudaMalloc(&dseq, total + 16)); CU(cudaMalloc(&doff, (n_reads + 1) * 8));
+    CU(cudaMalloc(&gl, (size_t)n_warps * 2 * a.list_cap * sizeof(ulonglong2)));
+    CU(cudaMalloc(&dstatus, 8));
+    std::vector<uint64_t> rel(n_reads + 1);
+    for (uint64_t r = 0; r <= n_reads; r++) rel[r] = offsets[r] - offsets[0];
+    CU(cudaMemcpyAsync(dseq, seq + offsets[0], total, cudaMemcpyHostToDevice, d.stream));
+    CU(cudaMemcpyAsync(doff, rel.data(), (n_reads + 1) * 8, cudaMemcpyHostToDevice, d.stream));
+    CU(cudaMemsetAsync(dstatus, 0, 8, d.stream));
+    a.seq = dseq; a.offsets = doff; a.glists = gl; a.status = dstatus;
+    uint32_t hstatus = 0;
+    if (which == 2) {
+        unsigned long long *dcur, *droff; uint32_t *drcnt; ulonglong2 *dout;
+        unsigned long long cap = n_reads * 8 + 4096;
+        CU(cudaMalloc(&dcur, 8)); CU(cudaMalloc(&droff, n_reads * 8)); CU(cudaMalloc(&drcnt, n_reads * 4));
+        for (int attempt = 0;; attempt++) {
+            CU(cudaMalloc(&dout, cap * sizeof(ulonglong2)));
+            CU(cudaMemsetAsync(dcur, 0, 8, d.stream));
+            a.out_iv = dout; a.out_cap = cap; a.out_cursor = dcur; a.read_off = droff; a.read_cnt = drcnt;
+            const size_t smem = (size_t)wpb * (2 * SL * sizeof(ulonglong2) + ((max_len + 15) & ~15));
+            k_exact<<<grid, wpb * 32, smem, d.stream>>>(a);
+            CU(cudaGetLastError());
+            unsigned long long used = 0;
+            CU(cudaMemcpyAsync(&used, dcur, 8, cudaMemcpyDeviceToHost, d.stream));
+            CU(cudaMemcpyAsync(&hstatus, dstatus, 4, cudaMemcpyDeviceToHost, d.stream));
+            CU(cudaStreamSynchronize(d.stream));
+            if (used <= cap || attempt > 4) {
+                if (used > cap) return fail(ctx, BWB_ERR_CAPACITY, "exact-match output does not fit");
+                std::vector<unsigned long long> roff(n_reads);
+                std::vector<ulonglong2> iv(used ? used : 1);
+                CU(cudaMemcpy(roff.data(), droff, n_reads * 8, cudaMemcpyDeviceToHost));
+                CU(cudaMemcpy(counts, drcnt, n_reads * 4, cudaMemcpyDeviceToHost));
+                CU(cudaMemcpy(iv.data(), dout, used * sizeof(ulonglong2), cudaMemcpyDeviceToHost));
+                uint64_t *res = (uint64_t *)malloc((used ? used : 1) * 16);
+                uint64_t w = 0;
+                for (uint64_t r = 0; r < n_reads; r++)
+                    for (uint32_t k = 0; k < counts[r]; k++) { res[2 * w] = iv[roff[r] + k].x; res[2 * w + 1] = iv[roff[r] + k].y; w++; }
+                *intervals = res;
+                *n_intervals = w;
+                cudaFree(dout);
+                break;
+            }
+            cudaFree(dout);
+            cap = used + 4096;
+        }
+        cudaFree(dcur); cudaFree(droff); cudaFree(drcnt);
+    } else {
+        int32_t *dd;
+        const size_t nd = 2 * (total + n_reads);
+        CU(cudaMalloc(&dd, nd * 4 + 16));
+        CU(cudaMemsetAsync(dd, 0, nd * 4, d.stream));
+        a.out_d = dd;
+        const size_t smem = (size_t)wpb * (2 * SL * sizeof(ulonglong2) + (((max_len + 1) * 8 + 15) & ~15) + ((max_len + 15) & ~15));
+        CU(cudaFuncSetAttribute(k_calc_d, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_calc_d<<<grid, wpb * 32, smem, d.stream>>>(a);
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(out_d, dd, nd * 4, cudaMemcpyDeviceToHost, d.stream));
+        CU(cudaMemcpyAsync(&hstatus, dstatus, 4, cudaMemcpyDeviceToHost, d.stream));
+        CU(cudaStreamSynchronize(d.stream));
+        cudaFree(dd);
+    }
+    cudaFree(dseq); cudaFree(doff); cudaFree(gl); cudaFree(dstatus);
+    if (hstatus) return fail(ctx, -(int)hstatus, "interval list exceeded list_cap=%d (raise it with bwb_set_option)", ctx->list_cap);
+    return BWB_OK;
+}
+
+int bwb_exact_match(bwb_ctx *ctx, const uint8_t *seq, const uint64_t *offsets, uint64_t n_reads, uint32_t *counts,
+                    uint64_t **intervals_LU, uint64_t *n_intervals) {
+    if (!counts || !intervals_LU || !n_intervals) return BWB_ERR_ARG;
+    return run_list_kernel(ctx, 2, seq, offsets, n_reads, 0, counts, intervals_LU, n_intervals, nullptr);
+}
+
+int bwb_calculate_d(bwb_ctx *ctx, const uint8_t *seq, const uint64_t *offsets, uint64_t n_reads, int use_len, int32_t *out) {
+    if (!out) return BWB_ERR_ARG;
+    return run_list_kernel(ctx, 3, seq, offsets, n_reads, use_len, nullptr, nullptr, nullptr, out);
+}
+
+// ---- K4 + K5 ----------------------------------------------------------------------------------
+int bwb_reads_upload(bwb_ctx *ctx, const uint8_t *seq, const uint64_t *offsets, uint64_t n_reads, bwb_reads **out) {
+    if (!ctx || !seq || !offsets || !out) return BWB_ERR_ARG;
+    int max_len, rc;
+    if ((rc = check_reads(ctx, offsets, n_reads, max_len))) return rc;
+    bwb_reads *R = new bwb_reads();
+    R->ctx = ctx; R->n_reads = n_reads; R->max_len = max_len;
+    const int G = (int)ctx->dev.size();
+    R->shard_lo.resize(G + 1);
+    for (int g = 0; g <= G; g++) R->shard_lo[g] = (uint64_t)g * n_reads / G;
+    R->d_seq.assign(G, nullptr); R->d_off.assign(G, nullptr);
+    for (int g = 0; g < G; g++) {
+        Device &d = ctx->dev[g];
+        const uint64_t lo = R->shard_lo[g], hi = R->shard_lo[g + 1], n = hi - lo;
+        const uint64_t bytes = offsets[hi] - offsets[lo];
+        CU(cudaSetDevice(d.id));
+        CU(cudaMalloc(&R->d_seq[g], bytes + 16));
+        CU(cudaMalloc(&R->d_off[g], (n + 1) * 8));
+        std::vector<uint64_t> rel(n + 1);
+        for (uint64_t r = 0; r <= n; r++) rel[r] = offsets[lo + r] - offsets[lo];
+        CU(cudaMemcpyAsync(R->d_seq[g], seq + offsets[lo], bytes, cudaMemcpyHostToDevice, d.stream));
+        CU(cudaMemcpyAsync(R->d_off[g], rel.data(), (n + 1) * 8, cudaMemcpyHostToDevice, d.stream));
+        CU(cudaStreamSynchronize(d.stream));
+    }
+    *out = R;
+    return BWB_OK;
+}
+
+void bwb_reads_free(bwb_reads *r) {
+    if (!r) return;
+    for (size_t g = 0; g < r->d_seq.size(); g++) {
+        cudaSetDevice(r->ctx->dev[g].id);
+        if (r->d_seq[g]) cudaFree(r->d_seq[g]);
+        if (r->d_off[g]) cudaFree(r->d_off[g]);
+    }
+    delete r;
+}
+
+static int check_params(bwb_ctx *ctx, const bwb_params *p, int max_len, int &nb) {
+    if (p->use_precalc) return fail(ctx, BWB_ERR_UNSUPPORTED, "-P (pre-calculated intervals) is not built on the device path");
+    if (!p->is_multiref) return fail(ctx, BWB_ERR_UNSUPPORTED, "-S (single-genome mode) is not built on the device path");
+    if (p->max_diff < 0 || p->max_gapo < 0 || p->max_gape < 0 || p->mm_score < 0 || p->gapo_score < 0 || p->gape_score < 0 ||
+        p->seed_length < 0 || p->max_diff > 200)
+        return fail(ctx, BWB_ERR_ARG, "negative or out-of-range alignment parameter");
+    if (p->max_gapo > BWB_MAX_GAP_RUNS) return fail(ctx, BWB_ERR_UNSUPPORTED, "max_gapo > %d", BWB_MAX_GAP_RUNS);
+    nb = (p->max_diff + 1) * p->mm_score + (p->max_gapo + 1) * p->gapo_score + (p->max_gape + 1) * p->gape_score;
+    if (nb <= 0 || nb > 1024) return fail(ctx, BWB_ERR_UNSUPPORTED, "%d score buckets (supported: 1..1024)", nb);
+    if (p->seed_length > 255) return fail(ctx, BWB_ERR_ARG, "seed_length > 255");
+    int gaps = p->max_gapo + p->max_gape;
+    if (gaps > p->max_diff) gaps = p->max_diff;
+    if (max_len + gaps > 255) return fail(ctx, BWB_ERR_UNSUPPORTED, "read length %d + %d gap steps wraps the 8-bit path length (align.h:104)", max_len, gaps);
+    return BWB_OK;
+}
+
+// enqueue K4 + scan + K5 for one shard on its device stream
+static int launch_shard(bwb_ctx *ctx, Device &d, const bwb_params *p, int nb, const SmemLayout &L, int max_len,
+                        const void *d_seq, const void *d_off, uint64_t n, uint64_t read_base, unsigned long long out_cap) {
+    int rc;
+    CU(cudaSetDevice(d.id));
+    if ((rc = ensure(ctx, d.read_off, n * 8 + 8))) return rc;
+    if ((rc = ensure(ctx, d.read_cnt, n * 4 + 4))) return rc;
+    if ((rc = ensure(ctx, d.ordered_off, (n + 1) * 8))) return rc;
+    if ((rc = ensure(ctx, d.unordered, out_cap * sizeof(bwb_hit)))) return rc;
+    if ((rc = ensure(ctx, d.ordered, out_cap * sizeof(bwb_hit)))) return rc;
+    if ((rc = ensure(ctx, d.small, 256))) return rc;
+    // small block: [0] queue u32 | [8] status 2xu32 | [16] out_cursor u64 | [24] overflow cursor u32 | [32..] counters 8xu64
+    unsigned char *sm = (unsigned char *)d.small.p;
+    CU(cudaMemsetAsync(sm, 0, 256, d.stream));
+    const uint32_t ovf0 = (uint32_t)d.n_warps * d.chunks_per_warp;
+    CU(cudaMemcpyAsync(sm + 24, &ovf0, 4, cudaMemcpyHostToDevice, d.stream));
+
+    AlignArgs a;
+    memset(&a, 0, sizeof a);
+    a.ix = make_view(ctx, d);
+    a.seq = (const uint8_t *)d_seq; a.offsets = (const uint64_t *)d_off;
+    a.n_reads = (uint32_t)n; a.read_id_base = (uint32_t)read_base;
+    a.max_diff = p->max_diff; a.max_gapo = p->max_gapo; a.max_gape = p->max_gape; a.max_entries = p->max_entries;
+    a.mm_score = p->mm_score; a.gapo_score = p->gapo_score; a.gape_score = p->gape_score;
+    a.seed_len = p->seed_length; a.max_diff_seed = p->max_diff_seed; a.max_best = p->max_best;
+    a.no_indel_len = p->no_indel_length;
+    a.nb = nb; a.max_len = max_len;
+    a.queue = (uint32_t *)sm;
+    a.glists = (ulonglong2 *)d.glists.p; a.list_cap = ctx->list_cap;
+    a.chunks = (uint4 *)d.chunks.p; a.chunk_link = (uint32_t *)d.chunk_link.p;
+    a.chunks_per_warp = d.chunks_per_warp; a.n_chunks = d.n_chunks;
+    a.overflow_cursor = (uint32_t *)(sm + 24);
+    a.stage = (bwb_hit *)d.stage.p; a.hits_cap = ctx->hits_per_read;
+    a.out_hits = (bwb_hit *)d.unordered.p; a.out_cap = out_cap;
+    a.out_cursor = (unsigned long long *)(sm + 16);
+    a.read_off = (unsigned long long *)d.read_off.p; a.read_cnt = (uint32_t *)d.read_cnt.p;
+    a.status = (uint32_t *)(sm + 8);
+    a.counters = (unsigned long long *)(sm + 32);
+    a.smem_per_warp = L.per_warp; a.off_D = L.off_D; a.off_Ds = L.off_Ds; a.off_bk = L.off_bk; a.off_seq = L.off_seq;
+
+    if (n) {
+        k_align<<<d.grid, d.wpb * 32, d.smem_bytes, d.stream>>>(a);
+        CU(cudaGetLastError());
+    }
+    // K5: exclusive scan of the per-read counts, then ordered copy
+    const uint32_t *cnt = (const uint32_t *)d.read_cnt.p;
+    unsigned long long *ooff = (unsigned long long *)d.ordered_off.p;
+    if (n) {
+        k_scan_counts<<<1, 1024, 0, d.stream>>>(cnt, (uint32_t)n, ooff);
+        CU(cudaGetLastError());
+        k_emit<<<(unsigned)((n + 127) / 128), 128, 0, d.stream>>>((const bwb_hit *)d.unordered.p, a.read_off, cnt, ooff,
+                                                              (uint32_t)n, (bwb_hit *)d.ordered.p);
+        CU(cudaGetLastError());
+    }
+    return BWB_OK;
+}
+
+static int align_impl(bwb_ctx *ctx, const bwb_params *p, const bwb_reads *R, bwb_results **out) {
+    if (!ctx->have_index) return fail(ctx, BWB_ERR_NO_INDEX, "bwb_align before bwb_index_upload");
+    int nb = 0, rc;
+    if ((rc = check_params(ctx, p, R->max_len, nb))) return rc;
+    const SmemLayout L = k4_layout(R->max_len > 0 ? R->max_len : 1, p->seed_length, nb);
+    const int G = (int)ctx->dev.size();
+    bwb_results *res = new bwb_results();
+    res->ctx = ctx; res->n_reads = R->n_reads; res->shard_lo = R->shard_lo; res->shard_total.assign(G, 0);
+    res->counts.assign(R->n_reads, 0);
+
+    std::vector<unsigned long long> cap(G);
+    for (int g = 0; g < G; g++) {
+        if ((rc = prepare_search(ctx, ctx->dev[g], L))) { delete res; return rc; }
+        cap[g] = (R->shard_lo[g + 1] - R->shard_lo[g]) * 2 + 65536;
+    }
+    std::vector<char> done(G, 0);
+    for (int attempt = 0; attempt < 6; attempt++) {
+        for (int g = 0; g < G; g++) {
+            if (done[g]) continue;
+            const uint64_t lo = R->shard_lo[g], n = R->shard_lo[g + 1] - lo;
+            if ((rc = launch_shard(ctx, ctx->dev[g], p, nb, L, R->max_len > 0 ? R->max_len : 1, R->d_seq[g], R->d_off[g], n, lo, cap[g]))) {
+                delete res;
+                return rc;
+            }
+        }
+        bool again = false;
+        for (int g = 0; g < G; g++) {
+            if (done[g]) continue;
+            Device &d = ctx->dev[g];
+            CU(cudaSetDevice(d.id));
+            CU(cudaMemcpyAsync(d.h_small, d.small.p, 256, cudaMemcpyDeviceToHost, d.stream));
+            CU(cudaStreamSynchronize(d.stream));
+            const unsigned char *hs = (const unsigned char *)d.h_small;
+            uint32_t st[2];
+            memcpy(st, hs + 8, 8);
+            unsigned long long used;
+            memcpy(&used, hs + 16, 8);
+            if (st[0]) {
+                delete res;
+                return fail(ctx, -(int)st[0], "device pool overflow while aligning read %u (heap_pool_mb=%lld list_cap=%d hits_per_read=%d)",
+                            st[1], ctx->heap_pool_mb, ctx->list_cap, ctx->hits_per_read);
+            }
+            if (used > cap[g]) { cap[g] = used + used / 8 + 1024; again = true; continue; }
+            done[g] = 1;
+            res->shard_total[g] = used;
+            const unsigned long long *ctr = (const unsigned long long *)(hs + 32);
+            for (int k = 0; k < 4; k++) res->counters[k] += ctr[k];
+            for (int k = 4; k < 6; k++) if (ctr[k] > res->counters[k]) res->counters[k] = ctr[k];
+        }
+        if (!again) break;
+    }
+    for (int g = 0; g < G; g++)
+        if (!done[g]) { delete res; return fail(ctx, BWB_ERR_CAPACITY, "hit output did not fit after retries"); }
+    *out = res;
+    return BWB_OK;
+}
+
+int bwb_results_fetch(bwb_results *r) {
+    if (!r) return BWB_ERR_ARG;
+    if (r->fetched) return BWB_OK;
+    bwb_ctx *ctx = r->ctx;
+    const int G = (int)ctx->dev.size();
+    uint64_t total = 0;
+    for (int g = 0; g < G; g++) total += r->shard_total[g];
+    r->hits.resize(total);
+    uint64_t w = 0;
+    for (int g = 0; g < G; g++) {
+        Device &d = ctx->dev[g];
+        const uint64_t lo = r->shard_lo[g], n = r->shard_lo[g + 1] - lo;
+        CU(cudaSetDevice(d.id));
+        if (n) CU(cudaMemcpyAsync(r->counts.data() + lo, d.read_cnt.p, n * 4, cudaMemcpyDeviceToHost, d.stream));
+        if (r->shard_total[g])
+            CU(cudaMemcpyAsync(r->hits.data() + w, d.ordered.p, r->shard_total[g] * sizeof(bwb_hit), cudaMemcpyDeviceToHost, d.stream));
+        w += r->shard_total[g];
+    }
+    for (int g = 0; g < G; g++) {
+        CU(cudaSetDevice(ctx->dev[g].id));
+        CU(cudaStreamSynchronize(ctx->dev[g].stream));
+    }
+    r->fetched = true;
+    return BWB_OK;
+}
+
+int bwb_align_resident(bwb_ctx *ctx, const bwb_params *params, const bwb_reads *reads, int fetch, bwb_results **out) {
+    if (!ctx || !params || !reads || !out || reads->ctx != ctx) return BWB_ERR_ARG;
+    int rc = align_impl(ctx, params, reads, out);
+    if (rc) return rc;
+    if (fetch) {
+        rc = bwb_results_fetch(*out);
+        if (rc) { delete *out; *out = nullptr; }
+    }
+    return rc;
+}
+
+int bwb_align(bwb_ctx *ctx, const bwb_params *params, const uint8_t *seq, const uint64_t *offsets, uint64_t n_reads,
+              bwb_results **out) {
+    if (!ctx || !params || !seq || !offsets || !out) return BWB_ERR_ARG;
+    if (!ctx->have_index) return fail(ctx, BWB_ERR_NO_INDEX, "bwb_align before bwb_index_upload");
+    bwb_reads *R = nullptr;
+    int rc = bwb_reads_upload(ctx, seq, offsets, n_reads, &R);
+    if (rc) return rc;
+    rc = bwb_align_resident(ctx, params, R, 1, out);
+    bwb_reads_free(R);
+    return rc;
+}
+
+uint64_t bwb_results_num_reads(const bwb_results *r) { return r ? r->n_reads : 0; }
+uint64_t bwb_results_num_hits(const bwb_results *r) {
+    if (!r) return 0;
+    uint64_t t = 0;
+    for (uint64_t v : r->shard_total) t += v;
+    return t;
+}
+const uint32_t *bwb_results_counts(const bwb_results *r) { return r && r->fetched ? r->counts.data() : nullptr; }
+const bwb_hit *bwb_results_hits(const bwb_results *r) { return r && r->fetched ? r->hits.data() : nullptr; }
+int bwb_results_counters(const bwb_results *r, uint64_t out[8]) {
+    if (!r || !out) return BWB_ERR_ARG;
+    memcpy(out, r->counters, sizeof r->counters);
+    return BWB_OK;
+}
+void bwb_results_free(bwb_results *r) { delete r; }
+void bwb_free(void *p) { free(p); }
+
+}  // extern "C"
+
+// serialisation lives in aln_io.cpp; it needs the private layout of bwb_results
+namespace bwb_host {
+const std::vector<uint32_t> &results_counts(const bwb_results *r) { return r->counts; }
+const std::vector<bwb_hit> &results_hits(const bwb_results *r) { return r->hits; }
+bool results_fetched(const bwb_results *r) { return r->fetched; }
+}  // namespace bwb_host

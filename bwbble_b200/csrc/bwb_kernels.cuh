@@ -1,0 +1,848 @@
+// bwb_kernels.cuh -- the sm_100a kernels of the BWBBLE hot path (included by bwb_abi.cu).
+//
+//   K0 k_relayout        .bwt arrays -> 128-B index blocks                     (bwt.c:90-125 product)
+//   K1 k_occ / k_occ_alphabet / k_occ_bench   rank primitives, gather bench    (bwt.c:348-438)
+//   K2 k_exact           exact_match_bounded from the full range, warp / read  (exact_match.c:66-119)
+//   K3 k_calc_d          calculate_d, warp / read                              (inexact_match.c:171-254)
+//   K4 k_align           calculate_d + inexact_match, persistent warp / read   (inexact_match.c:25-168,256-610)
+//   K5 k_emit            per-read hit groups -> one array in input order       (inexact_match.c:152-164)
+//
+// No tensor cores: nothing on this path is a dense contraction (integer rank + popcount only).
+#pragma once
+#include "bwb_device.cuh"
+#include "bwbble_b200.h"
+
+namespace bwb {
+
+// ---------------------------------------------------------------------------------------------
+// K0: one thread per 128-row block
+// ---------------------------------------------------------------------------------------------
+__global__ void k_relayout(const uint32_t *__restrict__ bwt, uint64_t num_words, const uint64_t *__restrict__ O,
+                           uint64_t num_occ, uint64_t sa0_index, uint32_t *__restrict__ blocks,
+                           uint64_t num_blocks, uint32_t *__restrict__ err) {
+    const uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= num_blocks) return;
+    uint32_t plane[4][4];
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+#pragma unroll
+        for (int w = 0; w < 4; w++) plane[k][w] = 0;
+    uint32_t first = 0;
+#pragma unroll
+    for (int wi = 0; wi < 16; wi++) {
+        const uint64_t widx = b * 16 + wi;
+        const uint32_t w = widx < num_words ? bwt[widx] : 0u;
+        if (wi == 0) first = w >> 28;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const uint32_t sym = (w >> (28 - 4 * j)) & 15u;
+            const int bit = 8 * (wi & 3) + j;
+#pragma unroll
+            for (int k = 0; k < 4; k++) plane[k][wi >> 2] |= ((sym >> k) & 1u) << bit;
+        }
+    }
+    uint32_t *out = blocks + b * 32;
+    for (uint32_t c = 0; c < 16; c++) {
+        // reference checkpoint row is inclusive of row 128*b; make it exclusive.  The sentinel row
+        // holds nibble 0 but is never counted in O[.][0] (bwt.c:284-286).
+        uint64_t v = b < num_occ ? O[b * 16 + c] : 0ull;
+        if (c == first && !(c == 0 && b * 128 == sa0_index)) v -= 1;
+        if (v >> 32) atomicExch(err, 1u);
+        out[c] = (uint32_t)v;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+#pragma unroll
+        for (int w = 0; w < 4; w++) out[16 + 4 * k + w] = plane[k][w];
+}
+
+// ---------------------------------------------------------------------------------------------
+// K1: rank primitives
+// ---------------------------------------------------------------------------------------------
+__global__ void k_occ(IndexView ix, const uint8_t *__restrict__ code, const uint64_t *__restrict__ pos, uint64_t n,
+                      uint64_t *__restrict__ out) {
+    __shared__ uint64_t sC[17];
+    if (threadIdx.x < 17) sC[threadIdx.x] = ix.C[threadIdx.x];
+    __syncthreads();
+    const uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n) return;
+    out[q] = occ1(ix, sC, code[q] & 15u, pos[q]);
+}
+
+// 16 lanes per query, lane j computes occ[j]
+__global__ void k_occ_alphabet(IndexView ix, const uint64_t *__restrict__ pos, uint64_t n, uint32_t inc,
+                               uint64_t *__restrict__ out) {
+    __shared__ uint64_t sC[17];
+    if (threadIdx.x < 17) sC[threadIdx.x] = ix.C[threadIdx.x];
+    __syncthreads();
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t q = t >> 4;
+    const uint32_t j = (uint32_t)(t & 15u);
+    if (q >= n) return;
+    out[q * 16 + j] = j ? occ_alpha(ix, sC, j, pos[q], inc) : 0ull;
+}
+
+__device__ __forceinline__ uint64_t mix64(uint64_t x) {   // splitmix64 finaliser
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+
+// Occ-gather micro-benchmark: uniform random positions over the whole index.
+// mode 0: one thread = one O(c,i) query.  mode 1: 16 lanes = one O_alphabet(i) query.
+// CHAIN dependent queries per thread (next position derived from the previous result) model the
+// search's dependent gathers; CHAIN=1 is the pure throughput case.
+template <int MODE>
+__global__ void k_occ_bench(IndexView ix, uint64_t n, uint64_t seed, int chain, unsigned long long *__restrict__ sink) {
+    __shared__ uint64_t sC[17];
+    if (threadIdx.x < 17) sC[threadIdx.x] = ix.C[threadIdx.x];
+    __syncthreads();
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t q = MODE ? (t >> 4) : t;
+    if (q >= n) return;
+    uint64_t h = mix64(seed ^ (q * 0xD6E8FEB86659FD93ull));
+    uint64_t acc = 0;
+    for (int s = 0; s < chain; s++) {
+        const uint64_t pos = h % (ix.length - 1);
+        uint64_t v;
+        if (MODE) v = occ_alpha(ix, sC, (uint32_t)(t & 15u), pos, 0);
+        else v = occ1(ix, sC, 1u + (uint32_t)((h >> 58) % 15u), pos);
+        acc += v;
+        h = mix64(h ^ v);
+    }
+    if (acc == 0x123456789ABCDEFull) atomicAdd(sink, acc);      // keeps the loads alive
+    if ((t & 0xFFFFF) == 0) atomicAdd(sink, acc);
+}
+
+// ---------------------------------------------------------------------------------------------
+// shared helpers for the warp-per-read kernels
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t nt4_compl(uint32_t c) { return c > 3u ? 4u : 3u - c; }
+
+// exact_match_bounded(read, i0, L, U) (exact_match.c:66-119) on the warp's lists.
+// use_rc: read base r is the complement of seq[len-1-r] (the search runs on the reverse complement).
+// Returns list length (0 = no match, -1 = list capacity exceeded); `cur` says which list holds it.
+__device__ __forceinline__ int exact_from(const IndexView &ix, const uint64_t *sC, const ListStore &ls,
+                                          const uint8_t *seq, int len, bool use_rc, int i0, uint64_t L, uint64_t U,
+                                          int &cur, uint32_t &nloads, uint32_t &maxlist) {
+    if (lane_id() == 0) lset(ls, 0, 0, make_ulonglong2(L, U));
+    __syncwarp();
+    cur = 0;
+    int n = 1;
+    for (int r = i0; r >= 0; r--) {
+        const uint32_t c = use_rc ? nt4_compl(seq[len - 1 - r]) : (uint32_t)seq[r];
+        if (c > 3u) return 0;                        // N in the read never matches
+        uint32_t sumw;
+        n = extend_step(ix, sC, ls, cur, n, c, sumw, nloads);
+        if (n < 0) return -1;
+        cur ^= 1;
+        if ((uint32_t)n > maxlist) maxlist = (uint32_t)n;
+        if (n == 0) return 0;
+    }
+    return n;
+}
+
+// calculate_d (inexact_match.c:208-254) on seq[0..dlen): D[k] = {num_diff, sa_intv_width}.
+__device__ __forceinline__ bool calc_d(const IndexView &ix, const uint64_t *sC, const ListStore &ls,
+                                       const uint8_t *seq, int dlen, int2 *D, uint32_t &nloads, uint32_t &maxlist) {
+    const uint32_t lane = lane_id();
+    const ulonglong2 full = make_ulonglong2(0ull, ix.length - 1);
+    if (lane == 0) lset(ls, 0, 0, full);
+    __syncwarp();
+    int cur = 0, n = 1, z = 0;
+    for (int i = dlen - 1; i >= 0; i--) {
+        const uint32_t c = seq[i];
+        uint32_t num = 0;
+        int nn = 0;
+        if (c <= 3u) {
+            nn = extend_step(ix, sC, ls, cur, n, c, num, nloads);
+            if (nn < 0) return false;
+            cur ^= 1;
+            if ((uint32_t)nn > maxlist) maxlist = (uint32_t)nn;
+        }
+        if (nn == 0) {                               // restart from the full range, one more difference
+            if (lane == 0) lset(ls, cur, 0, full);
+            __syncwarp();
+            nn = 1;
+            z++;
+            num = (uint32_t)ix.length;               // (int)(U-L+1) of the outer L,U (inexact_match.c:243)
+        }
+        n = nn;
+        if (lane == 0) D[dlen - 1 - i] = make_int2(z, (int)num);
+    }
+    if (lane == 0) D[dlen] = make_int2(z + 1, 0);
+    __syncwarp();
+    return true;
+}
+
+// stage one read's bases into shared memory (codes > 4 clamp to 4 = N)
+__device__ __forceinline__ uint32_t stage_read(const uint8_t *__restrict__ g, int len, uint8_t *s) {
+    uint32_t nN = 0;
+    for (int k = lane_id(); k < len; k += 32) {
+        uint8_t c = g[k];
+        if (c > 4) c = 4;
+        s[k] = c;
+        nN += (c == 4);
+    }
+    __syncwarp();
+    return __reduce_add_sync(FULL, nN);
+}
+
+// ---------------------------------------------------------------------------------------------
+// K2 / K3: parity kernels, one warp per read
+// ---------------------------------------------------------------------------------------------
+struct ListArgs {
+    IndexView ix;
+    const uint8_t *seq;
+    const uint64_t *offsets;
+    uint32_t n_reads;
+    ulonglong2 *glists;      // [n_warps][2][list_cap]
+    int list_cap;
+    int max_len;
+    int use_len;             // K3: prefix length (0 = whole read)
+    // K2 outputs
+    ulonglong2 *out_iv;
+    unsigned long long out_cap;
+    unsigned long long *out_cursor;
+    unsigned long long *read_off;
+    uint32_t *read_cnt;
+    // K3 output
+    int32_t *out_d;
+    uint32_t *status;
+};
+
+__device__ __forceinline__ void warp_smem(unsigned char *smem, int per_warp, ListStore &ls, unsigned char *&rest) {
+    unsigned char *base = smem + (size_t)(threadIdx.x >> 5) * per_warp;
+    ls.s = reinterpret_cast<ulonglong2 *>(base);
+    rest = base + 2 * SL * sizeof(ulonglong2);
+}
+
+__global__ void k_exact(ListArgs a) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ uint64_t sC[17];
+    if (threadIdx.x < 17) sC[threadIdx.x] = a.ix.C[threadIdx.x];
+    __syncthreads();
+    const int wpb = blockDim.x >> 5;
+    const int per_warp = 2 * SL * (int)sizeof(ulonglong2) + ((a.max_len + 15) & ~15);
+    const uint32_t gw = blockIdx.x * wpb + (threadIdx.x >> 5);
+    const uint32_t nw = gridDim.x * wpb;
+    ListStore ls;
+    unsigned char *rest;
+    warp_smem(smem, per_warp, ls, rest);
+    ls.g = a.glists + (size_t)gw * 2 * a.list_cap;
+    ls.cap = a.list_cap;
+    uint8_t *sseq = rest;
+    const uint32_t lane = lane_id();
+    for (uint32_t r = gw; r < a.n_reads; r += nw) {
+        const uint64_t off = a.offsets[r];
+        const int len = (int)(a.offsets[r + 1] - off);
+        stage_read(a.seq + off, len, sseq);
+        int cur;
+        uint32_t nl = 0, ml = 0;
+        int n = exact_from(a.ix, sC, ls, sseq, len, false, len - 1, 0ull, a.ix.length - 1, cur, nl, ml);
+        if (n < 0) { if (lane == 0) atomicExch(a.status, (uint32_t)(-BWB_ERR_CAPACITY)); n = 0; }
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(a.out_cursor, (unsigned long long)n);
+        base = shfl64(base, 0);
+        if (base + n <= a.out_cap)
+            for (int k = lane; k < n; k += 32) a.out_iv[base + k] = lget(ls, cur, k);
+        if (lane == 0) { a.read_off[r] = base; a.read_cnt[r] = (uint32_t)n; }
+        __syncwarp();
+    }
+}
+
+__global__ void k_calc_d(ListArgs a) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ uint64_t sC[17];
+    if (threadIdx.x < 17) sC[threadIdx.x] = a.ix.C[threadIdx.x];
+    __syncthreads();
+    const int wpb = blockDim.x >> 5;
+    const int dbytes = ((a.max_len + 1) * 8 + 15) & ~15;
+    const int per_warp = 2 * SL * (int)sizeof(ulonglong2) + dbytes + ((a.max_len + 15) & ~15);
+    const uint32_t gw = blockIdx.x * wpb + (threadIdx.x >> 5);
+    const uint32_t nw = gridDim.x * wpb;
+    ListStore ls;
+    unsigned char *rest;
+    warp_smem(smem, per_warp, ls, rest);
+    ls.g = a.glists + (size_t)gw * 2 * a.list_cap;
+    ls.cap = a.list_cap;
+    int2 *D = reinterpret_cast<int2 *>(rest);
+    uint8_t *sseq = rest + dbytes;
+    const uint32_t lane = lane_id();
+    for (uint32_t r = gw; r < a.n_reads; r += nw) {
+        const uint64_t off = a.offsets[r];
+        const int len = (int)(a.offsets[r + 1] - off);
+        const int dlen = (a.use_len > 0 && a.use_len < len) ? a.use_len : len;
+        stage_read(a.seq + off, len, sseq);
+        uint32_t nl = 0, ml = 0;
+        if (!calc_d(a.ix, sC, ls, sseq, dlen, D, nl, ml)) {
+            if (lane == 0) atomicExch(a.status, (uint32_t)(-BWB_ERR_CAPACITY));
+            continue;
+        }
+        int32_t *o = a.out_d + 2 * (off + r);
+        for (int k = lane; k <= dlen; k += 32) { o[2 * k] = D[k].x; o[2 * k + 1] = D[k].y; }
+        __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K4: calculate_d + inexact_match, persistent warp per read
+// ---------------------------------------------------------------------------------------------
+// Partial alignment (aln_entry_t, align.h:100-119) packed into 32 bytes.  The 256-byte edit path of
+// the reference is all STATE_M except for <= max_gapo runs of I/D, so only the runs are kept;
+// aln_length = readLen - i + (#D steps).  num_snps is never read by a decision nor serialised.
+//   a.x  L[31:0]            a.y  U[31:0]
+//   a.z  L[39:32] | U[39:32]<<8 | i<<16 | state<<24 | nruns<<26
+//   a.w  mm | go<<8 | ge<<16 | nD<<24
+//   b.x..b.w  gap runs: start | len<<8 | state<<16
+constexpr int CHUNK_ENTRIES = 32;                 // 32 entries x 32 B = 1 KB per chunk
+constexpr uint32_t NO_CHUNK = 0xffffffffu;
+
+struct AlignArgs {
+    IndexView ix;
+    const uint8_t *seq;
+    const uint64_t *offsets;
+    uint32_t n_reads;
+    uint32_t read_id_base;
+    // aln_params_t
+    int max_diff, max_gapo, max_gape, max_entries, mm_score, gapo_score, gape_score;
+    int seed_len, max_diff_seed, max_best, no_indel_len;
+    int nb;                   // number of score buckets, heap_init (inexact_match.c:513)
+    int max_len;
+    uint32_t *queue;          // next read to take
+    // per-warp scratch
+    ulonglong2 *glists;
+    int list_cap;
+    uint4 *chunks;            // [n_chunks][2*CHUNK_ENTRIES]
+    uint32_t *chunk_link;     // [n_chunks]
+    uint32_t chunks_per_warp;
+    uint32_t n_chunks;
+    uint32_t *overflow_cursor;   // starts at n_warps*chunks_per_warp
+    bwb_hit *stage;
+    int hits_cap;
+    // outputs (unordered groups; K5 orders them)
+    bwb_hit *out_hits;
+    unsigned long long out_cap;
+    unsigned long long *out_cursor;
+    unsigned long long *read_off;
+    uint32_t *read_cnt;
+    uint32_t *status;            // [0] error code, [1] read id
+    unsigned long long *counters;   // [0] pops [1] pushes [2] exact tails [3] rank queries [4] max heap [5] max list
+    // shared-memory layout (bytes per warp)
+    int smem_per_warp, off_D, off_Ds, off_bk, off_seq;
+};
+
+struct Entry {
+    uint64_t L, U;
+    uint32_t i, state, nruns, mm, go, ge, nD;
+    uint32_t run[BWB_MAX_GAP_RUNS];
+};
+
+__device__ __forceinline__ void pack_entry(const Entry &e, uint4 &a, uint4 &b) {
+    a.x = (uint32_t)e.L;
+    a.y = (uint32_t)e.U;
+    a.z = (uint32_t)(e.L >> 32) | ((uint32_t)(e.U >> 32) << 8) | (e.i << 16) | (e.state << 24) | (e.nruns << 26);
+    a.w = e.mm | (e.go << 8) | (e.ge << 16) | (e.nD << 24);
+    b.x = e.run[0]; b.y = e.run[1]; b.z = e.run[2]; b.w = e.run[3];
+}
+__device__ __forceinline__ void unpack_entry(const uint4 &a, const uint4 &b, Entry &e) {
+    e.L = (uint64_t)a.x | ((uint64_t)(a.z & 0xffu) << 32);
+    e.U = (uint64_t)a.y | ((uint64_t)((a.z >> 8) & 0xffu) << 32);
+    e.i = (a.z >> 16) & 0xffu;
+    e.state = (a.z >> 24) & 3u;
+    e.nruns = (a.z >> 26) & 7u;
+    e.mm = a.w & 0xffu; e.go = (a.w >> 8) & 0xffu; e.ge = (a.w >> 16) & 0xffu; e.nD = (a.w >> 24) & 0xffu;
+    e.run[0] = b.x; e.run[1] = b.y; e.run[2] = b.z; e.run[3] = b.w;
+}
+
+// per-warp bucket heap (priority_heap_t, inexact_match.h:16-34): bucket = LIFO stack of chunks
+struct Heap {
+    uint32_t *cnt, *top, *bot;    // shared memory, nb each
+    uint4 *chunks;
+    uint32_t *link;
+    uint32_t priv_lo, priv_hi;    // this warp's private chunk range
+    uint32_t bump;                // next never-used private chunk
+    uint32_t free_head;           // recycled chunks (linked through `link`)
+    uint32_t *overflow_cursor;
+    uint32_t n_chunks;
+    int nb;
+    int n;                        // entries in all buckets
+    int best;                     // lowest non-empty bucket (nb if none)
+};
+
+// all lanes call; returns the same chunk id on every lane (NO_CHUNK when the pool is exhausted)
+__device__ __forceinline__ uint32_t chunk_alloc(Heap &h) {
+    uint32_t id = NO_CHUNK;
+    if (lane_id() == 0) {
+        if (h.free_head != NO_CHUNK) {
+            id = h.free_head;
+        } else if (h.bump < h.priv_hi) {
+            id = h.bump;
+        } else {
+            const uint32_t o = atomicAdd(h.overflow_cursor, 1u);
+            id = o < h.n_chunks ? o : NO_CHUNK;
+        }
+    }
+    id = __shfl_sync(FULL, id, 0);
+    if (id != NO_CHUNK) {
+        if (h.free_head != NO_CHUNK) {           // uniform: every lane tracks the allocator state
+            uint32_t nx = 0;
+            if (lane_id() == 0) nx = h.link[id];
+            h.free_head = __shfl_sync(FULL, nx, 0);
+        } else if (h.bump < h.priv_hi) {
+            h.bump++;
+        }
+    }
+    return id;
+}
+
+__device__ __forceinline__ void heap_reset(Heap &h) {
+    for (int b = lane_id(); b < h.nb; b += 32) { h.cnt[b] = 0; h.top[b] = NO_CHUNK; h.bot[b] = NO_CHUNK; }
+    h.n = 0;
+    h.best = h.nb;
+    __syncwarp();
+}
+
+// give every chunk still held by a bucket back to the warp's free list (O(1) per bucket)
+__device__ __forceinline__ void heap_release(Heap &h) {
+    __syncwarp();
+    if (lane_id() == 0) {
+        uint32_t fh = h.free_head;
+        for (int b = 0; b < h.nb; b++) {
+            if (h.cnt[b]) {
+                h.link[h.bot[b]] = fh;
+                fh = h.top[b];
+            }
+        }
+        h.free_head = fh;
+    }
+    h.free_head = __shfl_sync(FULL, h.free_head, 0);
+    __syncwarp();
+}
+
+// Push the entries of the lanes in `grp` (same score `sc` on all of them) in lane order
+// (heap_push, inexact_match.c:548-591).  Returns false if no chunk could be allocated.
+__device__ __forceinline__ bool heap_push_group(Heap &h, uint32_t grp, int sc, const Entry &e) {
+    const uint32_t lane = lane_id();
+    const int k = __popc(grp);
+    const uint32_t cnt = h.cnt[sc];
+    const uint32_t oldtop = h.top[sc];
+    const bool need_new = (cnt == 0) || (((cnt + k - 1) / CHUNK_ENTRIES) > ((cnt - 1) / CHUNK_ENTRIES));
+    uint32_t newc = NO_CHUNK;
+    if (need_new) {
+        newc = chunk_alloc(h);
+        if (newc == NO_CHUNK) return false;
+        if (lane == 0) {
+            h.link[newc] = oldtop;
+            h.top[sc] = newc;
+            if (cnt == 0) h.bot[sc] = newc;
+        }
+    }
+    if ((grp >> lane) & 1u) {
+        const uint32_t pos = cnt + __popc(grp & ((1u << lane) - 1u));
+        const bool in_old = (cnt != 0) && ((pos / CHUNK_ENTRIES) == ((cnt - 1) / CHUNK_ENTRIES));
+        const uint32_t ch = in_old ? oldtop : newc;
+        uint4 a, b;
+        pack_entry(e, a, b);
+        uint4 *dst = h.chunks + ((size_t)ch * CHUNK_ENTRIES + (pos % CHUNK_ENTRIES)) * 2;
+        dst[0] = a;
+        dst[1] = b;
+    }
+    if (lane == 0) h.cnt[sc] = cnt + k;
+    h.n += k;
+    if (sc < h.best) h.best = sc;
+    __syncwarp();
+    return true;
+}
+
+// heap_pop (inexact_match.c:594-610): last entry of the lowest non-empty bucket; every lane gets it
+__device__ __forceinline__ int heap_pop(Heap &h, Entry &e) {
+    const uint32_t lane = lane_id();
+    const int b = h.best;
+    const uint32_t cnt = h.cnt[b];
+    const uint32_t ch = h.top[b];
+    const uint32_t slot = (cnt - 1) % CHUNK_ENTRIES;
+    const uint4 *src = h.chunks + ((size_t)ch * CHUNK_ENTRIES + slot) * 2;
+    const uint4 a = src[0], bb = src[1];
+    unpack_entry(a, bb, e);
+    __syncwarp();
+    h.n--;
+    if (slot == 0) {                                  // chunk is empty now: recycle it
+        uint32_t prev = 0;
+        if (lane == 0) {
+            prev = h.link[ch];
+            h.link[ch] = h.free_head;
+            h.top[b] = prev;
+            if (cnt == 1) h.bot[b] = NO_CHUNK;
+        }
+        h.free_head = ch;
+    }
+    if (lane == 0) h.cnt[b] = cnt - 1;
+    __syncwarp();
+    if (cnt == 1) {                                   // bucket drained: find the next non-empty one
+        int nbst = h.nb;
+        if (h.n) {
+            for (int s = b + 1; s < h.nb; s += 32) {
+                const int q = s + (int)lane;
+                const uint32_t m = __ballot_sync(FULL, q < h.nb && h.cnt[q] != 0);
+                if (m) { nbst = s + __ffs(m) - 1; break; }
+            }
+        }
+        h.best = nbst;
+    }
+    return b;
+}
+
+static_assert(sizeof(bwb_hit) == 48, "bwb_hit must be 3 x 16 bytes");
+
+struct HitSink {
+    bwb_hit *stage;
+    int cap;
+    int n;
+};
+
+// add_alignment (align.c:271-298) for `cnt` intervals held one per lane (lane k < cnt valid), in lane
+// order.  With gaps, an interval equal to an already recorded hit is dropped (align.c:273-280).
+__device__ __forceinline__ bool add_hits(HitSink &hs, const Entry &e, int score, uint32_t alen, uint32_t read_id,
+                                         bool have, uint64_t L, uint64_t U) {
+    const uint32_t lane = lane_id();
+    bool keep = have;
+    if (e.go) {
+        for (int j = 0; j < hs.n; j++) {
+            const uint64_t hl = hs.stage[j].L, hu = hs.stage[j].U;
+            if (hl == L && hu == U) keep = false;
+        }
+    }
+    const uint32_t K = __ballot_sync(FULL, keep);
+    const int nk = __popc(K);
+    if (hs.n + nk > hs.cap) return false;
+    if (keep) {
+        bwb_hit h;
+        h.L = L; h.U = U; h.score = score;
+        h.num_mm = (uint8_t)e.mm; h.num_gapo = (uint8_t)e.go; h.num_gape = (uint8_t)e.ge;
+        h.aln_length = (uint8_t)alen;
+        h.n_runs = (uint8_t)e.nruns; h.pad[0] = h.pad[1] = h.pad[2] = 0;
+#pragma unroll
+        for (int r = 0; r < BWB_MAX_GAP_RUNS; r++) {
+            const uint32_t v = (uint32_t)r < e.nruns ? e.run[r] : 0u;
+            h.runs[r].start = (uint8_t)(v & 0xffu);
+            h.runs[r].len = (uint8_t)((v >> 8) & 0xffu);
+            h.runs[r].state = (uint8_t)((v >> 16) & 0xffu);
+            h.runs[r].pad = 0;
+        }
+        h.read_id = read_id;
+        hs.stage[hs.n + __popc(K & ((1u << lane) - 1u))] = h;
+    }
+    hs.n += nk;
+    __syncwarp();
+    return true;
+}
+
+__global__ void __launch_bounds__(256) k_align(const __grid_constant__ AlignArgs a) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ uint64_t sC[17];
+    if (threadIdx.x < 17) sC[threadIdx.x] = a.ix.C[threadIdx.x];
+    __syncthreads();
+
+    const uint32_t lane = lane_id();
+    const int wpb = blockDim.x >> 5;
+    const uint32_t gw = blockIdx.x * wpb + (threadIdx.x >> 5);
+    unsigned char *wbase = smem + (size_t)(threadIdx.x >> 5) * a.smem_per_warp;
+
+    ListStore ls;
+    ls.s = reinterpret_cast<ulonglong2 *>(wbase);
+    ls.g = a.glists + (size_t)gw * 2 * a.list_cap;
+    ls.cap = a.list_cap;
+    int2 *D = reinterpret_cast<int2 *>(wbase + a.off_D);
+    int2 *Ds = reinterpret_cast<int2 *>(wbase + a.off_Ds);
+    uint8_t *sseq = wbase + a.off_seq;
+
+    Heap h;
+    h.cnt = reinterpret_cast<uint32_t *>(wbase + a.off_bk);
+    h.top = h.cnt + a.nb;
+    h.bot = h.top + a.nb;
+    h.chunks = a.chunks;
+    h.link = a.chunk_link;
+    h.priv_lo = gw * a.chunks_per_warp;
+    h.priv_hi = h.priv_lo + a.chunks_per_warp;
+    h.bump = h.priv_lo;
+    h.free_head = NO_CHUNK;
+    h.overflow_cursor = a.overflow_cursor;
+    h.n_chunks = a.n_chunks;
+    h.nb = a.nb;
+
+    HitSink hs;
+    hs.stage = a.stage + (size_t)gw * a.hits_cap;
+    hs.cap = a.hits_cap;
+
+    // lane roles in an expansion: lanes 0..15 = rank side L-1 / indel children, 16..31 = side U /
+    // match+mismatch children, symbol j = lane & 15
+    const uint32_t j = lane & 15u;
+    const uint32_t hi = lane >> 4;
+    // grayVal (io.h:29): base bitmask of code j
+    const uint32_t gray_j = (0x89BAEFDC45762310ull >> (4u * j)) & 15u;
+
+    uint64_t c_pops = 0, c_push = 0, c_tails = 0, c_rank = 0;
+    uint32_t c_maxheap = 0, c_maxlist = 0;
+
+    for (;;) {
+        uint32_t r = 0;
+        if (lane == 0) r = atomicAdd(a.queue, 1u);
+        r = __shfl_sync(FULL, r, 0);
+        if (r >= a.n_reads) break;
+        const uint64_t off = a.offsets[r];
+        const int len = (int)(a.offsets[r + 1] - off);
+        const uint32_t read_id = a.read_id_base + r;
+        const uint32_t nN = stage_read(a.seq + off, len, sseq);
+        hs.n = 0;
+        int err = 0;
+        uint32_t nloads = 0;
+
+        // lower bounds (inexact_match.c:61-64 / 140-143)
+        if (!calc_d(a.ix, sC, ls, sseq, len, D, nloads, c_maxlist)) err = BWB_ERR_CAPACITY;
+        if (!err && a.seed_len > 0) {
+            if (len > a.seed_len) {
+                if (!calc_d(a.ix, sC, ls, sseq, a.seed_len, Ds, nloads, c_maxlist)) err = BWB_ERR_CAPACITY;
+            } else {
+                // Q6: the reference consults a stale per-thread D_seed here; the defined behaviour
+                // of this implementation is the freshly calloc'ed one (all zero).
+                for (int k = lane; k <= a.seed_len; k += 32) Ds[k] = make_int2(0, 0);
+                __syncwarp();
+            }
+        }
+
+        if (!err && (int)nN <= a.max_diff) {
+            heap_reset(h);
+            {   // root: i = len, whole range, empty path (inexact_match.c:281)
+                Entry root;
+                root.L = 0; root.U = a.ix.length - 1; root.i = (uint32_t)len; root.state = 0; root.nruns = 0;
+                root.mm = root.go = root.ge = root.nD = 0;
+                root.run[0] = root.run[1] = root.run[2] = root.run[3] = 0;
+                if (!heap_push_group(h, 1u, 0, root)) err = BWB_ERR_CAPACITY;
+                c_push++;
+            }
+            int best_score = a.nb;            // aln_score(max_diff+1, max_gapo+1, max_gape+1)
+            int max_diff = a.max_diff;
+            int num_best = 0;
+
+            while (!err && h.n != 0) {
+                if ((uint32_t)h.n > c_maxheap) c_maxheap = (uint32_t)h.n;
+                if (h.n > a.max_entries) break;
+                Entry e;
+                const int bucket = heap_pop(h, e);
+                c_pops++;
+                const int escore = bucket & 0xff;                       // 8-bit field (Q4)
+                if (escore > best_score + a.mm_score) break;
+                const int used = (int)(e.mm + e.go + e.ge);
+                const int dl = max_diff - used;
+                if (dl < 0) continue;
+                const int ei = (int)e.i;
+                if (ei > 0 && dl < D[ei - 1].x) continue;
+                const int dls = a.max_diff_seed - used;
+                const int si = ei - (len - a.seed_len);
+                if (si > 0 && dls < Ds[si - 1].x) continue;
+                const uint32_t alen = ((uint32_t)(len - ei) + e.nD) & 0xffu;
+
+                if (ei == 0) {                                          // a hit (inexact_match.c:331-344)
+                    const int sc = (int)e.mm * a.mm_score + (int)e.go * a.gapo_score + (int)e.ge * a.gape_score;
+                    if (hs.n == 0) {
+                        best_score = sc;
+                        max_diff = (used + 1 > a.max_diff) ? a.max_diff : used + 1;
+                    }
+                    if (sc == best_score) num_best = (int)((uint32_t)num_best + (uint32_t)(e.U - e.L + 1));
+                    else if (num_best > a.max_best) break;
+                    if (!add_hits(hs, e, sc, alen, read_id, lane == 0, e.L, e.U)) err = BWB_ERR_CAPACITY;
+                    continue;
+                }
+                if (dl == 0) {                                          // exact tail (inexact_match.c:345-375)
+                    c_tails++;
+                    int cur;
+                    const int n = exact_from(a.ix, sC, ls, sseq, len, true, ei - 1, e.L, e.U, cur, nloads, c_maxlist);
+                    if (n < 0) { err = BWB_ERR_CAPACITY; break; }
+                    if (n > 0) {
+                        const int sc = (int)e.mm * a.mm_score + (int)e.go * a.gapo_score + (int)e.ge * a.gape_score;
+                        if (hs.n == 0) {
+                            best_score = sc;
+                            max_diff = (used + 1 > a.max_diff) ? a.max_diff : used + 1;
+                        }
+                        if (sc == best_score) {
+                            uint32_t w = 0;
+                            for (int k = lane; k < n; k += 32) {
+                                const ulonglong2 iv = lget(ls, cur, k);
+                                w += (uint32_t)(iv.y - iv.x + 1);
+                            }
+                            num_best = (int)((uint32_t)num_best + __reduce_add_sync(FULL, w));
+                        } else if (num_best > a.max_best) break;
+                        const uint32_t alen2 = (alen + (uint32_t)ei) & 0xffu;   // rest of the path is M
+                        for (int base = 0; base < n && !err; base += 32) {
+                            const int k = base + (int)lane;
+                            const bool have = k < n;
+                            const ulonglong2 iv = have ? lget(ls, cur, k) : make_ulonglong2(0, 0);
+                            if (!add_hits(hs, e, sc, alen2, read_id, have, iv.x, iv.y)) err = BWB_ERR_CAPACITY;
+                        }
+                    }
+                    continue;
+                }
+
+                // ---- expansion: the two 16-code rank gathers (inexact_match.c:377-383) ----
+                const uint64_t pos = hi ? e.U : (e.L - 1);
+                const uint64_t mine = occ_alpha(a.ix, sC, j, pos, hi ? 0u : 1u);
+                const uint64_t other = shfl64_xor(mine, 16);
+                const uint64_t Lj = hi ? other : mine;
+                const uint64_t Uj = hi ? mine : other;
+                const bool ok = (j != 0u) && (Lj <= Uj);
+                nloads += (lane == 0 || lane == 16) ? 1u : 0u;
+
+                // BWA heuristics (inexact_match.c:391-430)
+                bool allow_diff = true, allow_indels = true, allow_mm = true, allow_open = true, allow_ext = true;
+                const int i1 = ei - 1;
+                if (i1 > 0) {
+                    const int2 d1 = D[i1], d0 = D[i1 - 1];
+                    if (dl - 1 < d0.x) allow_diff = false;
+                    else if (d1.x == dl - 1 && d0.x == dl - 1 && d1.y == d0.y) allow_mm = false;
+                }
+                if (si - 1 > 0) {
+                    const int2 s1 = Ds[si - 1], s0 = Ds[si - 2];
+                    if (dls - 1 < s0.x) allow_diff = false;
+                    else if (s1.x == dls - 1 && s0.x == dls - 1 && s1.y == s0.y) allow_mm = false;
+                }
+                const int gaps = (int)(e.go + e.ge);
+                if (i1 < a.no_indel_len + gaps || len - i1 < a.no_indel_len + gaps) allow_indels = false;
+                if ((int)e.go >= a.max_gapo && (int)e.ge >= a.max_gape) allow_indels = false;
+                if ((int)e.go >= a.max_gapo) allow_open = false;
+                if ((int)e.ge >= a.max_gape) allow_ext = false;
+
+                // ---- children, one per lane, lane order = reference push order (:433-504) ----
+                const uint32_t c = nt4_compl(sseq[len - 1 - i1]);        // rc[i-1]
+                const uint32_t cmask = c == 0 ? 8u : (c == 1 ? 2u : (c == 2 ? 4u : (c == 3 ? 1u : 15u)));
+                Entry ch = e;
+                bool valid = false;
+                if (hi == 0) {
+                    const bool indel_ok = allow_diff && allow_indels;
+                    const bool opening = (e.state == 0);
+                    if (j == 0) {                                        // insertion: consume a read base
+                        valid = indel_ok && ((e.state == 1 && allow_ext) || (e.state == 0 && allow_open));
+                        ch.i = e.i - 1; ch.state = 1;
+                    } else {                                             // deletion of code j
+                        valid = indel_ok && ok && ((e.state == 0 && allow_open) || (e.state == 2 && allow_ext));
+                        ch.L = Lj; ch.U = Uj; ch.state = 2; ch.nD = e.nD + 1;
+                    }
+                    if (opening) {
+                        ch.go = e.go + 1;
+                        const uint32_t nr = alen | (1u << 8) | (ch.state << 16);
+                        if (e.nruns == 0) ch.run[0] = nr;
+                        else if (e.nruns == 1) ch.run[1] = nr;
+                        else if (e.nruns == 2) ch.run[2] = nr;
+                        else ch.run[3] = nr;
+                        ch.nruns = e.nruns + 1;
+                    } else {
+                        ch.ge = e.ge + 1;
+                        if (e.nruns == 1) ch.run[0] += 1u << 8;
+                        else if (e.nruns == 2) ch.run[1] += 1u << 8;
+                        else if (e.nruns == 3) ch.run[2] += 1u << 8;
+                        else if (e.nruns == 4) ch.run[3] += 1u << 8;
+                    }
+                } else {
+                    const bool is_mm = (c > 3u) || (j == 10u) || ((cmask & gray_j) == 0u);
+                    const bool full = allow_diff && allow_mm;
+                    valid = ok && (full || !is_mm);
+                    ch.L = Lj; ch.U = Uj; ch.i = e.i - 1; ch.state = 0;
+                    ch.mm = e.mm + (is_mm ? 1u : 0u);
+                }
+                const int csc = (int)ch.mm * a.mm_score + (int)ch.go * a.gapo_score + (int)ch.ge * a.gape_score;
+
+                uint32_t pending = __ballot_sync(FULL, valid);
+                c_push += __popc(pending);
+                while (pending) {
+                    const int leader = __ffs(pending) - 1;
+                    const int sc = __shfl_sync(FULL, csc, leader);
+                    const uint32_t grp = __ballot_sync(FULL, valid && csc == sc) & pending;
+                    if (!heap_push_group(h, grp, sc, ch)) { err = BWB_ERR_CAPACITY; break; }
+                    pending &= ~grp;
+                }
+            }
+            heap_release(h);
+        }
+
+        // ---- hand the read's hit group over (unordered; K5 restores input order) ----
+        if (err) {
+            if (lane == 0 && atomicCAS(a.status, 0u, (uint32_t)(-err)) == 0u) a.status[1] = read_id;
+            hs.n = 0;
+        }
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(a.out_cursor, (unsigned long long)hs.n);
+        base = shfl64(base, 0);
+        if (base + hs.n <= a.out_cap) {
+            const uint4 *src = reinterpret_cast<const uint4 *>(hs.stage);
+            uint4 *dst = reinterpret_cast<uint4 *>(a.out_hits + base);
+            for (int k = lane; k < hs.n * 3; k += 32) dst[k] = src[k];
+        }
+        if (lane == 0) { a.read_off[r] = base; a.read_cnt[r] = (uint32_t)hs.n; }
+        c_rank += __reduce_add_sync(FULL, nloads);
+        __syncwarp();
+    }
+
+    if (lane == 0) {
+        atomicAdd(a.counters + 0, (unsigned long long)c_pops);
+        atomicAdd(a.counters + 1, (unsigned long long)c_push);
+        atomicAdd(a.counters + 2, (unsigned long long)c_tails);
+        atomicAdd(a.counters + 3, (unsigned long long)c_rank);
+        atomicMax(a.counters + 4, (unsigned long long)c_maxheap);
+        atomicMax(a.counters + 5, (unsigned long long)c_maxlist);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K5: ordered emit.  ordered_off = exclusive scan of read_cnt, then a gather in input order.
+// ---------------------------------------------------------------------------------------------
+// single-block exclusive scan (n is a few million at most; <1 ms), out has n+1 entries
+__global__ void __launch_bounds__(1024) k_scan_counts(const uint32_t *__restrict__ cnt, uint32_t n,
+                                                      unsigned long long *__restrict__ out) {
+    __shared__ unsigned long long warp_tot[32];
+    __shared__ unsigned long long carry_s;
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
+    if (tid == 0) carry_s = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < n; base += 4096) {
+        const uint32_t i0 = base + tid * 4;
+        uint32_t v[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) v[k] = (i0 + k < n) ? cnt[i0 + k] : 0u;
+        unsigned long long mine = (unsigned long long)v[0] + v[1] + v[2] + v[3];
+        unsigned long long inc = mine;                                   // inclusive warp scan
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long t = shfl64(inc, (int)lane - o >= 0 ? (int)lane - o : 0);
+            if ((int)lane - o >= 0) inc += t;
+        }
+        if (lane == 31) warp_tot[wid] = inc;
+        __syncthreads();
+        unsigned long long wbase = 0;
+        for (uint32_t w = 0; w < wid; w++) wbase += warp_tot[w];
+        const unsigned long long carry = carry_s;
+        unsigned long long run = carry + wbase + inc - mine;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            if (i0 + k < n) out[i0 + k] = run;
+            run += v[k];
+        }
+        __syncthreads();
+        if (tid == 1023) carry_s = carry + wbase + inc;
+        __syncthreads();
+    }
+    if (tid == 0) out[n] = carry_s;
+}
+
+__global__ void k_emit(const bwb_hit *__restrict__ unordered, const unsigned long long *__restrict__ read_off,
+                       const uint32_t *__restrict__ read_cnt, const unsigned long long *__restrict__ ordered_off,
+                       uint32_t n_reads, bwb_hit *__restrict__ ordered) {
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_reads) return;
+    const uint32_t n = read_cnt[r];
+    const uint4 *src = reinterpret_cast<const uint4 *>(unordered + read_off[r]);
+    uint4 *dst = reinterpret_cast<uint4 *>(ordered + ordered_off[r]);
+    for (uint32_t k = 0; k < n * 3; k++) dst[k] = src[k];
+}
+
+}  // namespace bwb

@@ -1,0 +1,22 @@
+// host_common.h -- host-side containers shared by the index builder, the .bwt reader and the ABI.
+#pragma once
+#include <cstdint>
+#include <vector>
+
+namespace bwb_host {
+
+// In-memory image of a .bwt file (store_bwt layout, mg-aligner/bwt.c:66-82; fields of bwt_t,
+// bwt.h:19-40).
+struct HostIndex {
+    uint64_t length = 0, num_words = 0, num_sa = 0, num_occ = 0, sa0_index = 0;
+    uint64_t C[17] = {0};
+    std::vector<uint32_t> bwt;
+    std::vector<uint64_t> O;
+    std::vector<uint64_t> SA;
+};
+
+int build_index_arrays(const uint8_t *text, uint64_t n, HostIndex &ix);
+int write_bwt_file(const HostIndex &ix, const char *path);
+int read_bwt_file(const char *path, HostIndex &ix, bool load_sa);
+
+}  // namespace bwb_host

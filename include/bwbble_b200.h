@@ -1,0 +1,178 @@
+/* bwbble_b200.h -- C ABI of the B200-native BWBBLE read-mapping hot path.
+ *
+ * Drop-in boundary: the reference's only callers of the hot path are
+ *     align_reads()            mg-aligner/align.c:72-76
+ * which calls
+ *     int align_reads_inexact         (bwt_t*, reads_t*, sa_intv_list_t*, aln_params_t*, char*)
+ *     int align_reads_inexact_parallel(bwt_t*, reads_t*, sa_intv_list_t*, aln_params_t*, char*)
+ *                              mg-aligner/inexact_match.h:39-40, inexact_match.c:25-168
+ * bwbble_b200/csrc/shim/bwbble_shim.c defines those two symbols on top of this ABI, so the
+ * reference's own main.o/align.o/bwt.o/io.o link against it unchanged.
+ *
+ * Plain pointers and sizes only; no torch/CUDA types.  Every function returns 0 on success or a
+ * negative bwb_status; the text of the last failure is bwb_last_error().  Nothing here calls
+ * exit(), and nothing falls back to the CPU: without a usable CUDA device bwb_create() fails.
+ */
+#ifndef BWBBLE_B200_H
+#define BWBBLE_B200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BWB_ABI_VERSION 1
+
+typedef enum {
+    BWB_OK = 0,
+    BWB_ERR_ARG = -1,          /* bad argument / unsupported parameter combination */
+    BWB_ERR_CUDA = -2,         /* CUDA runtime failure (no device, OOM, launch error) */
+    BWB_ERR_IO = -3,           /* file could not be read / written */
+    BWB_ERR_NO_INDEX = -4,     /* bwb_align before bwb_index_upload */
+    BWB_ERR_CAPACITY = -5,     /* a device pool (heap chunks, interval lists, hits) overflowed */
+    BWB_ERR_UNSUPPORTED = -6   /* feature of the reference not built yet (-P, -S on device) */
+} bwb_status;
+
+/* Mirror of aln_params_t (mg-aligner/align.h:48-79): the same 15 ints in the same order, so a
+ * reference aln_params_t* can be passed as a bwb_params*. */
+typedef struct {
+    int32_t max_diff;         /* -n */
+    int32_t max_gapo;         /* -o */
+    int32_t max_gape;         /* -e */
+    int32_t max_entries;      /* -m */
+    int32_t mm_score;         /* -M */
+    int32_t gapo_score;       /* -O */
+    int32_t gape_score;       /* -E */
+    int32_t seed_length;      /* -l */
+    int32_t max_diff_seed;    /* -k */
+    int32_t max_best;
+    int32_t no_indel_length;
+    int32_t matched_Ncontig;  /* unused by the reference's hot path */
+    int32_t use_precalc;      /* -P: BWB_ERR_UNSUPPORTED */
+    int32_t is_multiref;      /* 0 = -S: BWB_ERR_UNSUPPORTED on device */
+    int32_t n_threads;        /* -t: ignored by the device path */
+} bwb_params;
+
+/* set_default_aln_params, align.c:22-38 */
+void bwb_default_params(bwb_params *p);
+
+/* One gap run of an alignment path.  A path (aln_entry_t.aln_path, align.h:118) is all STATE_M
+ * except for at most num_gapo runs of STATE_I(1)/STATE_D(2); `start` is the index of the run's
+ * first element in search order (path[0] = first step = last read base). */
+typedef struct {
+    uint8_t start, len, state, pad;
+} bwb_gap_run;
+
+#define BWB_MAX_GAP_RUNS 4     /* max_gapo above this is BWB_ERR_UNSUPPORTED */
+
+/* One alignment hit = one aln_t (align.h:81-91) without num_snps (never serialised). */
+typedef struct {
+    uint64_t L, U;             /* SA interval */
+    int32_t score;
+    uint8_t num_mm, num_gapo, num_gape, aln_length;
+    uint8_t n_runs, pad[3];
+    uint32_t read_id;          /* index of the read inside the bwb_align call */
+    bwb_gap_run runs[BWB_MAX_GAP_RUNS];
+} bwb_hit;                     /* 48 bytes */
+
+typedef struct bwb_ctx bwb_ctx;
+typedef struct bwb_results bwb_results;
+typedef struct bwb_reads bwb_reads;
+
+/* ---- context ------------------------------------------------------------------------ */
+/* devices==NULL / ndev<=0: CUDA device 0 only.  Reads of one bwb_align call are sharded over the
+ * context's devices in contiguous ranges (the reference's static OpenMP chunks,
+ * inexact_match.c:115-116); the index is replicated.  Returns NULL on failure
+ * (bwb_last_error(NULL) has the reason). */
+bwb_ctx *bwb_create(const int *devices, int ndev);
+void bwb_destroy(bwb_ctx *ctx);
+const char *bwb_last_error(const bwb_ctx *ctx);
+int bwb_device_count(const bwb_ctx *ctx);
+
+/* Options (before bwb_index_upload / first bwb_align):
+ *   "heap_pool_mb"     device bytes for the bucket-heap chunk pool, per device (default 8192)
+ *   "list_cap"         max SA intervals per list per read-slot (default 8192)
+ *   "hits_per_read"    staging capacity for hits of one read (default 4096)
+ *   "warps_per_block"  search kernel block shape (default 8)
+ *   "blocks_per_sm"    persistent blocks per SM (default: occupancy query)                      */
+int bwb_set_option(bwb_ctx *ctx, const char *key, long long value);
+/* Launch on a caller-owned cudaStream_t (e.g. torch's current stream) instead of the context's own. */
+int bwb_set_stream(bwb_ctx *ctx, int dev_slot, void *cuda_stream);
+
+/* ---- index (replaces load_bwt's in-memory result, bwt.c:90-125, bwt.h:19-40) ---------- */
+/* bwt: 8 symbols per word, first symbol in the top nibble; O: num_occ rows of 16 inclusive counts.
+ * Re-laid-out on the device into 128-byte blocks (K0).  Host arrays are not referenced afterwards. */
+int bwb_index_upload(bwb_ctx *ctx, uint64_t length, uint64_t sa0_index, const uint64_t C[17],
+                     const uint32_t *bwt, uint64_t num_words, const uint64_t *O, uint64_t num_occ);
+/* Read "<path>" in store_bwt's layout (bwt.c:66-82) and upload it. */
+int bwb_index_load_file(bwb_ctx *ctx, const char *bwt_path);
+/* Download the device blocks of device slot 0 (tests): out must hold bwb_index_num_blocks()*128 bytes. */
+uint64_t bwb_index_num_blocks(const bwb_ctx *ctx);
+int bwb_index_download_blocks(bwb_ctx *ctx, void *out);
+
+/* ---- rank primitives (K1; parity tests + the Occ-gather micro-benchmark) -------------- */
+/* out[q] = O(code[q], pos[q])  (bwt.c:348-372), code in 1..15 */
+int bwb_occ(bwb_ctx *ctx, const uint8_t *code, const uint64_t *pos, uint64_t n, uint64_t *out);
+/* out[q*16+j] = occ[j] of O_alphabet(pos[q], inc) with occ pre-zeroed (bwt.c:374-438), j=1..15 */
+int bwb_occ_alphabet(bwb_ctx *ctx, const uint64_t *pos, uint64_t n, int inc, uint64_t *out);
+/* n uniform random rank queries (device-generated positions, whole index), `iters` timed launches.
+ * mode 0: one code per query (16 B counters+planes by one lane); mode 1: all 15 codes (16 lanes).
+ * Returns average ms per launch and a checksum (so the work cannot be elided). */
+int bwb_occ_bench(bwb_ctx *ctx, uint64_t n, uint64_t seed, int mode, int iters, float *ms_per_launch,
+                  uint64_t *checksum);
+
+/* ---- search ---------------------------------------------------------------------------- */
+/* seq: nt4 codes (A0 G1 C2 T3, anything else = N) of the FORWARD reads, concatenated;
+ * offsets: n_reads+1 entries.  Reads longer than 255 are rejected (8-bit positions, align.h:104). */
+
+/* exact_match_bounded(read, len-1, 0, length-1) per read (exact_match.c:58-60,66-119): interval
+ * lists in reference order.  counts[n_reads]; intervals returned flat as (L,U) pairs. */
+int bwb_exact_match(bwb_ctx *ctx, const uint8_t *seq, const uint64_t *offsets, uint64_t n_reads,
+                    uint32_t *counts, uint64_t **intervals_LU, uint64_t *n_intervals);
+/* calculate_d (inexact_match.c:171-254) per read on read[0..dlen) where dlen = use_len>0 ?
+ * min(use_len,len) : len.  out holds, per read, (dlen+1) pairs {num_diff, sa_intv_width} packed at
+ * 2*(offsets[r]+r) int32s. */
+int bwb_calculate_d(bwb_ctx *ctx, const uint8_t *seq, const uint64_t *offsets, uint64_t n_reads,
+                    int use_len, int32_t *out);
+
+/* The hot path: calculate_d + inexact_match for every read (inexact_match.c:25-168), results in
+ * input order.  Host buffers in, host-readable results out (H2D/D2H inside). */
+int bwb_align(bwb_ctx *ctx, const bwb_params *params, const uint8_t *seq, const uint64_t *offsets,
+              uint64_t n_reads, bwb_results **out);
+
+/* Device-resident variant: upload once, align many times (bench `value`; no PCIe in the loop). */
+int bwb_reads_upload(bwb_ctx *ctx, const uint8_t *seq, const uint64_t *offsets, uint64_t n_reads,
+                     bwb_reads **out);
+void bwb_reads_free(bwb_reads *r);
+/* Runs the kernels on the context's stream(s); results stay on the device until
+ * bwb_results_fetch().  Asynchronous when fetch==0 (caller times with events on the stream set
+ * by bwb_set_stream and must call bwb_results_fetch or bwb_results_free afterwards). */
+int bwb_align_resident(bwb_ctx *ctx, const bwb_params *params, const bwb_reads *reads, int fetch,
+                       bwb_results **out);
+int bwb_results_fetch(bwb_results *r);
+
+/* ---- results --------------------------------------------------------------------------- */
+uint64_t bwb_results_num_reads(const bwb_results *r);
+uint64_t bwb_results_num_hits(const bwb_results *r);
+const uint32_t *bwb_results_counts(const bwb_results *r);   /* hits per read, input order */
+const bwb_hit *bwb_results_hits(const bwb_results *r);      /* flat, grouped by read, input order */
+/* kernel-side counters of the last call: [0] pops [1] pushes [2] exact-tail calls [3] block loads
+ * (physical 128-B rank gathers) [4] max heap entries of any read [5] max interval-list length */
+int bwb_results_counters(const bwb_results *r, uint64_t out[8]);
+/* Serialise exactly as alns2alnf_bin (align.c:345-382) does for each read in order. */
+int bwb_results_aln_bytes(const bwb_results *r, uint8_t **buf, uint64_t *len);   /* free with bwb_free */
+int bwb_results_write_aln(const bwb_results *r, const char *path, int append);
+void bwb_results_free(bwb_results *r);
+void bwb_free(void *p);
+
+/* ---- host-side index construction (bwbble index, bwt.c:29-63; SURVEY 8f "next") ----------- */
+/* Builds <fasta>.bwt and <fasta>.ann byte-identical to the reference's `bwbble index <fasta>`
+ * (io.c:190-321 fasta2ref, bwt.c:161-218 construct_bwt, is.c:214-243) with an own SA-IS. */
+int bwb_index_build(const char *fasta_path, int write_ref_file);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

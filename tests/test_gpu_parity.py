@@ -1,0 +1,192 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu).  Every check goes through the C ABI of
+libbwbble_b200.so and compares with the CPU restatement under oracle/ on the same seeded inputs.
+Integer / byte / index work: the bar is bit-exact."""
+import numpy as np
+import pytest
+
+import oracle
+from bwbble_b200 import Aligner, default_params, load_bwt
+from bwbble_b200.aln import first_difference
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def gpu_case(small_case):
+    al = Aligner(heap_pool_mb=512, hits_per_read=512, list_cap=2048)
+    al.load_index(small_case["bwt"])
+    orc = oracle.Oracle(small_case["bwt"])
+    yield {"al": al, "orc": orc, **small_case}
+    orc.close()
+    al.close()
+
+
+def _expected_blocks(ix):
+    """numpy restatement of the K0 layout (bwb_device.cuh): exclusive counters + 4 bit planes."""
+    sym = ix.symbols().astype(np.uint32)
+    nb = (ix.length + 127) // 128
+    pad = np.zeros(nb * 128, dtype=np.uint32)
+    pad[: ix.length] = sym
+    blk = pad.reshape(nb, 4, 32)
+    out = np.zeros((nb, 32), dtype=np.uint32)
+    O = ix.O.reshape(-1, 16).astype(np.int64)
+    first = pad.reshape(nb, 128)[:, 0]
+    cnt = O[:nb].copy()
+    rows = np.arange(nb)
+    adj = np.ones(nb, dtype=np.int64)
+    adj[(first == 0) & (rows * 128 == ix.sa0_index)] = 0
+    cnt[rows, first] -= adj
+    out[:, :16] = cnt.astype(np.uint32)
+    w = (1 << np.arange(32, dtype=np.uint64))[None, None, :]
+    for k in range(4):
+        out[:, 16 + 4 * k:20 + 4 * k] = (((blk >> k) & 1).astype(np.uint64) * w).sum(axis=2).astype(np.uint32)
+    return out
+
+
+def test_relayout_blocks(gpu_case):
+    ix = load_bwt(gpu_case["bwt"])
+    got = gpu_case["al"].download_blocks()
+    exp = _expected_blocks(ix)
+    assert got.shape == exp.shape
+    bad = np.argwhere(got != exp)
+    assert len(bad) == 0, "first differing (block, word): %s got %s exp %s" % (bad[0], got[tuple(bad[0])], exp[tuple(bad[0])])
+
+
+def _positions(length, rng, n):
+    edge = [0, 1, 126, 127, 128, 129, 255, 256, length - 2, length - 1, (1 << 64) - 1, length - 129, length - 128]
+    pos = np.concatenate([np.array(edge, dtype=np.uint64), rng.integers(0, length, size=n, dtype=np.uint64)])
+    return pos
+
+
+def test_occ_matches_oracle(gpu_case):
+    rng = np.random.default_rng(3)
+    al, orc = gpu_case["al"], gpu_case["orc"]
+    pos = _positions(orc.length, rng, 4000)
+    codes = rng.integers(1, 16, size=len(pos), dtype=np.uint8)
+    got = al.occ(codes, pos)
+    exp = np.array([orc.O(int(c), int(p)) for c, p in zip(codes, pos)], dtype=np.uint64)
+    bad = np.nonzero(got != exp)[0]
+    assert len(bad) == 0, "O(%d,%d): got %d exp %d" % (codes[bad[0]], pos[bad[0]], got[bad[0]], exp[bad[0]])
+
+
+def test_occ_sentinel_block(gpu_case):
+    """rows around sa0_index (nibble 0 there) and every code."""
+    al, orc = gpu_case["al"], gpu_case["orc"]
+    sa0 = load_bwt(gpu_case["bwt"]).sa0_index
+    pos = np.array([p for p in range(max(0, sa0 - 130), min(orc.length, sa0 + 130))], dtype=np.uint64)
+    for c in range(1, 16):
+        got = al.occ(np.full(len(pos), c, dtype=np.uint8), pos)
+        exp = np.array([orc.O(c, int(p)) for p in pos], dtype=np.uint64)
+        assert (got == exp).all(), "code %d" % c
+
+
+@pytest.mark.parametrize("inc", [0, 1])
+def test_occ_alphabet_matches_oracle_including_quirk(gpu_case, inc):
+    rng = np.random.default_rng(4)
+    al, orc = gpu_case["al"], gpu_case["orc"]
+    pos = _positions(orc.length, rng, 3000)
+    got = al.occ_alphabet(pos, inc)
+    for q, p in enumerate(pos):
+        exp = orc.O_alphabet(int(p), inc)
+        assert (got[q, 1:] == exp[1:]).all(), "O_alphabet(%d,%d): got %s exp %s" % (p, inc, got[q], exp)
+
+
+def test_exact_match_interval_lists(gpu_case):
+    al, orc, reads = gpu_case["al"], gpu_case["orc"], gpu_case["reads"]
+    got = al.exact_match(reads.seq, reads.offsets)
+    nonempty = 0
+    for r in range(reads.n):
+        exp = orc.exact_match(reads.read(r))
+        assert got[r].shape == exp.shape and (got[r] == exp).all(), "read %d: got %s exp %s" % (r, got[r], exp)
+        nonempty += len(exp) > 0
+    assert nonempty > 10
+
+
+def test_exact_match_short_prefixes_long_lists(gpu_case):
+    """short reads keep the search in the wide top of the tree: long lists, merges, smem spill."""
+    al, orc, reads = gpu_case["al"], gpu_case["orc"], gpu_case["reads"]
+    rng = np.random.default_rng(5)
+    lens = rng.integers(1, 9, size=200)
+    seqs = [reads.read(i)[:l] for i, l in enumerate(lens)]
+    seq = np.concatenate(seqs)
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
+    got = al.exact_match(seq, off)
+    longest = 0
+    for r, s in enumerate(seqs):
+        exp = orc.exact_match(s)
+        assert got[r].shape == exp.shape and (got[r] == exp).all(), "read %d len %d" % (r, len(s))
+        longest = max(longest, len(exp))
+    assert longest > 32, "fixture does not reach the shared-memory spill (longest list %d)" % longest
+
+
+@pytest.mark.parametrize("use_len", [0, 32, 20])
+def test_calculate_d(gpu_case, use_len):
+    al, orc, reads = gpu_case["al"], gpu_case["orc"], gpu_case["reads"]
+    got = al.calculate_d(reads.seq, reads.offsets, use_len)
+    for r in range(reads.n):
+        exp = orc.calculate_d(reads.read(r), use_len)
+        assert got[r].shape == exp.shape and (got[r] == exp).all(), "read %d:\n got %s\n exp %s" % (r, got[r].T, exp.T)
+
+
+GRID = [
+    dict(n=0), dict(n=1), dict(n=2), dict(n=3), dict(n=5),
+    dict(n=4, o=2, e=3, k=3, l=20), dict(n=3, M=2, O=5, E=2), dict(n=4, l=0), dict(n=3, k=1),
+    dict(n=6, o=2, M=4, O=4, E=4), dict(n=3, o=0), dict(n=2, e=0), dict(n=4, m=200),
+]
+
+
+@pytest.mark.parametrize("kw", GRID, ids=lambda k: "-".join("%s%d" % kv for kv in k.items()))
+def test_align_aln_bytes_equal_oracle(gpu_case, kw):
+    al, orc, reads = gpu_case["al"], gpu_case["orc"], gpu_case["reads"]
+    p = default_params(**kw)
+    res = al.align(reads.seq, reads.offsets, p)
+    got = res.aln_bytes()
+    exp, st = orc.align(reads.seq, reads.offsets, p)
+    if got != exp:
+        d = first_difference(got, exp)
+        raise AssertionError("params %s: first differing read %s\n got %s\n exp %s" % (kw, d[0], d[1], d[2]))
+    ctr = res.counters()
+    assert ctr["pops"] == st["pops"] and ctr["pushes"] == st["pushes"], (ctr, st)
+    assert ctr["exact_tails"] == st["exact_tail_calls"]
+    assert ctr["max_heap"] == st["max_heap"]
+    res.close()
+
+
+def test_align_ragged_lengths_and_n_reads(gpu_case):
+    from bwbble_b200 import synth
+    al, orc = gpu_case["al"], gpu_case["orc"]
+    reads = synth.make_reads(gpu_case["genome"], 11, 300, 150, 4, indel_frac=0.3, n_base_frac=0.01, ragged=(36, 150))
+    p = default_params(n=4)
+    got = al.align(reads.seq, reads.offsets, p).aln_bytes()
+    exp, _ = orc.align(reads.seq, reads.offsets, p)
+    assert got == exp, first_difference(got, exp)
+
+
+def test_align_empty_batch_and_all_n_read(gpu_case):
+    al, orc = gpu_case["al"], gpu_case["orc"]
+    p = default_params(n=2)
+    res = al.align(np.zeros(0, dtype=np.uint8), np.zeros(1, dtype=np.uint64), p)
+    assert res.num_reads == 0 and res.aln_bytes() == b""
+    seq = np.concatenate([np.full(50, 4, dtype=np.uint8), gpu_case["reads"].read(0)])
+    off = np.array([0, 50, 50 + len(gpu_case["reads"].read(0))], dtype=np.uint64)
+    got = al.align(seq, off, p).aln_bytes()
+    exp, _ = orc.align(seq, off, p)
+    assert got == exp
+
+
+def test_resident_path_equals_host_path(gpu_case):
+    al, reads = gpu_case["al"], gpu_case["reads"]
+    p = default_params(n=3)
+    a = al.align(reads.seq, reads.offsets, p).aln_bytes()
+    dr = al.upload_reads(reads.seq, reads.offsets)
+    res = al.align_resident(dr, p, fetch=False)
+    b = res.fetch().aln_bytes()
+    assert a == b
+
+
+def test_unsupported_params_fail_loudly(gpu_case):
+    from bwbble_b200 import BwbError
+    al, reads = gpu_case["al"], gpu_case["reads"]
+    for kw in (dict(use_precalc=1), dict(is_multiref=0), dict(o=9)):
+        with pytest.raises(BwbError):
+            al.align(reads.seq, reads.offsets, default_params(n=2, **kw))
