@@ -1,0 +1,93 @@
+"""Generate the golden fixtures with the UNMODIFIED reference (run here, where /root/reference exists):
+
+    python tests/golden/make_golden.py
+
+Builds oracle/_ref/bwbble from /root/reference/mg-aligner (make -C oracle ref), generates a small
+seeded multi-genome + reads, and records what the real reference produces:
+    g.fa, r.fq                      inputs (committed so the fixtures do not depend on the generator)
+    g.fa.bwt.gz, g.fa.ann           `bwbble index g.fa`
+    aln_<tag>.aln                   `bwbble align <flags> g.fa r.fq out.aln`   for every entry of GRID
+    sam_<tag>.sam                   `bwbble aln2sam -n <n> g.fa r.fq out.aln out.sam` (SAM = "next" row)
+    manifest.json                   tag -> flags, md5 of every file
+The reference repository ships no golden vectors of its own, so these ARE the pin.
+"""
+import gzip
+import hashlib
+import json
+import os
+import shutil
+import subprocess
+import sys
+import tempfile
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+GRID = {
+    "n0": ["-n", "0"],
+    "n1": ["-n", "1"],
+    "n2": ["-n", "2"],
+    "n3": ["-n", "3"],
+    "n5": ["-n", "5"],
+    "n3_t4": ["-n", "3", "-t", "4"],
+    "n4_o2_e3_k3_l20": ["-n", "4", "-o", "2", "-e", "3", "-k", "3", "-l", "20"],
+    "n3_M2_O5_E2": ["-n", "3", "-M", "2", "-O", "5", "-E", "2"],
+    "n4_l0": ["-n", "4", "-l", "0"],
+    "n6_o2_M4_O4_E4": ["-n", "6", "-o", "2", "-M", "4", "-O", "4", "-E", "4"],
+    "n3_o0": ["-n", "3", "-o", "0"],
+    "n4_m200": ["-n", "4", "-m", "200"],
+}
+
+
+def md5(path):
+    return hashlib.md5(open(path, "rb").read()).hexdigest()
+
+
+def main():
+    import oracle
+    from bwbble_b200 import synth
+    ref = oracle.ensure_ref_binary()
+    assert ref, "/root/reference is required to (re)generate the golden files"
+    g = synth.make_genome(101, 24000, n_records=2, snp_rate=0.015, tri_frac=0.08, n_bubbles=16, n_frac=0.03,
+                          n_repeat_copies=8, repeat_len=200, n_microsats=3, lowercase_frac=0.01)
+    reads = synth.make_reads(g, 102, 160, 100, 3, indel_frac=0.2, n_base_frac=0.004, bubble_frac=0.1)
+    short = synth.make_reads(g, 103, 40, 150, 4, indel_frac=0.3, n_base_frac=0.01, ragged=(36, 150))
+    with tempfile.TemporaryDirectory() as d:
+        fa, fq = os.path.join(d, "g.fa"), os.path.join(d, "r.fq")
+        g.write_fasta(fa)
+        reads.write_fastq(fq)
+        with open(fq, "ab") as f:                      # ragged 36..150 bp reads appended
+            tmp = os.path.join(d, "s.fq")
+            short.names = ["s%d" % i for i in range(short.n)]
+            short.write_fastq(tmp)
+            f.write(open(tmp, "rb").read())
+        run = lambda *a: subprocess.run([ref, *a], check=True, stdout=subprocess.DEVNULL)
+        run("index", fa)
+        manifest = {"grid": GRID, "md5": {}}
+        shutil.copy(fa, os.path.join(HERE, "g.fa"))
+        shutil.copy(fq, os.path.join(HERE, "r.fq"))
+        shutil.copy(fa + ".ann", os.path.join(HERE, "g.fa.ann"))
+        with open(fa + ".bwt", "rb") as src, gzip.GzipFile(os.path.join(HERE, "g.fa.bwt.gz"), "wb", mtime=0) as dst:
+            dst.write(src.read())
+        manifest["md5"]["g.fa.bwt"] = md5(fa + ".bwt")
+        for tag, flags in GRID.items():
+            aln = os.path.join(d, "out.aln")
+            run("align", *flags, fa, fq, aln)
+            shutil.copy(aln, os.path.join(HERE, "aln_%s.aln" % tag))
+            manifest["md5"]["aln_%s.aln" % tag] = md5(aln)
+            if tag in ("n0", "n3", "n4_o2_e3_k3_l20"):
+                sam = os.path.join(d, "out.sam")
+                n = flags[flags.index("-n") + 1]
+                run("aln2sam", "-n", n, fa, fq, aln, sam)
+                shutil.copy(sam, os.path.join(HERE, "sam_%s.sam" % tag))
+                manifest["md5"]["sam_%s.sam" % tag] = md5(sam)
+        for f in ("g.fa", "r.fq", "g.fa.ann"):
+            manifest["md5"][f] = md5(os.path.join(HERE, f))
+    json.dump(manifest, open(os.path.join(HERE, "manifest.json"), "w"), indent=1, sort_keys=True)
+    print("golden files written to", HERE)
+
+
+if __name__ == "__main__":
+    main()

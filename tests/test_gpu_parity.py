@@ -102,11 +102,31 @@ def test_exact_match_interval_lists(gpu_case):
     assert nonempty > 10
 
 
-def test_exact_match_short_prefixes_long_lists(gpu_case):
+@pytest.fixture(scope="module")
+def dense_case(tmp_path_factory):
+    """1.5 Mbp genome with 4 % SNP sites: interval lists of several hundred entries (shared-memory
+    spill + ordered merge across passes)."""
+    from bwbble_b200 import synth, index
+    d = tmp_path_factory.mktemp("dense")
+    g = synth.make_genome(17, 1500000, snp_rate=0.04, tri_frac=0.1, n_bubbles=100)
+    fa = str(d / "g.fa")
+    g.write_fasta(fa)
+    index.build_index(fa)
+    al = Aligner(heap_pool_mb=512, hits_per_read=512, list_cap=4096)
+    al.load_index(fa + ".bwt")
+    orc = oracle.Oracle(fa + ".bwt")
+    yield {"al": al, "orc": orc, "genome": g}
+    orc.close()
+    al.close()
+
+
+def test_exact_match_short_prefixes_long_lists(dense_case):
     """short reads keep the search in the wide top of the tree: long lists, merges, smem spill."""
-    al, orc, reads = gpu_case["al"], gpu_case["orc"], gpu_case["reads"]
+    from bwbble_b200 import synth
+    al, orc = dense_case["al"], dense_case["orc"]
+    reads = synth.make_reads(dense_case["genome"], 5, 300, 12, 0)
     rng = np.random.default_rng(5)
-    lens = rng.integers(1, 9, size=200)
+    lens = rng.integers(1, 13, size=300)
     seqs = [reads.read(i)[:l] for i, l in enumerate(lens)]
     seq = np.concatenate(seqs)
     off = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
@@ -116,7 +136,20 @@ def test_exact_match_short_prefixes_long_lists(gpu_case):
         exp = orc.exact_match(s)
         assert got[r].shape == exp.shape and (got[r] == exp).all(), "read %d len %d" % (r, len(s))
         longest = max(longest, len(exp))
-    assert longest > 32, "fixture does not reach the shared-memory spill (longest list %d)" % longest
+    assert longest > 64, "fixture does not reach the shared-memory spill (longest list %d)" % longest
+
+
+def test_dense_genome_align(dense_case):
+    """long interval lists inside calculate_d and the exact tails of the inexact search"""
+    from bwbble_b200 import synth
+    al, orc = dense_case["al"], dense_case["orc"]
+    reads = synth.make_reads(dense_case["genome"], 6, 400, 100, 2, indel_frac=0.1)
+    p = default_params(n=3)
+    res = al.align(reads.seq, reads.offsets, p)
+    got = res.aln_bytes()
+    exp, st = orc.align(reads.seq, reads.offsets, p)
+    assert got == exp, first_difference(got, exp)
+    assert st["max_list"] > 32 and res.counters()["max_list"] == st["max_list"]
 
 
 @pytest.mark.parametrize("use_len", [0, 32, 20])
