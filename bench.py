@@ -1,0 +1,349 @@
+#!/usr/bin/env python
+"""bench.py -- reads/s of the BWBBLE hot path (100 bp reads, BWA-default diffs) on 1..N B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload chr21|small]
+
+A "step" is one pass of the hot path (calculate_d + inexact_match for every read, K4+K5) over one
+batch of synthetic reads.  Workload `chr21` = BASELINE.json configs[1]: a synthetic chr21-scale
+multi-genome (48.1 Mbp, 27 % N runs, 1.2 % SNP sites of which 3 % tri-allelic, 40 k indel bubbles;
+the real chr21 files are absent from the reference tree) and the 10 M-read set of 100 bp reads with
+0-2 substitutions, consumed one batch per step; parameters `-n 5` + the reference defaults.
+
+  value         whole-job reads/s with the reads already resident in HBM (kernels only)
+  e2e           same metric through the public C-ABI call bwb_align() with HOST buffers: pinned
+                H2D of the batch and D2H of every hit record inside the timed region
+  roofline      K4's algorithmic bytes (rank queries the REFERENCE algorithm issues on these reads,
+                counted by the instrumented oracle, x 128 B) / K4's CUDA-event duration, vs the
+                measured HBM copy peak (MEASURED_PEAKS.json)
+  cpu_baseline  the reference's own OpenMP CPU path (oracle/_ref/bwbble when present, else the
+                oracle port) on this box's host cores, on a bounded sample of the same batch
+
+Multi-GPU: one process per GPU (torchrun), index replicated, reads sharded contiguously, no
+collective on the data path ("weak" scaling: every rank gets a full batch).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CACHE = os.environ.get("BWBBLE_B200_CACHE", "/tmp/bwbble_b200_cache")
+
+WORKLOADS = {
+    # name: genome kwargs, reads kwargs, reads per step (per GPU)
+    "chr21": dict(genome=dict(seed=21, n_bases=48_100_000, n_records=1, snp_rate=0.012, tri_frac=0.03,
+                              n_bubbles=40_000, n_frac=0.27),
+                  reads=dict(read_len=100, max_sub=2), batch=1 << 19, total_reads=10_000_000,
+                  desc="synthetic chr21-scale multi-genome (48.1 Mbp, 27% N, 1.2% SNP, 40k bubbles); 10M x 100bp reads, 0-2 subs"),
+    "small": dict(genome=dict(seed=5, n_bases=2_000_000, n_records=2, snp_rate=0.012, tri_frac=0.03,
+                              n_bubbles=1000, n_frac=0.05),
+                  reads=dict(read_len=100, max_sub=2), batch=1 << 15, total_reads=1_000_000,
+                  desc="2 Mbp synthetic multi-genome (CI-size)"),
+}
+PARAMS = dict(n=5)   # BWA's -n 0.04 => 5 differences at 100 bp; everything else = reference defaults
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def prepare_index(workload: str, rank: int, barrier) -> str:
+    """Generate the genome and build <fasta>.bwt once per box (cached under CACHE)."""
+    from bwbble_b200 import index, synth
+    d = os.path.join(CACHE, workload)
+    fa = os.path.join(d, "g.fa")
+    done = os.path.join(d, "DONE")
+    if rank == 0 and not os.path.exists(done):
+        os.makedirs(d, exist_ok=True)
+        t = time.time()
+        kw = dict(WORKLOADS[workload]["genome"])
+        g = synth.make_genome(kw.pop("seed"), kw.pop("n_bases"), **kw)
+        g.write_fasta(fa)
+        np.save(os.path.join(d, "hap.npy"), g.hap)
+        log("[bench] genome generated in %.1fs" % (time.time() - t))
+        t = time.time()
+        index.build_index(fa)
+        log("[bench] index built in %.1fs" % (time.time() - t))
+        open(done, "w").close()
+    barrier()
+    return fa
+
+
+def make_batch(workload: str, step: int, rank: int, world: int):
+    """Batch `step` of the read set for this rank (seeded; identical on every run)."""
+    from bwbble_b200 import synth
+    w = WORKLOADS[workload]
+    hap = np.load(os.path.join(CACHE, workload, "hap.npy"), mmap_mode="r")
+    g = synth.Genome([], np.asarray(hap), [], 0)
+    seed = 1_000_003 * (step + 1) + rank
+    return synth.make_reads(g, seed, w["batch"], with_names=False, bubble_frac=0.0, **w["reads"])
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu: int):
+        super().__init__(daemon=True)
+        self.gpu, self.rows, self.stop_flag = gpu, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                for ln in out.strip().splitlines():
+                    self.rows.append([x.strip() for x in ln.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        sm = [float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 8:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def host_cores() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def run_cpu_reference(fa: str, reads, n_sample: int, params: dict, threads: int, want_stats: bool):
+    """Time the reference CPU implementation on reads[0:n_sample].  Returns dict(value, kind, ...).
+    This is the ONE place bench.py executes anything under oracle/ (the cpu_baseline / reference arm)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle
+    from bwbble_b200 import default_params
+    sub = reads.slice(0, n_sample)
+    out = {"cores": threads, "sample": "first %d reads of step-0 batch, -n %d, %d threads" % (n_sample, params["n"], threads)}
+    stats = None
+    p = default_params(**params)
+    if want_stats:      # instrumented restatement: rank-query count Q of the reference algorithm
+        orc = oracle.Oracle(fa + ".bwt")
+        t = time.time()
+        _, stats = orc.align(sub.seq, sub.offsets, p, threads=threads)
+        port_s = time.time() - t
+        orc.close()
+        out["port_reads_per_s"] = n_sample / port_s
+    ref_bin = os.path.join(ROOT, "oracle", "_ref", "bwbble")
+    if os.path.exists(ref_bin):
+        with tempfile.TemporaryDirectory() as d:
+            fq = os.path.join(d, "s.fq")
+            sub.write_fastq(fq)
+            tiny = os.path.join(d, "t.fq")
+            sub.write_fastq(tiny, 0, 4)
+            cmd = [ref_bin, "align", "-n", str(params["n"]), "-t", str(threads), fa]
+            t = time.time()
+            subprocess.run(cmd + [tiny, os.path.join(d, "t.aln")], check=True, stdout=subprocess.DEVNULL)
+            load_s = time.time() - t          # index + FASTQ load (subtract a 4-read run)
+            t = time.time()
+            subprocess.run(cmd + [fq, os.path.join(d, "s.aln")], check=True, stdout=subprocess.DEVNULL)
+            full_s = time.time() - t
+        out.update(kind="reference", value=n_sample / max(full_s - load_s, 1e-6), load_s=load_s)
+    else:
+        if not want_stats:
+            orc = oracle.Oracle(fa + ".bwt")
+            t = time.time()
+            orc.align(sub.seq, sub.offsets, p, threads=threads)
+            port_s = time.time() - t
+            orc.close()
+            out["port_reads_per_s"] = n_sample / port_s
+        out.update(kind="port", value=out["port_reads_per_s"])
+    out["unit"] = "reads/s"
+    return out, stats
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=4)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="chr21", choices=list(WORKLOADS))
+    ap.add_argument("--cpu-sample", type=int, default=0, help="reads in the CPU baseline sample (0 = auto)")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--batch", type=int, default=0, help="override reads per step per GPU (profiling)")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    w = WORKLOADS[args.workload]
+    if args.batch:
+        w["batch"] = args.batch
+    cores = host_cores()
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        fa = prepare_index(args.workload, 0, lambda: None)
+        reads = make_batch(args.workload, 0, 0, 1)
+        n_s = args.cpu_sample or max(256, cores * 48)
+        times = []
+        meta = None
+        for s in range(args.warmup + args.steps):
+            res, _ = run_cpu_reference(fa, reads.slice((s * n_s) % (reads.n - n_s), (s * n_s) % (reads.n - n_s) + n_s),
+                                       n_s, PARAMS, cores, want_stats=False)
+            meta = res
+            if s >= args.warmup:
+                times.append(n_s / res["value"])
+        ms = 1e3 * float(np.mean(times))
+        val = n_s / (ms / 1e3)
+        line = {"impl": "reference", "metric": "reads/sec (100bp, BWA-default diffs)", "value": val, "unit": "reads/s",
+                "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64/u32 integer",
+                "data": "synthetic",
+                "config": {"workload": w["desc"], "params": "-n 5 -k 2 -l 32 -o 1 -e 6 -M 3 -O 11 -E 4",
+                           "reads_per_step": n_s},
+                "cpu_baseline": {"value": val, "unit": "reads/s", "cores": cores, "kind": meta["kind"],
+                                 "sample": "%d reads per step, %d host threads" % (n_s, cores)},
+                "e2e": {"value": val, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line), flush=True)
+        return 0
+
+    import torch
+    import torch.distributed as dist
+    from bwbble_b200 import Aligner, default_params
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    fa = prepare_index(args.workload, rank, barrier)
+    p = default_params(**PARAMS)
+    n_steps = args.warmup + args.steps
+    t0 = time.time()
+    batches = [make_batch(args.workload, s, rank, world) for s in range(n_steps)]
+    log("[bench] rank %d: %d batches x %d reads generated in %.1fs" % (rank, n_steps, w["batch"], time.time() - t0))
+
+    al = Aligner([local_rank])
+    al.load_index(fa + ".bwt")
+    stream = torch.cuda.current_stream()
+    al.set_stream(stream.cuda_stream)
+
+    # ---- value: reads resident in HBM ------------------------------------------------------
+    dev_reads = [al.upload_reads(b.seq, b.offsets) for b in batches]
+    kernel_ms, hits_total, ctr_sum = [], 0, {}
+    for s in range(args.warmup):
+        al.align_resident(dev_reads[s], p, fetch=False).close()
+    torch.cuda.synchronize()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for s in range(args.warmup, n_steps):
+        r = al.align_resident(dev_reads[s], p, fetch=False)
+        kernel_ms.append(r.kernel_ms)
+        hits_total += r.num_hits
+        for k, v in r.counters().items():
+            ctr_sum[k] = max(ctr_sum.get(k, 0), v) if k.startswith("max") else ctr_sum.get(k, 0) + v
+        r.close()
+    ev1.record(stream)
+    torch.cuda.synchronize()
+    barrier()
+    dev_ms = ev0.elapsed_time(ev1)
+
+    # ---- e2e: host buffers through bwb_align (pinned H2D + D2H of every hit) -------------------
+    pinned = [(torch.from_numpy(b.seq).pin_memory(), torch.from_numpy(b.offsets.view(np.int64)).pin_memory()) for b in batches]
+    h2d = int(np.mean([b.seq.nbytes + b.offsets.nbytes for b in batches[args.warmup:]]))
+    d2h_bytes = []
+    al.align(pinned[0][0].numpy(), pinned[0][1].numpy().view(np.uint64), p).close()
+    torch.cuda.synchronize()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_host0 = time.time()
+    e0.record(stream)
+    for s in range(args.warmup, n_steps):
+        r = al.align(pinned[s][0].numpy(), pinned[s][1].numpy().view(np.uint64), p)
+        d2h_bytes.append(4 * r.num_reads + 48 * r.num_hits + 256)
+        r.close()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    e2e_ms = max(e0.elapsed_time(e1), 1e3 * (time.time() - t_host0))
+    barrier()
+    sampler.stop_flag = True
+    sampler.join(timeout=3)
+
+    if world > 1:
+        t = torch.tensor([dev_ms, e2e_ms, max(kernel_ms)], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_ms, e2e_ms = float(t[0]), float(t[1])
+    reads_per_step = w["batch"] * world
+    value = reads_per_step * args.steps / (dev_ms / 1e3)
+    e2e = reads_per_step * args.steps / (e2e_ms / 1e3)
+
+    if rank == 0:
+        cpu, stats = None, None
+        if not args.no_cpu and world == 1:
+            n_s = args.cpu_sample or max(2048, min(cores * 512, 65536))
+            cpu, stats = run_cpu_reference(fa, batches[args.warmup], n_s, PARAMS, cores, want_stats=True)
+        elif not args.no_cpu:
+            n_s = 4096
+            sys.path.insert(0, os.path.join(ROOT, "tests"))
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        roof = None
+        if stats:
+            q_per_read = (stats["n_O"] + stats["n_Oalpha"]) / n_s
+            k_ms = float(np.mean(kernel_ms))
+            achieved = w["batch"] * q_per_read * 128 / (k_ms / 1e3) / 1e9
+            roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": None, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
+                    "kernel": "k_align", "kernel_ms_per_launch": k_ms, "rank_queries_per_read_reference": q_per_read,
+                    "bytes_per_query": 128,
+                    "physical_block_loads_per_read": ctr_sum.get("rank_queries", 0) / (w["batch"] * args.steps)}
+        line = {"metric": "reads/sec (100bp, BWA-default diffs)", "value": value, "unit": "reads/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64/u32 integer",
+                "data": "synthetic",
+                "config": {"workload": w["desc"], "params": "-n 5 -k 2 -l 32 -o 1 -e 6 -M 3 -O 11 -E 4",
+                           "reads_per_step": reads_per_step, "reads_per_step_per_gpu": w["batch"],
+                           "l2": "index (~%d MB) + heap/list scratch exceed L2; every step is a fresh batch" % (116),
+                           "parallelism": "reads sharded x%d, index replicated, no collective" % world},
+                "e2e": {"value": e2e, "unit": "reads/s", "h2d_bytes_per_step": h2d * world,
+                        "d2h_bytes_per_step": int(np.mean(d2h_bytes)) * world},
+                "gpu_launches": 3 * args.steps,
+                "clocks": sampler.summary(),
+                "roofline": roof, "cpu_baseline": None if cpu is None else
+                {"value": cpu["value"], "unit": "reads/s", "cores": cpu["cores"], "kind": cpu["kind"], "sample": cpu["sample"],
+                 "port_reads_per_s": cpu.get("port_reads_per_s")},
+                "counters_per_read": {k: (v if k.startswith("max") else v / (w["batch"] * args.steps)) for k, v in ctr_sum.items()},
+                "hits_per_read": hits_total / (w["batch"] * args.steps)}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

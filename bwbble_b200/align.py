@@ -85,6 +85,10 @@ class AlignResult:
         names = ["pops", "pushes", "exact_tails", "rank_queries", "max_heap", "max_list"]
         return {k: int(arr[i]) for i, k in enumerate(names)}
 
+    @property
+    def kernel_ms(self) -> float:
+        return float(_lib.lib().bwb_results_kernel_ms(self._h))
+
     def aln_bytes(self) -> bytes:
         buf = C.c_void_p()
         ln = C.c_uint64()

@@ -45,6 +45,7 @@ struct Device {
     DevBuf seq, offsets, read_off, read_cnt, ordered_off, unordered, ordered, cub_tmp, small;
     // pinned staging for small D2H
     unsigned long long *h_small = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;   // bracket K4 on the launch stream
 };
 
 }  // namespace
@@ -78,6 +79,7 @@ struct bwb_results {
     std::vector<uint32_t> counts;
     std::vector<bwb_hit> hits;
     uint64_t counters[8] = {0};
+    float kernel_ms = 0.f;    // K4 duration (max over devices), CUDA events on the launch stream
     // pending (device-resident) state
     bool fetched = false;
     std::vector<uint64_t> shard_lo;
@@ -238,7 +240,8 @@ bwb_ctx *bwb_create(const int *devices, int ndev) {
         cudaDeviceProp prop;
         if (cudaSetDevice(id) != cudaSuccess || cudaGetDeviceProperties(&prop, id) != cudaSuccess ||
             cudaStreamCreateWithFlags(&d.own_stream, cudaStreamNonBlocking) != cudaSuccess ||
-            cudaMallocHost((void **)&d.h_small, 64 * sizeof(unsigned long long)) != cudaSuccess) {
+            cudaMallocHost((void **)&d.h_small, 64 * sizeof(unsigned long long)) != cudaSuccess ||
+            cudaEventCreate(&d.ev0) != cudaSuccess || cudaEventCreate(&d.ev1) != cudaSuccess) {
             fail(nullptr, BWB_ERR_CUDA, "cannot initialise device %d: %s", id, cudaGetErrorString(cudaGetLastError()));
             delete ctx;
             return nullptr;
@@ -260,6 +263,8 @@ void bwb_destroy(bwb_ctx *ctx) {
                           &d.ordered_off, &d.unordered, &d.ordered, &d.cub_tmp, &d.small};
         for (DevBuf *b : bufs) release(*b);
         if (d.h_small) cudaFreeHost(d.h_small);
+        if (d.ev0) cudaEventDestroy(d.ev0);
+        if (d.ev1) cudaEventDestroy(d.ev1);
         if (d.own_stream) cudaStreamDestroy(d.own_stream);
     }
     delete ctx;
@@ -610,10 +615,12 @@ static int launch_shard(bwb_ctx *ctx, Device &d, const bwb_params *p, int nb, co
     a.counters = (unsigned long long *)(sm + 32);
     a.smem_per_warp = L.per_warp; a.off_D = L.off_D; a.off_Ds = L.off_Ds; a.off_bk = L.off_bk; a.off_seq = L.off_seq;
 
+    CU(cudaEventRecord(d.ev0, d.stream));
     if (n) {
         k_align<<<d.grid, d.wpb * 32, d.smem_bytes, d.stream>>>(a);
         CU(cudaGetLastError());
     }
+    CU(cudaEventRecord(d.ev1, d.stream));
     // K5: exclusive scan of the per-read counts, then ordered copy
     const uint32_t *cnt = (const uint32_t *)d.read_cnt.p;
     unsigned long long *ooff = (unsigned long long *)d.ordered_off.p;
@@ -672,6 +679,9 @@ static int align_impl(bwb_ctx *ctx, const bwb_params *p, const bwb_reads *R, bwb
             if (used > cap[g]) { cap[g] = used + used / 8 + 1024; again = true; continue; }
             done[g] = 1;
             res->shard_total[g] = used;
+            float ms = 0.f;
+            CU(cudaEventElapsedTime(&ms, d.ev0, d.ev1));
+            if (ms > res->kernel_ms) res->kernel_ms = ms;
             const unsigned long long *ctr = (const unsigned long long *)(hs + 32);
             for (int k = 0; k < 4; k++) res->counters[k] += ctr[k];
             for (int k = 4; k < 6; k++) if (ctr[k] > res->counters[k]) res->counters[k] = ctr[k];
@@ -747,6 +757,7 @@ int bwb_results_counters(const bwb_results *r, uint64_t out[8]) {
     memcpy(out, r->counters, sizeof r->counters);
     return BWB_OK;
 }
+double bwb_results_kernel_ms(const bwb_results *r) { return r ? (double)r->kernel_ms : 0.0; }
 void bwb_results_free(bwb_results *r) { delete r; }
 void bwb_free(void *p) { free(p); }
 

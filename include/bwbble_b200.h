@@ -147,8 +147,7 @@ int bwb_reads_upload(bwb_ctx *ctx, const uint8_t *seq, const uint64_t *offsets, 
                      bwb_reads **out);
 void bwb_reads_free(bwb_reads *r);
 /* Runs the kernels on the context's stream(s); results stay on the device until
- * bwb_results_fetch().  Asynchronous when fetch==0 (caller times with events on the stream set
- * by bwb_set_stream and must call bwb_results_fetch or bwb_results_free afterwards). */
+ * bwb_results_fetch() (fetch==0: no bulk D2H, only the 256-byte status block is read back). */
 int bwb_align_resident(bwb_ctx *ctx, const bwb_params *params, const bwb_reads *reads, int fetch,
                        bwb_results **out);
 int bwb_results_fetch(bwb_results *r);
@@ -161,6 +160,9 @@ const bwb_hit *bwb_results_hits(const bwb_results *r);      /* flat, grouped by 
 /* kernel-side counters of the last call: [0] pops [1] pushes [2] exact-tail calls [3] block loads
  * (physical 128-B rank gathers) [4] max heap entries of any read [5] max interval-list length */
 int bwb_results_counters(const bwb_results *r, uint64_t out[8]);
+/* Duration of the search kernel (K4) of the call that produced r, in ms: CUDA events on the launch
+ * stream, max over the context's devices. */
+double bwb_results_kernel_ms(const bwb_results *r);
 /* Serialise exactly as alns2alnf_bin (align.c:345-382) does for each read in order. */
 int bwb_results_aln_bytes(const bwb_results *r, uint8_t **buf, uint64_t *len);   /* free with bwb_free */
 int bwb_results_write_aln(const bwb_results *r, const char *path, int append);
