@@ -182,6 +182,7 @@ def main():
     ap.add_argument("--workload", default="chr21", choices=list(WORKLOADS))
     ap.add_argument("--cpu-sample", type=int, default=0, help="reads in the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--quick", action="store_true", help="A/B experiments: resident timing only, short JSON")
     ap.add_argument("--batch", type=int, default=0, help="override reads per step per GPU (profiling)")
     args = ap.parse_args()
 
@@ -268,6 +269,11 @@ def main():
     torch.cuda.synchronize()
     barrier()
     dev_ms = ev0.elapsed_time(ev1)
+
+    if args.quick:
+        print(json.dumps({"reads_per_s": w["batch"] * args.steps / (dev_ms / 1e3), "kernel_ms": kernel_ms,
+                          "lib": os.environ.get("BWBBLE_B200_LIB", "default"), "ctr": ctr_sum}), flush=True)
+        return 0
 
     # ---- e2e: host buffers through bwb_align (pinned H2D + D2H of every hit) -------------------
     pinned = [(torch.from_numpy(b.seq).pin_memory(), torch.from_numpy(b.offsets.view(np.int64)).pin_memory()) for b in batches]

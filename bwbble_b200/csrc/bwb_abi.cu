@@ -63,6 +63,7 @@ struct bwb_ctx {
     int hits_per_read = 1024;
     int warps_per_block = 8;
     int blocks_per_sm = 0;
+    int force_wide = 0;       // tests: run the 64-bit / 32-byte-entry kernels on a small index
 };
 
 struct bwb_reads {
@@ -146,6 +147,9 @@ int check_reads(bwb_ctx *ctx, const uint64_t *offsets, uint64_t n_reads, int &ma
     return BWB_OK;
 }
 
+// 64-bit coordinates are needed from 2^32-16 rows on (all-ones is the "-1" row)
+bool index_is_wide(const bwb_ctx *ctx) { return ctx->force_wide || ctx->length >= 0xfffffff0ull; }
+
 // per-warp shared-memory layout of K4 (must match k_align)
 struct SmemLayout {
     int per_warp, off_D, off_Ds, off_bk, off_seq;
@@ -166,15 +170,17 @@ SmemLayout k4_layout(int max_len, int seed_len, int nb) {
 }
 
 // size the persistent grid and the per-warp scratch for K4
-int prepare_search(bwb_ctx *ctx, Device &d, const SmemLayout &L) {
+int prepare_search(bwb_ctx *ctx, Device &d, const SmemLayout &L, bool wide) {
     CU(cudaSetDevice(d.id));
     const int wpb = ctx->warps_per_block;
     const size_t smem = (size_t)wpb * L.per_warp;
     if (smem > 227 * 1024) return fail(ctx, BWB_ERR_ARG, "shared memory per block %zu exceeds 227 KB", smem);
-    CU(cudaFuncSetAttribute(k_align, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (wide) CU(cudaFuncSetAttribute(k_align<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    else CU(cudaFuncSetAttribute(k_align<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int bps = ctx->blocks_per_sm;
     if (bps <= 0) {
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_align, wpb * 32, smem));
+        if (wide) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_align<true>, wpb * 32, smem));
+        else CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_align<false>, wpb * 32, smem));
         if (bps <= 0) return fail(ctx, BWB_ERR_CUDA, "k_align does not fit on an SM");
     }
     const int grid = bps * d.sm_count;
@@ -189,7 +195,7 @@ int prepare_search(bwb_ctx *ctx, Device &d, const SmemLayout &L) {
     if ((rc = ensure(ctx, d.glists, (size_t)n_warps * 2 * ctx->list_cap * sizeof(ulonglong2), false))) return rc;
     if ((rc = ensure(ctx, d.stage, (size_t)n_warps * ctx->hits_per_read * sizeof(bwb_hit), false))) return rc;
     if (!d.chunks.p) {
-        const size_t chunk_bytes = (size_t)CHUNK_ENTRIES * 32;
+        const size_t chunk_bytes = (size_t)CHUNK_ENTRIES * 32;   // sized for the 32-byte entry format
         uint64_t n_chunks = ((uint64_t)ctx->heap_pool_mb << 20) / chunk_bytes;
         if (n_chunks < (uint64_t)n_warps * 8) n_chunks = (uint64_t)n_warps * 8;
         if (n_chunks > 0xfffffff0ull) n_chunks = 0xfffffff0ull;
@@ -275,7 +281,7 @@ int bwb_device_count(const bwb_ctx *ctx) { return ctx ? (int)ctx->dev.size() : 0
 int bwb_set_option(bwb_ctx *ctx, const char *key, long long value) {
     if (!ctx || !key) return BWB_ERR_ARG;
     std::string k(key);
-    if (value <= 0 && k != "blocks_per_sm") return fail(ctx, BWB_ERR_ARG, "option %s needs a positive value", key);
+    if (value <= 0 && k != "blocks_per_sm" && k != "force_wide") return fail(ctx, BWB_ERR_ARG, "option %s needs a positive value", key);
     if (k == "heap_pool_mb") ctx->heap_pool_mb = value;
     else if (k == "list_cap") ctx->list_cap = (int)(value < SL + 4 ? SL + 4 : value);
     else if (k == "hits_per_read") ctx->hits_per_read = (int)value;
@@ -283,6 +289,7 @@ int bwb_set_option(bwb_ctx *ctx, const char *key, long long value) {
         if (value > 8) return fail(ctx, BWB_ERR_ARG, "warps_per_block must be 1..8");
         ctx->warps_per_block = (int)value;
     } else if (k == "blocks_per_sm") ctx->blocks_per_sm = (int)value;
+    else if (k == "force_wide") ctx->force_wide = value > 1 ? 0 : 1;
     else return fail(ctx, BWB_ERR_ARG, "unknown option %s", key);
     for (auto &d : ctx->dev) {       // scratch is re-sized lazily
         cudaSetDevice(d.id);
@@ -366,7 +373,8 @@ int bwb_occ(bwb_ctx *ctx, const uint8_t *code, const uint64_t *pos, uint64_t n, 
     CU(cudaMalloc(&dc, n)); CU(cudaMalloc(&dp, n * 8)); CU(cudaMalloc(&dout, n * 8));
     CU(cudaMemcpyAsync(dc, code, n, cudaMemcpyHostToDevice, d.stream));
     CU(cudaMemcpyAsync(dp, pos, n * 8, cudaMemcpyHostToDevice, d.stream));
-    k_occ<<<(unsigned)((n + 255) / 256), 256, 0, d.stream>>>(make_view(ctx, d), dc, dp, n, dout);
+    if (index_is_wide(ctx)) k_occ<uint64_t><<<(unsigned)((n + 255) / 256), 256, 0, d.stream>>>(make_view(ctx, d), dc, dp, n, dout);
+    else k_occ<uint32_t><<<(unsigned)((n + 255) / 256), 256, 0, d.stream>>>(make_view(ctx, d), dc, dp, n, dout);
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(out, dout, n * 8, cudaMemcpyDeviceToHost, d.stream));
     CU(cudaStreamSynchronize(d.stream));
@@ -383,7 +391,8 @@ int bwb_occ_alphabet(bwb_ctx *ctx, const uint64_t *pos, uint64_t n, int inc, uin
     uint64_t *dp, *dout;
     CU(cudaMalloc(&dp, n * 8)); CU(cudaMalloc(&dout, n * 16 * 8));
     CU(cudaMemcpyAsync(dp, pos, n * 8, cudaMemcpyHostToDevice, d.stream));
-    k_occ_alphabet<<<(unsigned)((n * 16 + 255) / 256), 256, 0, d.stream>>>(make_view(ctx, d), dp, n, (uint32_t)inc, dout);
+    if (index_is_wide(ctx)) k_occ_alphabet<uint64_t><<<(unsigned)((n * 16 + 255) / 256), 256, 0, d.stream>>>(make_view(ctx, d), dp, n, (uint32_t)inc, dout);
+    else k_occ_alphabet<uint32_t><<<(unsigned)((n * 16 + 255) / 256), 256, 0, d.stream>>>(make_view(ctx, d), dp, n, (uint32_t)inc, dout);
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(out, dout, n * 16 * 8, cudaMemcpyDeviceToHost, d.stream));
     CU(cudaStreamSynchronize(d.stream));
@@ -445,6 +454,7 @@ static int run_list_kernel(bwb_ctx *ctx, int which, const uint8_t *seq, const ui
     a.max_len = max_len;
     a.use_len = use_len;
     uint8_t *dseq; uint64_t *doff; ulonglong2 *gl; uint32_t *dstatus;
+    const bool wide = index_is_wide(ctx);
     CU(cudaMalloc(&dseq, total + 16)); CU(cudaMalloc(&doff, (n_reads + 1) * 8));
     CU(cudaMalloc(&gl, (size_t)n_warps * 2 * a.list_cap * sizeof(ulonglong2)));
     CU(cudaMalloc(&dstatus, 8));
@@ -453,7 +463,7 @@ static int run_list_kernel(bwb_ctx *ctx, int which, const uint8_t *seq, const ui
     CU(cudaMemcpyAsync(dseq, seq + offsets[0], total, cudaMemcpyHostToDevice, d.stream));
     CU(cudaMemcpyAsync(doff, rel.data(), (n_reads + 1) * 8, cudaMemcpyHostToDevice, d.stream));
     CU(cudaMemsetAsync(dstatus, 0, 8, d.stream));
-    a.seq = dseq; a.offsets = doff; a.glists = gl; a.status = dstatus;
+    a.seq = dseq; a.offsets = doff; a.glists = (void *)gl; a.status = dstatus;
     uint32_t hstatus = 0;
     if (which == 2) {
         unsigned long long *dcur, *droff; uint32_t *drcnt; ulonglong2 *dout;
@@ -464,7 +474,8 @@ static int run_list_kernel(bwb_ctx *ctx, int which, const uint8_t *seq, const ui
             CU(cudaMemsetAsync(dcur, 0, 8, d.stream));
             a.out_iv = dout; a.out_cap = cap; a.out_cursor = dcur; a.read_off = droff; a.read_cnt = drcnt;
             const size_t smem = (size_t)wpb * (2 * SL * sizeof(ulonglong2) + ((max_len + 15) & ~15));
-            k_exact<<<grid, wpb * 32, smem, d.stream>>>(a);
+            if (wide) k_exact<uint64_t><<<grid, wpb * 32, smem, d.stream>>>(a);
+            else k_exact<uint32_t><<<grid, wpb * 32, smem, d.stream>>>(a);
             CU(cudaGetLastError());
             unsigned long long used = 0;
             CU(cudaMemcpyAsync(&used, dcur, 8, cudaMemcpyDeviceToHost, d.stream));
@@ -497,8 +508,13 @@ static int run_list_kernel(bwb_ctx *ctx, int which, const uint8_t *seq, const ui
         CU(cudaMemsetAsync(dd, 0, nd * 4, d.stream));
         a.out_d = dd;
         const size_t smem = (size_t)wpb * (2 * SL * sizeof(ulonglong2) + (((max_len + 1) * 8 + 15) & ~15) + ((max_len + 15) & ~15));
-        CU(cudaFuncSetAttribute(k_calc_d, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_calc_d<<<grid, wpb * 32, smem, d.stream>>>(a);
+        if (wide) {
+            CU(cudaFuncSetAttribute(k_calc_d<uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_calc_d<uint64_t><<<grid, wpb * 32, smem, d.stream>>>(a);
+        } else {
+            CU(cudaFuncSetAttribute(k_calc_d<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_calc_d<uint32_t><<<grid, wpb * 32, smem, d.stream>>>(a);
+        }
         CU(cudaGetLastError());
         CU(cudaMemcpyAsync(out_d, dd, nd * 4, cudaMemcpyDeviceToHost, d.stream));
         CU(cudaMemcpyAsync(&hstatus, dstatus, 4, cudaMemcpyDeviceToHost, d.stream));
@@ -576,7 +592,7 @@ static int check_params(bwb_ctx *ctx, const bwb_params *p, int max_len, int &nb)
 }
 
 // enqueue K4 + scan + K5 for one shard on its device stream
-static int launch_shard(bwb_ctx *ctx, Device &d, const bwb_params *p, int nb, const SmemLayout &L, int max_len,
+static int launch_shard(bwb_ctx *ctx, Device &d, const bwb_params *p, int nb, const SmemLayout &L, int max_len, bool wide,
                         const void *d_seq, const void *d_off, uint64_t n, uint64_t read_base, unsigned long long out_cap) {
     int rc;
     CU(cudaSetDevice(d.id));
@@ -603,7 +619,7 @@ static int launch_shard(bwb_ctx *ctx, Device &d, const bwb_params *p, int nb, co
     a.no_indel_len = p->no_indel_length;
     a.nb = nb; a.max_len = max_len;
     a.queue = (uint32_t *)sm;
-    a.glists = (ulonglong2 *)d.glists.p; a.list_cap = ctx->list_cap;
+    a.glists = d.glists.p; a.list_cap = ctx->list_cap;
     a.chunks = (uint4 *)d.chunks.p; a.chunk_link = (uint32_t *)d.chunk_link.p;
     a.chunks_per_warp = d.chunks_per_warp; a.n_chunks = d.n_chunks;
     a.overflow_cursor = (uint32_t *)(sm + 24);
@@ -617,7 +633,8 @@ static int launch_shard(bwb_ctx *ctx, Device &d, const bwb_params *p, int nb, co
 
     CU(cudaEventRecord(d.ev0, d.stream));
     if (n) {
-        k_align<<<d.grid, d.wpb * 32, d.smem_bytes, d.stream>>>(a);
+        if (wide) k_align<true><<<d.grid, d.wpb * 32, d.smem_bytes, d.stream>>>(a);
+        else k_align<false><<<d.grid, d.wpb * 32, d.smem_bytes, d.stream>>>(a);
         CU(cudaGetLastError());
     }
     CU(cudaEventRecord(d.ev1, d.stream));
@@ -639,6 +656,8 @@ static int align_impl(bwb_ctx *ctx, const bwb_params *p, const bwb_reads *R, bwb
     int nb = 0, rc;
     if ((rc = check_params(ctx, p, R->max_len, nb))) return rc;
     const SmemLayout L = k4_layout(R->max_len > 0 ? R->max_len : 1, p->seed_length, nb);
+    // 16-byte entries + 32-bit coordinates unless the index or the gap-run count needs the wide format
+    const bool wide = index_is_wide(ctx) || p->max_gapo > 1;
     const int G = (int)ctx->dev.size();
     bwb_results *res = new bwb_results();
     res->ctx = ctx; res->n_reads = R->n_reads; res->shard_lo = R->shard_lo; res->shard_total.assign(G, 0);
@@ -646,7 +665,7 @@ static int align_impl(bwb_ctx *ctx, const bwb_params *p, const bwb_reads *R, bwb
 
     std::vector<unsigned long long> cap(G);
     for (int g = 0; g < G; g++) {
-        if ((rc = prepare_search(ctx, ctx->dev[g], L))) { delete res; return rc; }
+        if ((rc = prepare_search(ctx, ctx->dev[g], L, wide))) { delete res; return rc; }
         cap[g] = (R->shard_lo[g + 1] - R->shard_lo[g]) * 2 + 65536;
     }
     std::vector<char> done(G, 0);
@@ -654,7 +673,7 @@ static int align_impl(bwb_ctx *ctx, const bwb_params *p, const bwb_reads *R, bwb
         for (int g = 0; g < G; g++) {
             if (done[g]) continue;
             const uint64_t lo = R->shard_lo[g], n = R->shard_lo[g + 1] - lo;
-            if ((rc = launch_shard(ctx, ctx->dev[g], p, nb, L, R->max_len > 0 ? R->max_len : 1, R->d_seq[g], R->d_off[g], n, lo, cap[g]))) {
+            if ((rc = launch_shard(ctx, ctx->dev[g], p, nb, L, R->max_len > 0 ? R->max_len : 1, wide, R->d_seq[g], R->d_off[g], n, lo, cap[g]))) {
                 delete res;
                 return rc;
             }

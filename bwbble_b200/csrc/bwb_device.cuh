@@ -12,6 +12,10 @@
 // and the in-block count of code c up to row offset r is popc(AND_k (plane_k ^ ~c_k) & mask(r)).
 // The reference stores inclusive checkpoints (row 128*blk counted, bwt.c:280-291) and subtracts the
 // checkpoint symbol again (bwt.c:596-598); the exclusive counter here yields the same values.
+//
+// Everything is templated on the SA-coordinate type: uint32_t when the index has < 2^32-1 rows
+// (chr21 scale), uint64_t otherwise (genome scale).  "-1" (L-1 of L==0) is the all-ones value of
+// the type; it can never collide with a real row because length-1 < all-ones.
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -28,81 +32,137 @@ struct IndexView {
     uint64_t C[17];
 };
 
+template <class T> struct Pair;
+template <> struct Pair<uint32_t> { typedef uint2 type; };
+template <> struct Pair<uint64_t> { typedef ulonglong2 type; };
+
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
 
-__device__ __forceinline__ uint64_t shfl64(uint64_t v, int src) {
+__device__ __forceinline__ uint32_t shfl(uint32_t v, int src) { return __shfl_sync(FULL, v, src); }
+__device__ __forceinline__ uint64_t shfl(uint64_t v, int src) {
     uint32_t lo = __shfl_sync(FULL, (uint32_t)v, src);
     uint32_t hi = __shfl_sync(FULL, (uint32_t)(v >> 32), src);
     return ((uint64_t)hi << 32) | lo;
 }
-__device__ __forceinline__ uint64_t shfl64_xor(uint64_t v, int m) {
+__device__ __forceinline__ uint32_t shfl_xor(uint32_t v, int m) { return __shfl_xor_sync(FULL, v, m); }
+__device__ __forceinline__ uint64_t shfl_xor(uint64_t v, int m) {
     uint32_t lo = __shfl_xor_sync(FULL, (uint32_t)v, m);
     uint32_t hi = __shfl_xor_sync(FULL, (uint32_t)(v >> 32), m);
     return ((uint64_t)hi << 32) | lo;
 }
+__device__ __forceinline__ uint64_t shfl64(uint64_t v, int src) { return shfl(v, src); }
 
-// cnt[c] + #{rows p in [0, r] of this block holding code c};  first = [row 0 of the block holds c]
-__device__ __forceinline__ uint32_t block_rank(const uint4 *__restrict__ blk, uint32_t c, uint32_t r,
-                                               uint32_t &first) {
-    const uint32_t cnt = __ldg(reinterpret_cast<const uint32_t *>(blk) + c);
-    const uint4 p0 = __ldg(blk + 4), p1 = __ldg(blk + 5), p2 = __ldg(blk + 6), p3 = __ldg(blk + 7);
-    const uint32_t x0 = (c & 1u) ? 0u : ~0u, x1 = (c & 2u) ? 0u : ~0u;
-    const uint32_t x2 = (c & 4u) ? 0u : ~0u, x3 = (c & 8u) ? 0u : ~0u;
-    const uint32_t m0 = (p0.x ^ x0) & (p1.x ^ x1) & (p2.x ^ x2) & (p3.x ^ x3);
-    const uint32_t m1 = (p0.y ^ x0) & (p1.y ^ x1) & (p2.y ^ x2) & (p3.y ^ x3);
-    const uint32_t m2 = (p0.z ^ x0) & (p1.z ^ x1) & (p2.z ^ x2) & (p3.z ^ x3);
-    const uint32_t m3 = (p0.w ^ x0) & (p1.w ^ x1) & (p2.w ^ x2) & (p3.w ^ x3);
-    const uint32_t w = r >> 5;
-    const uint32_t last = (2u << (r & 31u)) - 1u;          // bits 0..r%32 (r%32==31 -> all ones)
-    const uint32_t k0 = w > 0 ? ~0u : last;
-    const uint32_t k1 = w > 1 ? ~0u : (w == 1 ? last : 0u);
-    const uint32_t k2 = w > 2 ? ~0u : (w == 2 ? last : 0u);
-    const uint32_t k3 = w == 3 ? last : 0u;
-    first = m0 & 1u;
-    return cnt + __popc(m0 & k0) + __popc(m1 & k1) + __popc(m2 & k2) + __popc(m3 & k3);
+// per-block C[] staged in shared memory, in the coordinate type
+template <class T>
+__device__ __forceinline__ void stage_C(const IndexView &ix, T *sC) {
+    if (threadIdx.x < 17) sC[threadIdx.x] = (T)ix.C[threadIdx.x];
+    __syncthreads();
 }
 
-// O(c, i), c in 1..15 (bwt.c:348-372).  sC = C[] staged in shared memory.
-__device__ __forceinline__ uint64_t occ1(const IndexView &ix, const uint64_t *sC, uint32_t c, uint64_t i) {
-    const bool top = (i == ix.length - 1), neg = (i == ~0ull);
-    const uint64_t ii = (top || neg) ? 0ull : i;
-    uint32_t first;
-    const uint32_t v = block_rank(ix.blocks + (ii >> 7) * 8, c, (uint32_t)(ii & 127u), first);
-    return top ? (sC[c + 1] - sC[c]) : (neg ? 0ull : (uint64_t)v);
+struct BlockBits {       // match mask of one code over the 128 rows of a block + its counter
+    uint32_t cnt, m0, m1, m2, m3;
+};
+
+__device__ __forceinline__ BlockBits load_block(const uint4 *__restrict__ blk, uint32_t c) {
+    BlockBits b;
+    b.cnt = __ldg(reinterpret_cast<const uint32_t *>(blk) + c);
+    const uint4 p0 = __ldg(blk + 4), p1 = __ldg(blk + 5), p2 = __ldg(blk + 6), p3 = __ldg(blk + 7);
+    const uint32_t x0 = 0u - (~c & 1u), x1 = 0u - ((~c >> 1) & 1u);      // all ones where bit k of c is 0
+    const uint32_t x2 = 0u - ((~c >> 2) & 1u), x3 = 0u - ((~c >> 3) & 1u);
+    b.m0 = (p0.x ^ x0) & (p1.x ^ x1) & (p2.x ^ x2) & (p3.x ^ x3);
+    b.m1 = (p0.y ^ x0) & (p1.y ^ x1) & (p2.y ^ x2) & (p3.y ^ x3);
+    b.m2 = (p0.z ^ x0) & (p1.z ^ x1) & (p2.z ^ x2) & (p3.z ^ x3);
+    b.m3 = (p0.w ^ x0) & (p1.w ^ x1) & (p2.w ^ x2) & (p3.w ^ x3);
+    return b;
+}
+
+// cnt + #{rows p in [0, r] of the block holding the code}
+__device__ __forceinline__ uint32_t rank_in_block(const BlockBits &b, uint32_t r) {
+    // 128-bit mask of bits 0..r as four words, branch-free: word w gets clamp(r+1-32w, 0, 32) low bits
+    const int n = (int)r + 1;
+    const uint32_t k0 = n >= 32 ? ~0u : ((1u << n) - 1u);
+    const int n1 = n - 32, n2 = n - 64, n3 = n - 96;
+    const uint32_t k1 = n1 >= 32 ? ~0u : (n1 <= 0 ? 0u : ((1u << n1) - 1u));
+    const uint32_t k2 = n2 >= 32 ? ~0u : (n2 <= 0 ? 0u : ((1u << n2) - 1u));
+    const uint32_t k3 = n3 >= 32 ? ~0u : (n3 <= 0 ? 0u : ((1u << n3) - 1u));
+    return b.cnt + __popc(b.m0 & k0) + __popc(b.m1 & k1) + __popc(b.m2 & k2) + __popc(b.m3 & k3);
+}
+
+// O(c, i), c in 1..15 (bwt.c:348-372).
+template <class T>
+__device__ __forceinline__ T occ1(const IndexView &ix, const T *sC, uint32_t c, T i) {
+    const T last = (T)(ix.length - 1);
+    const bool top = (i == last), neg = (i == (T)~(T)0);
+    const T ii = (top || neg) ? (T)0 : i;
+    const BlockBits b = load_block(ix.blocks + (size_t)(ii >> 7) * 8, c);
+    const uint32_t v = rank_in_block(b, (uint32_t)(ii & 127u));
+    return top ? (T)(sC[c + 1] - sC[c]) : (neg ? (T)0 : (T)v);
+}
+
+// O(c, iL) and O(c, iU) for the two ends of one interval.  When both rows fall into the same
+// block (the common case once the interval is narrow) the block is loaded and matched once.
+template <class T>
+__device__ __forceinline__ void occ_pair(const IndexView &ix, const T *sC, uint32_t c, T iL, T iU, T &oL, T &oU) {
+    const T last = (T)(ix.length - 1), none = (T)~(T)0;
+    const bool topL = (iL == last), negL = (iL == none), topU = (iU == last), negU = (iU == none);
+    const T aL = (topL || negL) ? (T)0 : iL, aU = (topU || negU) ? (T)0 : iU;
+    const BlockBits bu = load_block(ix.blocks + (size_t)(aU >> 7) * 8, c);
+    const uint32_t vU = rank_in_block(bu, (uint32_t)(aU & 127u));
+    uint32_t vL;
+    if ((aL >> 7) == (aU >> 7)) {
+        vL = rank_in_block(bu, (uint32_t)(aL & 127u));
+    } else {
+        const BlockBits bl = load_block(ix.blocks + (size_t)(aL >> 7) * 8, c);
+        vL = rank_in_block(bl, (uint32_t)(aL & 127u));
+    }
+    const T tot = (T)(sC[c + 1] - sC[c]);
+    oL = topL ? tot : (negL ? (T)0 : (T)vL);
+    oU = topU ? tot : (negU ? (T)0 : (T)vU);
 }
 
 // occ[j] of O_alphabet(i, inc) for one code j (bwt.c:374-438) including quirk Q1: codes 5,9,11,13
 // get neither the in-block count nor the checkpoint, only the "checkpoint symbol" decrement
-// (bwt.c:427-435,780), in wrapping u64 arithmetic.
-__device__ __forceinline__ uint64_t occ_alpha(const IndexView &ix, const uint64_t *sC, uint32_t j, uint64_t i,
-                                              uint32_t inc) {
-    const bool top = (i == ix.length - 1), neg = (i == ~0ull);
-    const uint64_t ii = (top || neg) ? 0ull : i;
-    uint32_t first;
-    const uint32_t v = block_rank(ix.blocks + (ii >> 7) * 8, j, (uint32_t)(ii & 127u), first);
+// (bwt.c:427-435,780), in wrapping arithmetic of the reference's u64 (low bits are what matter:
+// the values are only compared L<=U and stored; for T=uint32_t see k_align's idx32 precondition).
+template <class T>
+__device__ __forceinline__ T occ_alpha(const IndexView &ix, const T *sC, uint32_t j, T i, uint32_t inc) {
+    const T last = (T)(ix.length - 1);
+    const bool top = (i == last), neg = (i == (T)~(T)0);
+    const T ii = (top || neg) ? (T)0 : i;
+    const BlockBits b = load_block(ix.blocks + (size_t)(ii >> 7) * 8, j);
+    const uint32_t v = rank_in_block(b, (uint32_t)(ii & 127u));
     const bool quirk = (0x2A20u >> j) & 1u;
-    const uint64_t mid = quirk ? (sC[j] - (uint64_t)first) : (sC[j] + (uint64_t)v);
-    const uint64_t r = top ? sC[j + 1] : (neg ? sC[j] : mid);
-    return r + inc;
+    const T mid = quirk ? (T)(sC[j] - (T)(b.m0 & 1u)) : (T)(sC[j] + (T)v);
+    const T r = top ? sC[j + 1] : (neg ? sC[j] : mid);
+    return (T)(r + inc);
 }
 
 // ---- interval lists: first SL entries in shared memory, the rest in a per-warp HBM scratch -------
+template <class T>
 struct ListStore {
-    ulonglong2 *s;   // [2][SL]
-    ulonglong2 *g;   // [2][cap]
+    typedef typename Pair<T>::type P;
+    P *s;   // [2][SL]
+    P *g;   // [2][cap]
     int cap;
 };
-__device__ __forceinline__ ulonglong2 lget(const ListStore &ls, int which, int k) {
+template <class T>
+__device__ __forceinline__ typename Pair<T>::type lget(const ListStore<T> &ls, int which, int k) {
     return k < SL ? ls.s[which * SL + k] : ls.g[(size_t)which * ls.cap + k];
 }
-__device__ __forceinline__ void lset(const ListStore &ls, int which, int k, ulonglong2 v) {
+template <class T>
+__device__ __forceinline__ void lset(const ListStore<T> &ls, int which, int k, T L, T U) {
+    typename Pair<T>::type v;
+    v.x = L;
+    v.y = U;
     if (k < SL) ls.s[which * SL + k] = v;
     else ls.g[(size_t)which * ls.cap + k] = v;
 }
 
 // nucl_bases_table (io.h:102-106) packed one nibble per entry, rows in nt4 order A,G,C,T
 __device__ __forceinline__ uint32_t compat_codes(uint32_t c) {
-    return c == 0 ? 0xFEDCB98u : (c == 1 ? 0xDCB5432u : (c == 2 ? 0xB987654u : 0xED96521u));
+    const uint32_t lo = (c & 1u) ? 0xDCB5432u : 0xFEDCB98u;   // G : A
+    const uint32_t hi = (c & 1u) ? 0xED96521u : 0xB987654u;   // T : C
+    return (c & 2u) ? hi : lo;
 }
 
 // One backward-extension step of list `cur` (n_cur intervals) by read base c (0..3) into list cur^1.
@@ -111,55 +171,58 @@ __device__ __forceinline__ uint32_t compat_codes(uint32_t c) {
 // (interval order x code ascending) and an item merges into its predecessor iff L == prev.U + 1
 // (add_sa_interval, align.c:93-110): ballots find run heads, shuffles fetch each run's last U.
 // Returns the new list length, or -1 if it exceeds ls.cap.  sumw = wrapped int sum of widths.
-__device__ __forceinline__ int extend_step(const IndexView &ix, const uint64_t *sC, const ListStore &ls, int cur,
+template <class T>
+__device__ __forceinline__ int extend_step(const IndexView &ix, const T *sC, const ListStore<T> &ls, int cur,
                                            int n_cur, uint32_t c, uint32_t &sumw, uint32_t &nloads) {
     const uint32_t lane = lane_id();
     const uint32_t g = lane / 7u, k = lane - g * 7u;
     const uint32_t code = (compat_codes(c) >> (4u * k)) & 15u;
-    const uint64_t Cc = sC[code];
+    const T Cc = sC[code];
     const int nxt = cur ^ 1;
     const uint32_t lt = (1u << lane) - 1u;
     int n_next = 0;
     bool tail_valid = false;
-    uint64_t tailU = 0;
+    T tailU = 0;
     uint32_t acc = 0;
     for (int base = 0; base < n_cur; base += 4) {
         const int s = base + (int)g;
         const bool active = (g < 4u) && (s < n_cur);
-        const ulonglong2 iv = active ? lget(ls, cur, s) : make_ulonglong2(1ull, 0ull);
-        const uint64_t nL = Cc + occ1(ix, sC, code, iv.x - 1) + 1;
-        const uint64_t nU = Cc + occ1(ix, sC, code, iv.y);
+        typename Pair<T>::type iv;
+        iv.x = 1; iv.y = 0;
+        if (active) iv = lget(ls, cur, s);
+        T oL, oU;
+        occ_pair<T>(ix, sC, code, (T)(iv.x - 1), iv.y, oL, oU);
+        const T nL = (T)(Cc + oL + 1), nU = (T)(Cc + oU);
         const bool valid = active && (nL <= nU);
         nloads += active ? 2u : 0u;
 
         const uint32_t V = __ballot_sync(FULL, valid);
         const uint32_t below = V & lt;
-        const uint64_t prevU = shfl64(nU, below ? (31 - __clz(below)) : 0);
+        const T prevU = shfl(nU, below ? (31 - __clz(below)) : 0);
         const bool cmp_ok = below ? true : tail_valid;
-        const uint64_t cmpU = below ? prevU : tailU;
-        const bool head = valid && !(cmp_ok && nL == cmpU + 1);
+        const T cmpU = below ? prevU : tailU;
+        const bool head = valid && !(cmp_ok && nL == (T)(cmpU + 1));
         const uint32_t H = __ballot_sync(FULL, head);
         // last valid lane of my run = highest valid lane below the next head
         const uint32_t above = H & ~((2u << lane) - 1u);
         const uint32_t lim = above ? ((1u << (__ffs(above) - 1)) - 1u) : FULL;
         const uint32_t runV = V & lim;
-        const uint64_t endU = shfl64(nU, runV ? (31 - __clz(runV)) : 0);
+        const T endU = shfl(nU, runV ? (31 - __clz(runV)) : 0);
         // valid lanes before the first head extend the interval stored last
         const uint32_t leadV = V & (H ? ((1u << (__ffs(H) - 1)) - 1u) : FULL);
         if (leadV) {
-            const uint64_t nu = shfl64(nU, 31 - __clz(leadV));
+            const T nu = shfl(nU, 31 - __clz(leadV));
             if (lane == 0) {
-                ulonglong2 t = lget(ls, nxt, n_next - 1);
-                t.y = nu;
-                lset(ls, nxt, n_next - 1, t);
+                typename Pair<T>::type t = lget(ls, nxt, n_next - 1);
+                lset<T>(ls, nxt, n_next - 1, t.x, nu);
             }
         }
         const int nh = __popc(H);
         if (n_next + nh > ls.cap) return -1;
-        if (head) lset(ls, nxt, n_next + __popc(H & lt), make_ulonglong2(nL, endU));
+        if (head) lset<T>(ls, nxt, n_next + __popc(H & lt), nL, endU);
         n_next += nh;
         if (V) {
-            tailU = shfl64(nU, 31 - __clz(V));
+            tailU = shfl(nU, 31 - __clz(V));
             tail_valid = true;
         }
         acc += valid ? (uint32_t)(nU - nL + 1) : 0u;

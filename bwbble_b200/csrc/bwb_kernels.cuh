@@ -57,29 +57,31 @@ __global__ void k_relayout(const uint32_t *__restrict__ bwt, uint64_t num_words,
 }
 
 // ---------------------------------------------------------------------------------------------
-// K1: rank primitives
+// K1: rank primitives (tests + the Occ-gather micro-benchmark).  T = SA-coordinate type.
 // ---------------------------------------------------------------------------------------------
+template <class T>
 __global__ void k_occ(IndexView ix, const uint8_t *__restrict__ code, const uint64_t *__restrict__ pos, uint64_t n,
                       uint64_t *__restrict__ out) {
-    __shared__ uint64_t sC[17];
-    if (threadIdx.x < 17) sC[threadIdx.x] = ix.C[threadIdx.x];
-    __syncthreads();
+    __shared__ T sC[17];
+    stage_C<T>(ix, sC);
     const uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= n) return;
-    out[q] = occ1(ix, sC, code[q] & 15u, pos[q]);
+    const uint64_t p = pos[q];
+    out[q] = (uint64_t)occ1<T>(ix, sC, code[q] & 15u, p == ~0ull ? (T)~(T)0 : (T)p);
 }
 
-// 16 lanes per query, lane j computes occ[j]
+// 16 lanes per query, lane j computes occ[j]; results widened the way the reference's u64 wraps
+template <class T>
 __global__ void k_occ_alphabet(IndexView ix, const uint64_t *__restrict__ pos, uint64_t n, uint32_t inc,
                                uint64_t *__restrict__ out) {
-    __shared__ uint64_t sC[17];
-    if (threadIdx.x < 17) sC[threadIdx.x] = ix.C[threadIdx.x];
-    __syncthreads();
+    __shared__ T sC[17];
+    stage_C<T>(ix, sC);
     const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const uint64_t q = t >> 4;
     const uint32_t j = (uint32_t)(t & 15u);
     if (q >= n) return;
-    out[q * 16 + j] = j ? occ_alpha(ix, sC, j, pos[q], inc) : 0ull;
+    const uint64_t p = pos[q];
+    out[q * 16 + j] = j ? (uint64_t)occ_alpha<T>(ix, sC, j, p == ~0ull ? (T)~(T)0 : (T)p, inc) : 0ull;
 }
 
 __device__ __forceinline__ uint64_t mix64(uint64_t x) {   // splitmix64 finaliser
@@ -90,14 +92,13 @@ __device__ __forceinline__ uint64_t mix64(uint64_t x) {   // splitmix64 finalise
 }
 
 // Occ-gather micro-benchmark: uniform random positions over the whole index.
-// mode 0: one thread = one O(c,i) query.  mode 1: 16 lanes = one O_alphabet(i) query.
-// CHAIN dependent queries per thread (next position derived from the previous result) model the
-// search's dependent gathers; CHAIN=1 is the pure throughput case.
+// MODE 0: one thread = one O(c,i) query.  MODE 1: 16 lanes = one O_alphabet(i) query.
+// `chain` dependent queries per thread (next position derived from the previous result) model the
+// search's dependent gathers; chain=1 is the pure throughput case.
 template <int MODE>
 __global__ void k_occ_bench(IndexView ix, uint64_t n, uint64_t seed, int chain, unsigned long long *__restrict__ sink) {
     __shared__ uint64_t sC[17];
-    if (threadIdx.x < 17) sC[threadIdx.x] = ix.C[threadIdx.x];
-    __syncthreads();
+    stage_C<uint64_t>(ix, sC);
     const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const uint64_t q = MODE ? (t >> 4) : t;
     if (q >= n) return;
@@ -106,10 +107,10 @@ __global__ void k_occ_bench(IndexView ix, uint64_t n, uint64_t seed, int chain, 
     for (int s = 0; s < chain; s++) {
         const uint64_t pos = h % (ix.length - 1);
         uint64_t v;
-        if (MODE) v = occ_alpha(ix, sC, (uint32_t)(t & 15u), pos, 0);
-        else v = occ1(ix, sC, 1u + (uint32_t)((h >> 58) % 15u), pos);
+        if (MODE) v = occ_alpha<uint64_t>(ix, sC, (uint32_t)(t & 15u), pos, 0);
+        else v = occ1<uint64_t>(ix, sC, 1u + (uint32_t)((h >> 58) % 15u), pos);
         acc += v;
-        h = mix64(h ^ v);
+        h = mix64(h ^ (MODE ? __shfl_sync(FULL, (uint32_t)v, (threadIdx.x & 16u) + 7) : v));
     }
     if (acc == 0x123456789ABCDEFull) atomicAdd(sink, acc);      // keeps the loads alive
     if ((t & 0xFFFFF) == 0) atomicAdd(sink, acc);
@@ -123,10 +124,11 @@ __device__ __forceinline__ uint32_t nt4_compl(uint32_t c) { return c > 3u ? 4u :
 // exact_match_bounded(read, i0, L, U) (exact_match.c:66-119) on the warp's lists.
 // use_rc: read base r is the complement of seq[len-1-r] (the search runs on the reverse complement).
 // Returns list length (0 = no match, -1 = list capacity exceeded); `cur` says which list holds it.
-__device__ __forceinline__ int exact_from(const IndexView &ix, const uint64_t *sC, const ListStore &ls,
-                                          const uint8_t *seq, int len, bool use_rc, int i0, uint64_t L, uint64_t U,
-                                          int &cur, uint32_t &nloads, uint32_t &maxlist) {
-    if (lane_id() == 0) lset(ls, 0, 0, make_ulonglong2(L, U));
+template <class T>
+__device__ __forceinline__ int exact_from(const IndexView &ix, const T *sC, const ListStore<T> &ls,
+                                          const uint8_t *seq, int len, bool use_rc, int i0, T L, T U, int &cur,
+                                          uint32_t &nloads, uint32_t &maxlist) {
+    if (lane_id() == 0) lset<T>(ls, 0, 0, L, U);
     __syncwarp();
     cur = 0;
     int n = 1;
@@ -134,7 +136,7 @@ __device__ __forceinline__ int exact_from(const IndexView &ix, const uint64_t *s
         const uint32_t c = use_rc ? nt4_compl(seq[len - 1 - r]) : (uint32_t)seq[r];
         if (c > 3u) return 0;                        // N in the read never matches
         uint32_t sumw;
-        n = extend_step(ix, sC, ls, cur, n, c, sumw, nloads);
+        n = extend_step<T>(ix, sC, ls, cur, n, c, sumw, nloads);
         if (n < 0) return -1;
         cur ^= 1;
         if ((uint32_t)n > maxlist) maxlist = (uint32_t)n;
@@ -144,11 +146,12 @@ __device__ __forceinline__ int exact_from(const IndexView &ix, const uint64_t *s
 }
 
 // calculate_d (inexact_match.c:208-254) on seq[0..dlen): D[k] = {num_diff, sa_intv_width}.
-__device__ __forceinline__ bool calc_d(const IndexView &ix, const uint64_t *sC, const ListStore &ls,
-                                       const uint8_t *seq, int dlen, int2 *D, uint32_t &nloads, uint32_t &maxlist) {
+template <class T>
+__device__ __forceinline__ bool calc_d(const IndexView &ix, const T *sC, const ListStore<T> &ls, const uint8_t *seq,
+                                       int dlen, int2 *D, uint32_t &nloads, uint32_t &maxlist) {
     const uint32_t lane = lane_id();
-    const ulonglong2 full = make_ulonglong2(0ull, ix.length - 1);
-    if (lane == 0) lset(ls, 0, 0, full);
+    const T fullU = (T)(ix.length - 1);
+    if (lane == 0) lset<T>(ls, 0, 0, (T)0, fullU);
     __syncwarp();
     int cur = 0, n = 1, z = 0;
     for (int i = dlen - 1; i >= 0; i--) {
@@ -156,13 +159,13 @@ __device__ __forceinline__ bool calc_d(const IndexView &ix, const uint64_t *sC, 
         uint32_t num = 0;
         int nn = 0;
         if (c <= 3u) {
-            nn = extend_step(ix, sC, ls, cur, n, c, num, nloads);
+            nn = extend_step<T>(ix, sC, ls, cur, n, c, num, nloads);
             if (nn < 0) return false;
             cur ^= 1;
             if ((uint32_t)nn > maxlist) maxlist = (uint32_t)nn;
         }
         if (nn == 0) {                               // restart from the full range, one more difference
-            if (lane == 0) lset(ls, cur, 0, full);
+            if (lane == 0) lset<T>(ls, cur, 0, (T)0, fullU);
             __syncwarp();
             nn = 1;
             z++;
@@ -197,7 +200,7 @@ struct ListArgs {
     const uint8_t *seq;
     const uint64_t *offsets;
     uint32_t n_reads;
-    ulonglong2 *glists;      // [n_warps][2][list_cap]
+    void *glists;            // [n_warps][2][list_cap] of Pair<T> (allocated for 16-byte pairs)
     int list_cap;
     int max_len;
     int use_len;             // K3: prefix length (0 = whole read)
@@ -212,27 +215,29 @@ struct ListArgs {
     uint32_t *status;
 };
 
-__device__ __forceinline__ void warp_smem(unsigned char *smem, int per_warp, ListStore &ls, unsigned char *&rest) {
-    unsigned char *base = smem + (size_t)(threadIdx.x >> 5) * per_warp;
-    ls.s = reinterpret_cast<ulonglong2 *>(base);
-    rest = base + 2 * SL * sizeof(ulonglong2);
+constexpr int LIST_SMEM_BYTES = 2 * SL * (int)sizeof(ulonglong2);   // sized for the 64-bit pairs
+
+template <class T>
+__device__ __forceinline__ void warp_lists(unsigned char *wbase, void *glists, uint32_t gw, int cap, ListStore<T> &ls) {
+    typedef typename Pair<T>::type P;
+    ls.s = reinterpret_cast<P *>(wbase);
+    ls.g = reinterpret_cast<P *>(glists) + (size_t)gw * 2 * cap;
+    ls.cap = cap;
 }
 
+template <class T>
 __global__ void k_exact(ListArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
-    __shared__ uint64_t sC[17];
-    if (threadIdx.x < 17) sC[threadIdx.x] = a.ix.C[threadIdx.x];
-    __syncthreads();
+    __shared__ T sC[17];
+    stage_C<T>(a.ix, sC);
     const int wpb = blockDim.x >> 5;
-    const int per_warp = 2 * SL * (int)sizeof(ulonglong2) + ((a.max_len + 15) & ~15);
+    const int per_warp = LIST_SMEM_BYTES + ((a.max_len + 15) & ~15);
     const uint32_t gw = blockIdx.x * wpb + (threadIdx.x >> 5);
     const uint32_t nw = gridDim.x * wpb;
-    ListStore ls;
-    unsigned char *rest;
-    warp_smem(smem, per_warp, ls, rest);
-    ls.g = a.glists + (size_t)gw * 2 * a.list_cap;
-    ls.cap = a.list_cap;
-    uint8_t *sseq = rest;
+    unsigned char *wbase = smem + (size_t)(threadIdx.x >> 5) * per_warp;
+    ListStore<T> ls;
+    warp_lists<T>(wbase, a.glists, gw, a.list_cap, ls);
+    uint8_t *sseq = wbase + LIST_SMEM_BYTES;
     const uint32_t lane = lane_id();
     for (uint32_t r = gw; r < a.n_reads; r += nw) {
         const uint64_t off = a.offsets[r];
@@ -240,35 +245,36 @@ __global__ void k_exact(ListArgs a) {
         stage_read(a.seq + off, len, sseq);
         int cur;
         uint32_t nl = 0, ml = 0;
-        int n = exact_from(a.ix, sC, ls, sseq, len, false, len - 1, 0ull, a.ix.length - 1, cur, nl, ml);
+        int n = exact_from<T>(a.ix, sC, ls, sseq, len, false, len - 1, (T)0, (T)(a.ix.length - 1), cur, nl, ml);
         if (n < 0) { if (lane == 0) atomicExch(a.status, (uint32_t)(-BWB_ERR_CAPACITY)); n = 0; }
         unsigned long long base = 0;
         if (lane == 0) base = atomicAdd(a.out_cursor, (unsigned long long)n);
         base = shfl64(base, 0);
         if (base + n <= a.out_cap)
-            for (int k = lane; k < n; k += 32) a.out_iv[base + k] = lget(ls, cur, k);
+            for (int k = lane; k < n; k += 32) {
+                const typename Pair<T>::type iv = lget<T>(ls, cur, k);
+                a.out_iv[base + k] = make_ulonglong2((unsigned long long)iv.x, (unsigned long long)iv.y);
+            }
         if (lane == 0) { a.read_off[r] = base; a.read_cnt[r] = (uint32_t)n; }
         __syncwarp();
     }
 }
 
+template <class T>
 __global__ void k_calc_d(ListArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
-    __shared__ uint64_t sC[17];
-    if (threadIdx.x < 17) sC[threadIdx.x] = a.ix.C[threadIdx.x];
-    __syncthreads();
+    __shared__ T sC[17];
+    stage_C<T>(a.ix, sC);
     const int wpb = blockDim.x >> 5;
     const int dbytes = ((a.max_len + 1) * 8 + 15) & ~15;
-    const int per_warp = 2 * SL * (int)sizeof(ulonglong2) + dbytes + ((a.max_len + 15) & ~15);
+    const int per_warp = LIST_SMEM_BYTES + dbytes + ((a.max_len + 15) & ~15);
     const uint32_t gw = blockIdx.x * wpb + (threadIdx.x >> 5);
     const uint32_t nw = gridDim.x * wpb;
-    ListStore ls;
-    unsigned char *rest;
-    warp_smem(smem, per_warp, ls, rest);
-    ls.g = a.glists + (size_t)gw * 2 * a.list_cap;
-    ls.cap = a.list_cap;
-    int2 *D = reinterpret_cast<int2 *>(rest);
-    uint8_t *sseq = rest + dbytes;
+    unsigned char *wbase = smem + (size_t)(threadIdx.x >> 5) * per_warp;
+    ListStore<T> ls;
+    warp_lists<T>(wbase, a.glists, gw, a.list_cap, ls);
+    int2 *D = reinterpret_cast<int2 *>(wbase + LIST_SMEM_BYTES);
+    uint8_t *sseq = wbase + LIST_SMEM_BYTES + dbytes;
     const uint32_t lane = lane_id();
     for (uint32_t r = gw; r < a.n_reads; r += nw) {
         const uint64_t off = a.offsets[r];
@@ -276,7 +282,7 @@ __global__ void k_calc_d(ListArgs a) {
         const int dlen = (a.use_len > 0 && a.use_len < len) ? a.use_len : len;
         stage_read(a.seq + off, len, sseq);
         uint32_t nl = 0, ml = 0;
-        if (!calc_d(a.ix, sC, ls, sseq, dlen, D, nl, ml)) {
+        if (!calc_d<T>(a.ix, sC, ls, sseq, dlen, D, nl, ml)) {
             if (lane == 0) atomicExch(a.status, (uint32_t)(-BWB_ERR_CAPACITY));
             continue;
         }
@@ -289,14 +295,16 @@ __global__ void k_calc_d(ListArgs a) {
 // ---------------------------------------------------------------------------------------------
 // K4: calculate_d + inexact_match, persistent warp per read
 // ---------------------------------------------------------------------------------------------
-// Partial alignment (aln_entry_t, align.h:100-119) packed into 32 bytes.  The 256-byte edit path of
-// the reference is all STATE_M except for <= max_gapo runs of I/D, so only the runs are kept;
-// aln_length = readLen - i + (#D steps).  num_snps is never read by a decision nor serialised.
-//   a.x  L[31:0]            a.y  U[31:0]
-//   a.z  L[39:32] | U[39:32]<<8 | i<<16 | state<<24 | nruns<<26
-//   a.w  mm | go<<8 | ge<<16 | nD<<24
-//   b.x..b.w  gap runs: start | len<<8 | state<<16
-constexpr int CHUNK_ENTRIES = 32;                 // 32 entries x 32 B = 1 KB per chunk
+// Partial alignment (aln_entry_t, align.h:100-119) kept PACKED, in registers and in the heap.  The
+// reference's 256-byte edit path is all STATE_M except for <= max_gapo runs of I/D, so only the runs
+// are kept; aln_length = readLen - i + (#D steps); the score is the bucket index; num_snps is never
+// read by a decision nor serialised; the number of runs equals num_gapo.
+//   z = i | mm<<8 | ge<<16 | go<<24 (4 bits) | state<<28 (2 bits)
+//   w = nD | run0.start<<8 | run0.len<<16 | run0.state<<24
+//   r1..r3 = runs 1..3 as start | len<<8 | state<<16                      (WIDE format only)
+// Compact format (T=uint32_t, max_gapo<=1): one uint4 {L, U, z, w}             = 16 bytes
+// Wide format    (T=uint64_t or max_gapo>1): {Llo, Ulo, Lhi|Uhi<<8, z} {w,r1,r2,r3} = 32 bytes
+constexpr int CHUNK_ENTRIES = 32;
 constexpr uint32_t NO_CHUNK = 0xffffffffu;
 
 struct AlignArgs {
@@ -312,9 +320,9 @@ struct AlignArgs {
     int max_len;
     uint32_t *queue;          // next read to take
     // per-warp scratch
-    ulonglong2 *glists;
+    void *glists;
     int list_cap;
-    uint4 *chunks;            // [n_chunks][2*CHUNK_ENTRIES]
+    uint4 *chunks;            // [n_chunks][CHUNK_ENTRIES] entries of 16 or 32 bytes
     uint32_t *chunk_link;     // [n_chunks]
     uint32_t chunks_per_warp;
     uint32_t n_chunks;
@@ -333,27 +341,38 @@ struct AlignArgs {
     int smem_per_warp, off_D, off_Ds, off_bk, off_seq;
 };
 
-struct Entry {
-    uint64_t L, U;
-    uint32_t i, state, nruns, mm, go, ge, nD;
-    uint32_t run[BWB_MAX_GAP_RUNS];
+template <class T>
+struct PE {                   // packed entry
+    T L, U;
+    uint32_t z, w, r1, r2, r3;
 };
 
-__device__ __forceinline__ void pack_entry(const Entry &e, uint4 &a, uint4 &b) {
-    a.x = (uint32_t)e.L;
-    a.y = (uint32_t)e.U;
-    a.z = (uint32_t)(e.L >> 32) | ((uint32_t)(e.U >> 32) << 8) | (e.i << 16) | (e.state << 24) | (e.nruns << 26);
-    a.w = e.mm | (e.go << 8) | (e.ge << 16) | (e.nD << 24);
-    b.x = e.run[0]; b.y = e.run[1]; b.z = e.run[2]; b.w = e.run[3];
+template <bool WIDE> struct Coord { typedef uint32_t type; };
+template <> struct Coord<true> { typedef uint64_t type; };
+
+template <bool WIDE>
+__device__ __forceinline__ void store_entry(uint4 *chunks, uint32_t ch, uint32_t slot, const PE<typename Coord<WIDE>::type> &e) {
+    if constexpr (WIDE) {
+        uint4 *dst = chunks + ((size_t)ch * CHUNK_ENTRIES + slot) * 2;
+        dst[0] = make_uint4((uint32_t)e.L, (uint32_t)e.U,
+                            ((uint32_t)(e.L >> 32) & 0xffu) | (((uint32_t)(e.U >> 32) & 0xffu) << 8), e.z);
+        dst[1] = make_uint4(e.w, e.r1, e.r2, e.r3);
+    } else {
+        chunks[(size_t)ch * CHUNK_ENTRIES + slot] = make_uint4(e.L, e.U, e.z, e.w);
+    }
 }
-__device__ __forceinline__ void unpack_entry(const uint4 &a, const uint4 &b, Entry &e) {
-    e.L = (uint64_t)a.x | ((uint64_t)(a.z & 0xffu) << 32);
-    e.U = (uint64_t)a.y | ((uint64_t)((a.z >> 8) & 0xffu) << 32);
-    e.i = (a.z >> 16) & 0xffu;
-    e.state = (a.z >> 24) & 3u;
-    e.nruns = (a.z >> 26) & 7u;
-    e.mm = a.w & 0xffu; e.go = (a.w >> 8) & 0xffu; e.ge = (a.w >> 16) & 0xffu; e.nD = (a.w >> 24) & 0xffu;
-    e.run[0] = b.x; e.run[1] = b.y; e.run[2] = b.z; e.run[3] = b.w;
+template <bool WIDE>
+__device__ __forceinline__ void load_entry(const uint4 *chunks, uint32_t ch, uint32_t slot, PE<typename Coord<WIDE>::type> &e) {
+    if constexpr (WIDE) {
+        const uint4 *src = chunks + ((size_t)ch * CHUNK_ENTRIES + slot) * 2;
+        const uint4 a = src[0], b = src[1];
+        e.L = (uint64_t)a.x | ((uint64_t)(a.z & 0xffu) << 32);
+        e.U = (uint64_t)a.y | ((uint64_t)((a.z >> 8) & 0xffu) << 32);
+        e.z = a.w; e.w = b.x; e.r1 = b.y; e.r2 = b.z; e.r3 = b.w;
+    } else {
+        const uint4 a = chunks[(size_t)ch * CHUNK_ENTRIES + slot];
+        e.L = a.x; e.U = a.y; e.z = a.z; e.w = a.w; e.r1 = e.r2 = e.r3 = 0;
+    }
 }
 
 // per-warp bucket heap (priority_heap_t, inexact_match.h:16-34): bucket = LIFO stack of chunks
@@ -361,7 +380,7 @@ struct Heap {
     uint32_t *cnt, *top, *bot;    // shared memory, nb each
     uint4 *chunks;
     uint32_t *link;
-    uint32_t priv_lo, priv_hi;    // this warp's private chunk range
+    uint32_t priv_hi;             // end of this warp's private chunk range
     uint32_t bump;                // next never-used private chunk
     uint32_t free_head;           // recycled chunks (linked through `link`)
     uint32_t *overflow_cursor;
@@ -373,10 +392,11 @@ struct Heap {
 
 // all lanes call; returns the same chunk id on every lane (NO_CHUNK when the pool is exhausted)
 __device__ __forceinline__ uint32_t chunk_alloc(Heap &h) {
-    uint32_t id = NO_CHUNK;
+    uint32_t id = NO_CHUNK, nx = 0;
     if (lane_id() == 0) {
         if (h.free_head != NO_CHUNK) {
             id = h.free_head;
+            nx = h.link[id];
         } else if (h.bump < h.priv_hi) {
             id = h.bump;
         } else {
@@ -385,15 +405,8 @@ __device__ __forceinline__ uint32_t chunk_alloc(Heap &h) {
         }
     }
     id = __shfl_sync(FULL, id, 0);
-    if (id != NO_CHUNK) {
-        if (h.free_head != NO_CHUNK) {           // uniform: every lane tracks the allocator state
-            uint32_t nx = 0;
-            if (lane_id() == 0) nx = h.link[id];
-            h.free_head = __shfl_sync(FULL, nx, 0);
-        } else if (h.bump < h.priv_hi) {
-            h.bump++;
-        }
-    }
+    if (h.free_head != NO_CHUNK) h.free_head = __shfl_sync(FULL, nx, 0);     // uniform branch
+    else if (h.bump < h.priv_hi) h.bump++;
     return id;
 }
 
@@ -407,28 +420,29 @@ __device__ __forceinline__ void heap_reset(Heap &h) {
 // give every chunk still held by a bucket back to the warp's free list (O(1) per bucket)
 __device__ __forceinline__ void heap_release(Heap &h) {
     __syncwarp();
+    uint32_t fh = h.free_head;
     if (lane_id() == 0) {
-        uint32_t fh = h.free_head;
         for (int b = 0; b < h.nb; b++) {
             if (h.cnt[b]) {
                 h.link[h.bot[b]] = fh;
                 fh = h.top[b];
             }
         }
-        h.free_head = fh;
     }
-    h.free_head = __shfl_sync(FULL, h.free_head, 0);
+    h.free_head = __shfl_sync(FULL, fh, 0);
     __syncwarp();
 }
 
-// Push the entries of the lanes in `grp` (same score `sc` on all of them) in lane order
-// (heap_push, inexact_match.c:548-591).  Returns false if no chunk could be allocated.
-__device__ __forceinline__ bool heap_push_group(Heap &h, uint32_t grp, int sc, const Entry &e) {
+// Push the entries of the lanes in `grp` (all with score `sc`) in lane order (heap_push,
+// inexact_match.c:548-591).  Returns false if no chunk could be allocated.
+template <bool WIDE>
+__device__ __forceinline__ bool heap_push_group(Heap &h, uint32_t grp, int sc, const PE<typename Coord<WIDE>::type> &e) {
     const uint32_t lane = lane_id();
-    const int k = __popc(grp);
+    const uint32_t k = __popc(grp);
     const uint32_t cnt = h.cnt[sc];
     const uint32_t oldtop = h.top[sc];
-    const bool need_new = (cnt == 0) || (((cnt + k - 1) / CHUNK_ENTRIES) > ((cnt - 1) / CHUNK_ENTRIES));
+    const uint32_t topidx = (cnt - 1u) >> 5;                   // chunk ordinal of the current top (cnt>0)
+    const bool need_new = (cnt == 0u) || (((cnt + k - 1u) >> 5) != topidx);
     uint32_t newc = NO_CHUNK;
     if (need_new) {
         newc = chunk_alloc(h);
@@ -436,56 +450,48 @@ __device__ __forceinline__ bool heap_push_group(Heap &h, uint32_t grp, int sc, c
         if (lane == 0) {
             h.link[newc] = oldtop;
             h.top[sc] = newc;
-            if (cnt == 0) h.bot[sc] = newc;
+            if (cnt == 0u) h.bot[sc] = newc;
         }
     }
     if ((grp >> lane) & 1u) {
         const uint32_t pos = cnt + __popc(grp & ((1u << lane) - 1u));
-        const bool in_old = (cnt != 0) && ((pos / CHUNK_ENTRIES) == ((cnt - 1) / CHUNK_ENTRIES));
-        const uint32_t ch = in_old ? oldtop : newc;
-        uint4 a, b;
-        pack_entry(e, a, b);
-        uint4 *dst = h.chunks + ((size_t)ch * CHUNK_ENTRIES + (pos % CHUNK_ENTRIES)) * 2;
-        dst[0] = a;
-        dst[1] = b;
+        const bool in_old = (cnt != 0u) && ((pos >> 5) == topidx);
+        store_entry<WIDE>(h.chunks, in_old ? oldtop : newc, pos & 31u, e);
     }
     if (lane == 0) h.cnt[sc] = cnt + k;
-    h.n += k;
-    if (sc < h.best) h.best = sc;
+    h.n += (int)k;
+    h.best = min(h.best, sc);
     __syncwarp();
     return true;
 }
 
 // heap_pop (inexact_match.c:594-610): last entry of the lowest non-empty bucket; every lane gets it
-__device__ __forceinline__ int heap_pop(Heap &h, Entry &e) {
+template <bool WIDE>
+__device__ __forceinline__ int heap_pop(Heap &h, PE<typename Coord<WIDE>::type> &e) {
     const uint32_t lane = lane_id();
     const int b = h.best;
     const uint32_t cnt = h.cnt[b];
     const uint32_t ch = h.top[b];
-    const uint32_t slot = (cnt - 1) % CHUNK_ENTRIES;
-    const uint4 *src = h.chunks + ((size_t)ch * CHUNK_ENTRIES + slot) * 2;
-    const uint4 a = src[0], bb = src[1];
-    unpack_entry(a, bb, e);
+    const uint32_t slot = (cnt - 1u) & 31u;
+    load_entry<WIDE>(h.chunks, ch, slot, e);
     __syncwarp();
     h.n--;
-    if (slot == 0) {                                  // chunk is empty now: recycle it
-        uint32_t prev = 0;
+    if (slot == 0u) {                                 // chunk is empty now: recycle it
         if (lane == 0) {
-            prev = h.link[ch];
+            const uint32_t prev = h.link[ch];
             h.link[ch] = h.free_head;
             h.top[b] = prev;
-            if (cnt == 1) h.bot[b] = NO_CHUNK;
         }
         h.free_head = ch;
     }
-    if (lane == 0) h.cnt[b] = cnt - 1;
+    if (lane == 0) h.cnt[b] = cnt - 1u;
     __syncwarp();
-    if (cnt == 1) {                                   // bucket drained: find the next non-empty one
+    if (cnt == 1u) {                                  // bucket drained: find the next non-empty one
         int nbst = h.nb;
         if (h.n) {
             for (int s = b + 1; s < h.nb; s += 32) {
                 const int q = s + (int)lane;
-                const uint32_t m = __ballot_sync(FULL, q < h.nb && h.cnt[q] != 0);
+                const uint32_t m = __ballot_sync(FULL, q < h.nb && h.cnt[q] != 0u);
                 if (m) { nbst = s + __ffs(m) - 1; break; }
             }
         }
@@ -502,16 +508,18 @@ struct HitSink {
     int n;
 };
 
-// add_alignment (align.c:271-298) for `cnt` intervals held one per lane (lane k < cnt valid), in lane
-// order.  With gaps, an interval equal to an already recorded hit is dropped (align.c:273-280).
-__device__ __forceinline__ bool add_hits(HitSink &hs, const Entry &e, int score, uint32_t alen, uint32_t read_id,
-                                         bool have, uint64_t L, uint64_t U) {
+// add_alignment (align.c:271-298) for intervals held one per lane (`have` lanes), in lane order.
+// With gaps, an interval equal to an already recorded hit is dropped (align.c:273-280).
+template <class T>
+__device__ __forceinline__ bool add_hits(HitSink &hs, const PE<T> &e, int score, uint32_t alen, uint32_t read_id,
+                                         bool have, T L, T U) {
     const uint32_t lane = lane_id();
+    const uint32_t go = (e.z >> 24) & 15u;
     bool keep = have;
-    if (e.go) {
+    if (go) {
         for (int j = 0; j < hs.n; j++) {
             const uint64_t hl = hs.stage[j].L, hu = hs.stage[j].U;
-            if (hl == L && hu == U) keep = false;
+            if (hl == (uint64_t)L && hu == (uint64_t)U) keep = false;
         }
     }
     const uint32_t K = __ballot_sync(FULL, keep);
@@ -519,19 +527,20 @@ __device__ __forceinline__ bool add_hits(HitSink &hs, const Entry &e, int score,
     if (hs.n + nk > hs.cap) return false;
     if (keep) {
         bwb_hit h;
-        h.L = L; h.U = U; h.score = score;
-        h.num_mm = (uint8_t)e.mm; h.num_gapo = (uint8_t)e.go; h.num_gape = (uint8_t)e.ge;
+        h.L = (uint64_t)L; h.U = (uint64_t)U; h.score = score;
+        h.num_mm = (uint8_t)((e.z >> 8) & 0xffu); h.num_gapo = (uint8_t)go; h.num_gape = (uint8_t)((e.z >> 16) & 0xffu);
         h.aln_length = (uint8_t)alen;
-        h.n_runs = (uint8_t)e.nruns; h.pad[0] = h.pad[1] = h.pad[2] = 0;
+        h.n_runs = (uint8_t)go; h.pad[0] = h.pad[1] = h.pad[2] = 0;
+        h.read_id = read_id;
+        const uint32_t rr[BWB_MAX_GAP_RUNS] = {e.w >> 8, e.r1, e.r2, e.r3};
 #pragma unroll
         for (int r = 0; r < BWB_MAX_GAP_RUNS; r++) {
-            const uint32_t v = (uint32_t)r < e.nruns ? e.run[r] : 0u;
+            const uint32_t v = (uint32_t)r < go ? rr[r] : 0u;
             h.runs[r].start = (uint8_t)(v & 0xffu);
             h.runs[r].len = (uint8_t)((v >> 8) & 0xffu);
             h.runs[r].state = (uint8_t)((v >> 16) & 0xffu);
             h.runs[r].pad = 0;
         }
-        h.read_id = read_id;
         hs.stage[hs.n + __popc(K & ((1u << lane) - 1u))] = h;
     }
     hs.n += nk;
@@ -539,21 +548,24 @@ __device__ __forceinline__ bool add_hits(HitSink &hs, const Entry &e, int score,
     return true;
 }
 
-__global__ void __launch_bounds__(256) k_align(const __grid_constant__ AlignArgs a) {
+#ifndef BWB_K4_MIN_BLOCKS
+#define BWB_K4_MIN_BLOCKS 3
+#endif
+
+template <bool WIDE>
+__global__ void __launch_bounds__(256, BWB_K4_MIN_BLOCKS) k_align(const __grid_constant__ AlignArgs a) {
+    typedef typename Coord<WIDE>::type T;
     extern __shared__ __align__(16) unsigned char smem[];
-    __shared__ uint64_t sC[17];
-    if (threadIdx.x < 17) sC[threadIdx.x] = a.ix.C[threadIdx.x];
-    __syncthreads();
+    __shared__ T sC[17];
+    stage_C<T>(a.ix, sC);
 
     const uint32_t lane = lane_id();
     const int wpb = blockDim.x >> 5;
     const uint32_t gw = blockIdx.x * wpb + (threadIdx.x >> 5);
     unsigned char *wbase = smem + (size_t)(threadIdx.x >> 5) * a.smem_per_warp;
 
-    ListStore ls;
-    ls.s = reinterpret_cast<ulonglong2 *>(wbase);
-    ls.g = a.glists + (size_t)gw * 2 * a.list_cap;
-    ls.cap = a.list_cap;
+    ListStore<T> ls;
+    warp_lists<T>(wbase, a.glists, gw, a.list_cap, ls);
     int2 *D = reinterpret_cast<int2 *>(wbase + a.off_D);
     int2 *Ds = reinterpret_cast<int2 *>(wbase + a.off_Ds);
     uint8_t *sseq = wbase + a.off_seq;
@@ -564,9 +576,8 @@ __global__ void __launch_bounds__(256) k_align(const __grid_constant__ AlignArgs
     h.bot = h.top + a.nb;
     h.chunks = a.chunks;
     h.link = a.chunk_link;
-    h.priv_lo = gw * a.chunks_per_warp;
-    h.priv_hi = h.priv_lo + a.chunks_per_warp;
-    h.bump = h.priv_lo;
+    h.bump = gw * a.chunks_per_warp;
+    h.priv_hi = h.bump + a.chunks_per_warp;
     h.free_head = NO_CHUNK;
     h.overflow_cursor = a.overflow_cursor;
     h.n_chunks = a.n_chunks;
@@ -579,9 +590,9 @@ __global__ void __launch_bounds__(256) k_align(const __grid_constant__ AlignArgs
     // lane roles in an expansion: lanes 0..15 = rank side L-1 / indel children, 16..31 = side U /
     // match+mismatch children, symbol j = lane & 15
     const uint32_t j = lane & 15u;
-    const uint32_t hi = lane >> 4;
-    // grayVal (io.h:29): base bitmask of code j
-    const uint32_t gray_j = (0x89BAEFDC45762310ull >> (4u * j)) & 15u;
+    const bool hi = lane >= 16u;
+    const uint32_t gray_j = (uint32_t)(0x89BAEFDC45762310ull >> (4u * j)) & 15u;   // grayVal, io.h:29
+    const T lastrow = (T)(a.ix.length - 1);
 
     uint64_t c_pops = 0, c_push = 0, c_tails = 0, c_rank = 0;
     uint32_t c_maxheap = 0, c_maxlist = 0;
@@ -600,10 +611,10 @@ __global__ void __launch_bounds__(256) k_align(const __grid_constant__ AlignArgs
         uint32_t nloads = 0;
 
         // lower bounds (inexact_match.c:61-64 / 140-143)
-        if (!calc_d(a.ix, sC, ls, sseq, len, D, nloads, c_maxlist)) err = BWB_ERR_CAPACITY;
+        if (!calc_d<T>(a.ix, sC, ls, sseq, len, D, nloads, c_maxlist)) err = BWB_ERR_CAPACITY;
         if (!err && a.seed_len > 0) {
             if (len > a.seed_len) {
-                if (!calc_d(a.ix, sC, ls, sseq, a.seed_len, Ds, nloads, c_maxlist)) err = BWB_ERR_CAPACITY;
+                if (!calc_d<T>(a.ix, sC, ls, sseq, a.seed_len, Ds, nloads, c_maxlist)) err = BWB_ERR_CAPACITY;
             } else {
                 // Q6: the reference consults a stale per-thread D_seed here; the defined behaviour
                 // of this implementation is the freshly calloc'ed one (all zero).
@@ -614,88 +625,94 @@ __global__ void __launch_bounds__(256) k_align(const __grid_constant__ AlignArgs
 
         if (!err && (int)nN <= a.max_diff) {
             heap_reset(h);
-            {   // root: i = len, whole range, empty path (inexact_match.c:281)
-                Entry root;
-                root.L = 0; root.U = a.ix.length - 1; root.i = (uint32_t)len; root.state = 0; root.nruns = 0;
-                root.mm = root.go = root.ge = root.nD = 0;
-                root.run[0] = root.run[1] = root.run[2] = root.run[3] = 0;
-                if (!heap_push_group(h, 1u, 0, root)) err = BWB_ERR_CAPACITY;
-                c_push++;
-            }
+            // The entry that the next heap_pop would return is kept in registers whenever it is one
+            // of the children just generated (it would be pushed last into the lowest non-empty
+            // bucket and popped straight back); the root (inexact_match.c:281) starts there.
+            bool have_next = true;
+            PE<T> nx;
+            nx.L = 0; nx.U = lastrow; nx.z = (uint32_t)len; nx.w = 0; nx.r1 = nx.r2 = nx.r3 = 0;
+            int nx_bucket = 0;
+            c_push++;
             int best_score = a.nb;            // aln_score(max_diff+1, max_gapo+1, max_gape+1)
             int max_diff = a.max_diff;
             int num_best = 0;
 
-            while (!err && h.n != 0) {
-                if ((uint32_t)h.n > c_maxheap) c_maxheap = (uint32_t)h.n;
-                if (h.n > a.max_entries) break;
-                Entry e;
-                const int bucket = heap_pop(h, e);
+            while (!err) {
+                const int nvirt = h.n + (have_next ? 1 : 0);       // heap->num_entries of the reference
+                if (nvirt == 0) break;
+                if ((uint32_t)nvirt > c_maxheap) c_maxheap = (uint32_t)nvirt;
+                if (nvirt > a.max_entries) break;
+                PE<T> e;
+                int b;
+                if (have_next) { e = nx; b = nx_bucket; have_next = false; }
+                else b = heap_pop<WIDE>(h, e);
                 c_pops++;
-                const int escore = bucket & 0xff;                       // 8-bit field (Q4)
-                if (escore > best_score + a.mm_score) break;
-                const int used = (int)(e.mm + e.go + e.ge);
+                if ((b & 0xff) > best_score + a.mm_score) break;           // 8-bit score field (Q4)
+                const uint32_t z = e.z;
+                const int ei = (int)(z & 0xffu);
+                const int go = (int)((z >> 24) & 15u), ge = (int)((z >> 16) & 0xffu);
+                const int used = (int)((z >> 8) & 0xffu) + go + ge;
+                const uint32_t state = (z >> 28) & 3u;
                 const int dl = max_diff - used;
                 if (dl < 0) continue;
-                const int ei = (int)e.i;
                 if (ei > 0 && dl < D[ei - 1].x) continue;
                 const int dls = a.max_diff_seed - used;
                 const int si = ei - (len - a.seed_len);
                 if (si > 0 && dls < Ds[si - 1].x) continue;
-                const uint32_t alen = ((uint32_t)(len - ei) + e.nD) & 0xffu;
+                const uint32_t alen = ((uint32_t)(len - ei) + (e.w & 0xffu)) & 0xffu;
 
                 if (ei == 0) {                                          // a hit (inexact_match.c:331-344)
-                    const int sc = (int)e.mm * a.mm_score + (int)e.go * a.gapo_score + (int)e.ge * a.gape_score;
                     if (hs.n == 0) {
-                        best_score = sc;
+                        best_score = b;
                         max_diff = (used + 1 > a.max_diff) ? a.max_diff : used + 1;
                     }
-                    if (sc == best_score) num_best = (int)((uint32_t)num_best + (uint32_t)(e.U - e.L + 1));
+                    if (b == best_score) num_best = (int)((uint32_t)num_best + (uint32_t)(e.U - e.L + 1));
                     else if (num_best > a.max_best) break;
-                    if (!add_hits(hs, e, sc, alen, read_id, lane == 0, e.L, e.U)) err = BWB_ERR_CAPACITY;
+                    if (!add_hits<T>(hs, e, b, alen, read_id, lane == 0, e.L, e.U)) err = BWB_ERR_CAPACITY;
                     continue;
                 }
                 if (dl == 0) {                                          // exact tail (inexact_match.c:345-375)
                     c_tails++;
                     int cur;
-                    const int n = exact_from(a.ix, sC, ls, sseq, len, true, ei - 1, e.L, e.U, cur, nloads, c_maxlist);
+                    const int n = exact_from<T>(a.ix, sC, ls, sseq, len, true, ei - 1, e.L, e.U, cur, nloads, c_maxlist);
                     if (n < 0) { err = BWB_ERR_CAPACITY; break; }
                     if (n > 0) {
-                        const int sc = (int)e.mm * a.mm_score + (int)e.go * a.gapo_score + (int)e.ge * a.gape_score;
                         if (hs.n == 0) {
-                            best_score = sc;
+                            best_score = b;
                             max_diff = (used + 1 > a.max_diff) ? a.max_diff : used + 1;
                         }
-                        if (sc == best_score) {
-                            uint32_t w = 0;
+                        if (b == best_score) {
+                            uint32_t wsum = 0;
                             for (int k = lane; k < n; k += 32) {
-                                const ulonglong2 iv = lget(ls, cur, k);
-                                w += (uint32_t)(iv.y - iv.x + 1);
+                                const typename Pair<T>::type iv = lget<T>(ls, cur, k);
+                                wsum += (uint32_t)(iv.y - iv.x + 1);
                             }
-                            num_best = (int)((uint32_t)num_best + __reduce_add_sync(FULL, w));
+                            num_best = (int)((uint32_t)num_best + __reduce_add_sync(FULL, wsum));
                         } else if (num_best > a.max_best) break;
                         const uint32_t alen2 = (alen + (uint32_t)ei) & 0xffu;   // rest of the path is M
                         for (int base = 0; base < n && !err; base += 32) {
                             const int k = base + (int)lane;
                             const bool have = k < n;
-                            const ulonglong2 iv = have ? lget(ls, cur, k) : make_ulonglong2(0, 0);
-                            if (!add_hits(hs, e, sc, alen2, read_id, have, iv.x, iv.y)) err = BWB_ERR_CAPACITY;
+                            typename Pair<T>::type iv;
+                            iv.x = 0; iv.y = 0;
+                            if (have) iv = lget<T>(ls, cur, k);
+                            if (!add_hits<T>(hs, e, b, alen2, read_id, have, iv.x, iv.y)) err = BWB_ERR_CAPACITY;
                         }
                     }
                     continue;
                 }
 
                 // ---- expansion: the two 16-code rank gathers (inexact_match.c:377-383) ----
-                const uint64_t pos = hi ? e.U : (e.L - 1);
-                const uint64_t mine = occ_alpha(a.ix, sC, j, pos, hi ? 0u : 1u);
-                const uint64_t other = shfl64_xor(mine, 16);
-                const uint64_t Lj = hi ? other : mine;
-                const uint64_t Uj = hi ? mine : other;
+                const T pos = hi ? e.U : (T)(e.L - 1);
+                const T mine = occ_alpha<T>(a.ix, sC, j, pos, hi ? 0u : 1u);
+                const T other = shfl_xor(mine, 16);
+                const T Lj = hi ? other : mine;
+                const T Uj = hi ? mine : other;
                 const bool ok = (j != 0u) && (Lj <= Uj);
-                nloads += (lane == 0 || lane == 16) ? 1u : 0u;
+                nloads += (j == 0u) ? 1u : 0u;
 
                 // BWA heuristics (inexact_match.c:391-430)
-                bool allow_diff = true, allow_indels = true, allow_mm = true, allow_open = true, allow_ext = true;
+                bool allow_diff = true, allow_mm = true;
                 const int i1 = ei - 1;
                 if (i1 > 0) {
                     const int2 d1 = D[i1], d0 = D[i1 - 1];
@@ -707,60 +724,82 @@ __global__ void __launch_bounds__(256) k_align(const __grid_constant__ AlignArgs
                     if (dls - 1 < s0.x) allow_diff = false;
                     else if (s1.x == dls - 1 && s0.x == dls - 1 && s1.y == s0.y) allow_mm = false;
                 }
-                const int gaps = (int)(e.go + e.ge);
-                if (i1 < a.no_indel_len + gaps || len - i1 < a.no_indel_len + gaps) allow_indels = false;
-                if ((int)e.go >= a.max_gapo && (int)e.ge >= a.max_gape) allow_indels = false;
-                if ((int)e.go >= a.max_gapo) allow_open = false;
-                if ((int)e.ge >= a.max_gape) allow_ext = false;
+                const int gaps = go + ge;
+                const bool allow_indels = !(i1 < a.no_indel_len + gaps || len - i1 < a.no_indel_len + gaps) &&
+                                          !(go >= a.max_gapo && ge >= a.max_gape);
+                const bool opening = (state == 0u);
+                const bool gap_allowed = allow_diff && allow_indels && (opening ? (go < a.max_gapo) : (ge < a.max_gape));
+                const bool full = allow_diff && allow_mm;
 
                 // ---- children, one per lane, lane order = reference push order (:433-504) ----
                 const uint32_t c = nt4_compl(sseq[len - 1 - i1]);        // rc[i-1]
-                const uint32_t cmask = c == 0 ? 8u : (c == 1 ? 2u : (c == 2 ? 4u : (c == 3 ? 1u : 15u)));
-                Entry ch = e;
-                bool valid = false;
-                if (hi == 0) {
-                    const bool indel_ok = allow_diff && allow_indels;
-                    const bool opening = (e.state == 0);
-                    if (j == 0) {                                        // insertion: consume a read base
-                        valid = indel_ok && ((e.state == 1 && allow_ext) || (e.state == 0 && allow_open));
-                        ch.i = e.i - 1; ch.state = 1;
-                    } else {                                             // deletion of code j
-                        valid = indel_ok && ok && ((e.state == 0 && allow_open) || (e.state == 2 && allow_ext));
-                        ch.L = Lj; ch.U = Uj; ch.state = 2; ch.nD = e.nD + 1;
-                    }
-                    if (opening) {
-                        ch.go = e.go + 1;
-                        const uint32_t nr = alen | (1u << 8) | (ch.state << 16);
-                        if (e.nruns == 0) ch.run[0] = nr;
-                        else if (e.nruns == 1) ch.run[1] = nr;
-                        else if (e.nruns == 2) ch.run[2] = nr;
-                        else ch.run[3] = nr;
-                        ch.nruns = e.nruns + 1;
-                    } else {
-                        ch.ge = e.ge + 1;
-                        if (e.nruns == 1) ch.run[0] += 1u << 8;
-                        else if (e.nruns == 2) ch.run[1] += 1u << 8;
-                        else if (e.nruns == 3) ch.run[2] += 1u << 8;
-                        else if (e.nruns == 4) ch.run[3] += 1u << 8;
-                    }
-                } else {
-                    const bool is_mm = (c > 3u) || (j == 10u) || ((cmask & gray_j) == 0u);
-                    const bool full = allow_diff && allow_mm;
-                    valid = ok && (full || !is_mm);
-                    ch.L = Lj; ch.U = Uj; ch.i = e.i - 1; ch.state = 0;
-                    ch.mm = e.mm + (is_mm ? 1u : 0u);
-                }
-                const int csc = (int)ch.mm * a.mm_score + (int)ch.go * a.gapo_score + (int)ch.ge * a.gape_score;
+                const uint32_t cmask = (0x01428u >> (4u * c)) & 15u;     // nt4_gray_val; 0 for N
+                const bool is_mm = (j == 10u) || ((cmask & gray_j) == 0u);
+                const bool isD = (j != 0u);
+                // lanes < 16: lane 0 = insertion (not from state D), lanes 1..15 = deletion of code j
+                // (not from state I); lanes >= 16: match / mismatch with code j
+                const bool gap_lane = isD ? (state != 1u && ok) : (state != 2u);
+                const bool valid = hi ? (ok && (full || !is_mm)) : (gap_allowed && gap_lane);
 
-                uint32_t pending = __ballot_sync(FULL, valid);
-                c_push += __popc(pending);
-                while (pending) {
-                    const int leader = __ffs(pending) - 1;
-                    const int sc = __shfl_sync(FULL, csc, leader);
-                    const uint32_t grp = __ballot_sync(FULL, valid && csc == sc) & pending;
-                    if (!heap_push_group(h, grp, sc, ch)) { err = BWB_ERR_CAPACITY; break; }
-                    pending &= ~grp;
+                PE<T> ch;
+                ch.r1 = e.r1; ch.r2 = e.r2; ch.r3 = e.r3;
+                if (hi) {
+                    ch.L = Lj; ch.U = Uj;
+                    ch.z = ((z - 1u) & ~(3u << 28)) + (is_mm ? 0x100u : 0u);
+                    ch.w = e.w;
+                } else {
+                    const uint32_t st = isD ? 2u : 1u;
+                    ch.L = isD ? Lj : e.L;
+                    ch.U = isD ? Uj : e.U;
+                    ch.z = ((z & ~(3u << 28)) | (st << 28)) - (isD ? 0u : 1u) + (opening ? (1u << 24) : (1u << 16));
+                    uint32_t cw = e.w + (isD ? 1u : 0u);
+                    const uint32_t newrun = alen | (1u << 8) | (st << 16);
+                    if (opening) {
+                        if (go == 0) cw = (cw & 0xffu) | (newrun << 8);
+                        else if (WIDE && go == 1) ch.r1 = newrun;
+                        else if (WIDE && go == 2) ch.r2 = newrun;
+                        else if (WIDE) ch.r3 = newrun;
+                    } else {
+                        if (go == 1) cw += 1u << 16;
+                        else if (WIDE && go == 2) ch.r1 += 1u << 8;
+                        else if (WIDE && go == 3) ch.r2 += 1u << 8;
+                        else if (WIDE && go == 4) ch.r3 += 1u << 8;
+                    }
+                    ch.w = cw;
                 }
+
+                // score classes: match -> bucket b, mismatch -> b+M, gap -> b+O (open) or b+E (extend)
+                const uint32_t Vall = __ballot_sync(FULL, valid);
+                const uint32_t MM = __ballot_sync(FULL, is_mm);
+                c_push += __popc(Vall);
+                uint32_t g0 = Vall & 0xffff0000u & ~MM, g1 = Vall & 0xffff0000u & MM, g2 = Vall & 0x0000ffffu;
+                const int b0 = b, b1 = b + a.mm_score, b2 = b + (opening ? a.gapo_score : a.gape_score);
+                // classes that share a bucket are one push group (lane order = push order)
+                if (b2 == b1) { g1 |= g2; g2 = 0; }
+                if (b1 == b0) { g0 |= g1; g1 = 0; }
+                if (b2 == b0) { g0 |= g2; g2 = 0; }
+                // next pop = last child of the lowest child bucket, if that bucket is <= the heap's best
+                {
+                    uint32_t km = g0;
+                    int kb = b0, which = 0;
+                    if (!km) {
+                        if (g1 && (!g2 || b1 < b2)) { km = g1; kb = b1; which = 1; }
+                        else if (g2) { km = g2; kb = b2; which = 2; }
+                    }
+                    if (km && kb <= h.best) {
+                        const int kl = 31 - __clz(km);
+                        nx.L = shfl(ch.L, kl); nx.U = shfl(ch.U, kl);
+                        nx.z = shfl(ch.z, kl); nx.w = shfl(ch.w, kl);
+                        if constexpr (WIDE) { nx.r1 = shfl(ch.r1, kl); nx.r2 = shfl(ch.r2, kl); nx.r3 = shfl(ch.r3, kl); }
+                        nx_bucket = kb;
+                        have_next = true;
+                        const uint32_t bit = ~(1u << kl);
+                        if (which == 0) g0 &= bit; else if (which == 1) g1 &= bit; else g2 &= bit;
+                    }
+                }
+                if (g0 && !heap_push_group<WIDE>(h, g0, b0, ch)) { err = BWB_ERR_CAPACITY; break; }
+                if (g1 && !heap_push_group<WIDE>(h, g1, b1, ch)) { err = BWB_ERR_CAPACITY; break; }
+                if (g2 && !heap_push_group<WIDE>(h, g2, b2, ch)) { err = BWB_ERR_CAPACITY; break; }
             }
             heap_release(h);
         }

@@ -11,9 +11,13 @@ from bwbble_b200.aln import first_difference
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module")
-def gpu_case(small_case):
+@pytest.fixture(scope="module", params=["idx32", "idx64"])
+def gpu_case(small_case, request):
+    """idx32 = 32-bit SA coordinates + 16-byte heap entries (indexes < 2^32 rows, max_gapo <= 1);
+    idx64 = the wide kernels (genome-scale format) forced onto the same small index."""
     al = Aligner(heap_pool_mb=512, hits_per_read=512, list_cap=2048)
+    if request.param == "idx64":
+        al.set_option("force_wide", 1)
     al.load_index(small_case["bwt"])
     orc = oracle.Oracle(small_case["bwt"])
     yield {"al": al, "orc": orc, **small_case}
