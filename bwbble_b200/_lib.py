@@ -60,6 +60,7 @@ SIGNATURES = {
     "bwb_exact_match": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p,
                                   C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]),
     "bwb_calculate_d": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p]),
+    "bwb_lower_bounds": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p]),
     "bwb_align": (C.c_int, [C.c_void_p, C.POINTER(Params), C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p)]),
     "bwb_reads_upload": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p)]),
     "bwb_reads_free": (None, [C.c_void_p]),

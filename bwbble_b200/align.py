@@ -225,6 +225,26 @@ class Aligner:
             res.append(out[o:o + 2 * (dl + 1)].reshape(-1, 2).copy())
         return res
 
+    def lower_bounds(self, seq, offsets, seed_len: int):
+        """K3 of the production engine -> (list of D arrays, list of D_seed arrays or None)."""
+        seq, offsets = _u8(seq), _u64(offsets)
+        n = len(offsets) - 1
+        total = int(offsets[-1] - offsets[0])
+        dm = np.zeros(2 * (total + n), dtype=np.int32)
+        ds = np.zeros(2 * n * (seed_len + 1), dtype=np.int32) if seed_len else None
+        _lib.check(_lib.lib().bwb_lower_bounds(self._ctx, seq.ctypes.data, offsets.ctypes.data, n, seed_len,
+                                               dm.ctypes.data, ds.ctypes.data if seed_len else None), self._ctx)
+        base = int(offsets[0])
+        main = []
+        for r in range(n):
+            ln = int(offsets[r + 1] - offsets[r])
+            o = 2 * (int(offsets[r]) - base + r)
+            main.append(dm[o:o + 2 * (ln + 1)].reshape(-1, 2).copy())
+        seed = None
+        if seed_len:
+            seed = [ds[2 * r * (seed_len + 1):2 * (r + 1) * (seed_len + 1)].reshape(-1, 2).copy() for r in range(n)]
+        return main, seed
+
     # ---- K4 + K5 --------------------------------------------------------------------------------
     def align(self, seq, offsets, params: Optional[Params] = None) -> AlignResult:
         """Host buffers in, host-readable results out (H2D + kernels + D2H)."""

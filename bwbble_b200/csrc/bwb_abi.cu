@@ -14,6 +14,7 @@
 
 #include <cuda_runtime.h>
 
+#include "bwb_group.cuh"
 #include "bwb_kernels.cuh"
 #include "bwbble_b200.h"
 #include "host_common.h"
@@ -42,7 +43,8 @@ struct Device {
     DevBuf glists, chunks, chunk_link, stage;
     uint32_t chunks_per_warp = 0, n_chunks = 0;
     // per-call buffers
-    DevBuf seq, offsets, read_off, read_cnt, ordered_off, unordered, ordered, cub_tmp, small;
+    DevBuf seq, offsets, read_off, read_cnt, ordered_off, unordered, ordered, cub_tmp, small, d_main, d_seed;
+    int engine = -1;          // engine the scratch was sized for
     // pinned staging for small D2H
     unsigned long long *h_small = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;   // bracket K4 on the launch stream
@@ -59,10 +61,11 @@ struct bwb_ctx {
     uint64_t C[17] = {0};
     // options
     long long heap_pool_mb = 8192;
-    int list_cap = 8192;
-    int hits_per_read = 1024;
+    int list_cap = 4096;
+    int hits_per_read = 512;
     int warps_per_block = 8;
     int blocks_per_sm = 0;
+    int engine = 0;           // 0 = 8-lane groups (k_calc_d_g + k_search_g), 1 = warp per read (k_align)
     int force_wide = 0;       // tests: run the 64-bit / 32-byte-entry kernels on a small index
 };
 
@@ -72,6 +75,7 @@ struct bwb_reads {
     int max_len = 0;
     std::vector<uint64_t> shard_lo;      // per device, n_dev+1 entries
     std::vector<void *> d_seq, d_off;    // per device
+    std::vector<uint64_t> shard_bases;   // per device
 };
 
 struct bwb_results {
@@ -169,6 +173,60 @@ SmemLayout k4_layout(int max_len, int seed_len, int nb) {
     return L;
 }
 
+// per-group shared-memory layout of k_search_g (must match the kernel)
+SmemLayout g4_layout(int max_len, int seed_len, int nb) {
+    SmemLayout L;
+    int o = G_LIST_SMEM;
+    L.off_D = o;
+    o += ((max_len + 1) * 2 + 15) & ~15;
+    L.off_Ds = o;
+    o += ((seed_len + 1) * 2 + 15) & ~15;
+    L.off_bk = o;
+    o += (nb * 12 + 15) & ~15;
+    L.off_seq = o;
+    o += (max_len + 15) & ~15;
+    L.per_warp = o;          // bytes per GROUP here
+    return L;
+}
+
+// size the persistent grid and the per-group scratch for the group engine (K3 + K4)
+int prepare_search_group(bwb_ctx *ctx, Device &d, const SmemLayout &L, bool wide) {
+    CU(cudaSetDevice(d.id));
+    const int tpb = 256, gpb = tpb / GL;
+    const size_t smem = (size_t)gpb * L.per_warp;
+    if (smem > 227 * 1024) return fail(ctx, BWB_ERR_ARG, "shared memory per block %zu exceeds 227 KB", smem);
+    int bps = ctx->blocks_per_sm;
+    if (wide) CU(cudaFuncSetAttribute(k_search_g<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    else CU(cudaFuncSetAttribute(k_search_g<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (bps <= 0) {
+        if (wide) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_search_g<true>, tpb, smem));
+        else CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_search_g<false>, tpb, smem));
+        if (bps <= 0) return fail(ctx, BWB_ERR_CUDA, "k_search_g does not fit on an SM");
+    }
+    const int grid = bps * d.sm_count;
+    const int n_groups = grid * gpb;
+    d.smem_bytes = smem;
+    if (n_groups != d.n_warps || d.engine != 0) {
+        release(d.glists); release(d.chunks); release(d.chunk_link); release(d.stage);
+        d.n_warps = n_groups; d.engine = 0;
+    }
+    d.grid = grid; d.wpb = tpb / 32;
+    int rc;
+    if ((rc = ensure(ctx, d.glists, (size_t)n_groups * 2 * ctx->list_cap * sizeof(ulonglong2), false))) return rc;
+    if ((rc = ensure(ctx, d.stage, (size_t)n_groups * ctx->hits_per_read * sizeof(bwb_hit), false))) return rc;
+    if (!d.chunks.p) {
+        const size_t chunk_bytes = (size_t)CHUNK_ENTRIES * 32;
+        uint64_t n_chunks = ((uint64_t)ctx->heap_pool_mb << 20) / chunk_bytes;
+        if (n_chunks < (uint64_t)n_groups * 8) n_chunks = (uint64_t)n_groups * 8;
+        if (n_chunks > 0xfffffff0ull) n_chunks = 0xfffffff0ull;
+        d.n_chunks = (uint32_t)n_chunks;
+        d.chunks_per_warp = (uint32_t)((n_chunks - n_chunks / 4) / n_groups);
+        if ((rc = ensure(ctx, d.chunks, (size_t)n_chunks * chunk_bytes, false))) return rc;
+        if ((rc = ensure(ctx, d.chunk_link, (size_t)n_chunks * 4, false))) return rc;
+    }
+    return BWB_OK;
+}
+
 // size the persistent grid and the per-warp scratch for K4
 int prepare_search(bwb_ctx *ctx, Device &d, const SmemLayout &L, bool wide) {
     CU(cudaSetDevice(d.id));
@@ -186,9 +244,9 @@ int prepare_search(bwb_ctx *ctx, Device &d, const SmemLayout &L, bool wide) {
     const int grid = bps * d.sm_count;
     const int n_warps = grid * wpb;
     d.smem_bytes = smem;
-    if (n_warps != d.n_warps || wpb != d.wpb) {
+    if (n_warps != d.n_warps || wpb != d.wpb || d.engine != 1) {
         release(d.glists); release(d.chunks); release(d.chunk_link); release(d.stage);
-        d.n_warps = n_warps; d.grid = grid; d.wpb = wpb;
+        d.n_warps = n_warps; d.grid = grid; d.wpb = wpb; d.engine = 1;
     }
     d.grid = grid;
     int rc;
@@ -266,7 +324,7 @@ void bwb_destroy(bwb_ctx *ctx) {
         cudaDeviceSynchronize();
         if (d.blocks) cudaFree(d.blocks);
         DevBuf *bufs[] = {&d.glists, &d.chunks, &d.chunk_link, &d.stage, &d.seq, &d.offsets, &d.read_off, &d.read_cnt,
-                          &d.ordered_off, &d.unordered, &d.ordered, &d.cub_tmp, &d.small};
+                          &d.ordered_off, &d.unordered, &d.ordered, &d.cub_tmp, &d.small, &d.d_main, &d.d_seed};
         for (DevBuf *b : bufs) release(*b);
         if (d.h_small) cudaFreeHost(d.h_small);
         if (d.ev0) cudaEventDestroy(d.ev0);
@@ -281,7 +339,7 @@ int bwb_device_count(const bwb_ctx *ctx) { return ctx ? (int)ctx->dev.size() : 0
 int bwb_set_option(bwb_ctx *ctx, const char *key, long long value) {
     if (!ctx || !key) return BWB_ERR_ARG;
     std::string k(key);
-    if (value <= 0 && k != "blocks_per_sm" && k != "force_wide") return fail(ctx, BWB_ERR_ARG, "option %s needs a positive value", key);
+    if (value <= 0 && k != "blocks_per_sm" && k != "force_wide" && k != "engine") return fail(ctx, BWB_ERR_ARG, "option %s needs a positive value", key);
     if (k == "heap_pool_mb") ctx->heap_pool_mb = value;
     else if (k == "list_cap") ctx->list_cap = (int)(value < SL + 4 ? SL + 4 : value);
     else if (k == "hits_per_read") ctx->hits_per_read = (int)value;
@@ -290,6 +348,7 @@ int bwb_set_option(bwb_ctx *ctx, const char *key, long long value) {
         ctx->warps_per_block = (int)value;
     } else if (k == "blocks_per_sm") ctx->blocks_per_sm = (int)value;
     else if (k == "force_wide") ctx->force_wide = value > 1 ? 0 : 1;
+    else if (k == "engine") ctx->engine = value > 1 ? 0 : 1;
     else return fail(ctx, BWB_ERR_ARG, "unknown option %s", key);
     for (auto &d : ctx->dev) {       // scratch is re-sized lazily
         cudaSetDevice(d.id);
@@ -537,6 +596,56 @@ int bwb_calculate_d(bwb_ctx *ctx, const uint8_t *seq, const uint64_t *offsets, u
     return run_list_kernel(ctx, 3, seq, offsets, n_reads, use_len, nullptr, nullptr, nullptr, out);
 }
 
+// K3 of the production engine: D over every whole read and D_seed over its first seed_len bases
+int bwb_lower_bounds(bwb_ctx *ctx, const uint8_t *seq, const uint64_t *offsets, uint64_t n_reads, int seed_len,
+                     int32_t *d_main, int32_t *d_seed) {
+    if (!ctx || !seq || !offsets || !d_main || seed_len < 0 || seed_len > 255 || (seed_len && !d_seed)) return BWB_ERR_ARG;
+    if (!ctx->have_index) return fail(ctx, BWB_ERR_NO_INDEX, "no index uploaded");
+    int max_len, rc;
+    if ((rc = check_reads(ctx, offsets, n_reads, max_len))) return rc;
+    if (n_reads == 0) return BWB_OK;
+    Device &d = ctx->dev[0];
+    CU(cudaSetDevice(d.id));
+    const bool wide = index_is_wide(ctx);
+    const int grid = d.sm_count * 2, n_groups = grid * (256 / GL);
+    const uint64_t total = offsets[n_reads] - offsets[0];
+    uint8_t *dseq; uint64_t *doff; void *gl; unsigned char *sm; int2 *dm, *ds;
+    CU(cudaMalloc(&dseq, total + 16)); CU(cudaMalloc(&doff, (n_reads + 1) * 8));
+    CU(cudaMalloc(&gl, (size_t)n_groups * 2 * ctx->list_cap * sizeof(ulonglong2)));
+    CU(cudaMalloc(&sm, 256));
+    CU(cudaMalloc(&dm, (total + n_reads + 1) * sizeof(int2)));
+    CU(cudaMalloc(&ds, (n_reads * (size_t)(seed_len + 1) + 1) * sizeof(int2)));
+    std::vector<uint64_t> rel(n_reads + 1);
+    for (uint64_t r = 0; r <= n_reads; r++) rel[r] = offsets[r] - offsets[0];
+    CU(cudaMemcpyAsync(dseq, seq + offsets[0], total, cudaMemcpyHostToDevice, d.stream));
+    CU(cudaMemcpyAsync(doff, rel.data(), (n_reads + 1) * 8, cudaMemcpyHostToDevice, d.stream));
+    CU(cudaMemsetAsync(sm, 0, 256, d.stream));
+    CalcArgs c;
+    memset(&c, 0, sizeof c);
+    c.ix = make_view(ctx, d); c.seq = dseq; c.offsets = doff; c.n_reads = (uint32_t)n_reads;
+    c.seed_len = seed_len; c.max_len = max_len; c.queue = (uint32_t *)(sm + 4);
+    c.glists = gl; c.list_cap = ctx->list_cap; c.d_main = dm; c.d_seed = ds;
+    c.status = (uint32_t *)(sm + 8); c.counters = (unsigned long long *)(sm + 32);
+    c.smem_per_group = G_LIST_SMEM + ((max_len + 15) & ~15);
+    const size_t smem3 = (size_t)(256 / GL) * c.smem_per_group;
+    if (wide) {
+        CU(cudaFuncSetAttribute(k_calc_d_g<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
+        k_calc_d_g<true><<<grid, 256, smem3, d.stream>>>(c);
+    } else {
+        CU(cudaFuncSetAttribute(k_calc_d_g<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
+        k_calc_d_g<false><<<grid, 256, smem3, d.stream>>>(c);
+    }
+    CU(cudaGetLastError());
+    uint32_t hstatus = 0;
+    CU(cudaMemcpyAsync(d_main, dm, (total + n_reads) * sizeof(int2), cudaMemcpyDeviceToHost, d.stream));
+    if (seed_len) CU(cudaMemcpyAsync(d_seed, ds, n_reads * (size_t)(seed_len + 1) * sizeof(int2), cudaMemcpyDeviceToHost, d.stream));
+    CU(cudaMemcpyAsync(&hstatus, sm + 8, 4, cudaMemcpyDeviceToHost, d.stream));
+    CU(cudaStreamSynchronize(d.stream));
+    cudaFree(dseq); cudaFree(doff); cudaFree(gl); cudaFree(sm); cudaFree(dm); cudaFree(ds);
+    if (hstatus) return fail(ctx, -(int)hstatus, "interval list exceeded list_cap=%d (raise it with bwb_set_option)", ctx->list_cap);
+    return BWB_OK;
+}
+
 // ---- K4 + K5 ----------------------------------------------------------------------------------
 int bwb_reads_upload(bwb_ctx *ctx, const uint8_t *seq, const uint64_t *offsets, uint64_t n_reads, bwb_reads **out) {
     if (!ctx || !seq || !offsets || !out) return BWB_ERR_ARG;
@@ -547,11 +656,12 @@ int bwb_reads_upload(bwb_ctx *ctx, const uint8_t *seq, const uint64_t *offsets, 
     const int G = (int)ctx->dev.size();
     R->shard_lo.resize(G + 1);
     for (int g = 0; g <= G; g++) R->shard_lo[g] = (uint64_t)g * n_reads / G;
-    R->d_seq.assign(G, nullptr); R->d_off.assign(G, nullptr);
+    R->d_seq.assign(G, nullptr); R->d_off.assign(G, nullptr); R->shard_bases.assign(G, 0);
     for (int g = 0; g < G; g++) {
         Device &d = ctx->dev[g];
         const uint64_t lo = R->shard_lo[g], hi = R->shard_lo[g + 1], n = hi - lo;
         const uint64_t bytes = offsets[hi] - offsets[lo];
+        R->shard_bases[g] = bytes;
         CU(cudaSetDevice(d.id));
         CU(cudaMalloc(&R->d_seq[g], bytes + 16));
         CU(cudaMalloc(&R->d_off[g], (n + 1) * 8));
@@ -593,7 +703,7 @@ static int check_params(bwb_ctx *ctx, const bwb_params *p, int max_len, int &nb)
 
 // enqueue K4 + scan + K5 for one shard on its device stream
 static int launch_shard(bwb_ctx *ctx, Device &d, const bwb_params *p, int nb, const SmemLayout &L, int max_len, bool wide,
-                        const void *d_seq, const void *d_off, uint64_t n, uint64_t read_base, unsigned long long out_cap) {
+                        const void *d_seq, const void *d_off, uint64_t n, uint64_t total_bases, uint64_t read_base, unsigned long long out_cap) {
     int rc;
     CU(cudaSetDevice(d.id));
     if ((rc = ensure(ctx, d.read_off, n * 8 + 8))) return rc;
@@ -632,9 +742,50 @@ static int launch_shard(bwb_ctx *ctx, Device &d, const bwb_params *p, int nb, co
     a.smem_per_warp = L.per_warp; a.off_D = L.off_D; a.off_Ds = L.off_Ds; a.off_bk = L.off_bk; a.off_seq = L.off_seq;
 
     CU(cudaEventRecord(d.ev0, d.stream));
-    if (n) {
+    if (n && ctx->engine == 1) {
         if (wide) k_align<true><<<d.grid, d.wpb * 32, d.smem_bytes, d.stream>>>(a);
         else k_align<false><<<d.grid, d.wpb * 32, d.smem_bytes, d.stream>>>(a);
+        CU(cudaGetLastError());
+    } else if (n) {
+        // K3: lower-bound arrays of every read -> HBM
+        if ((rc = ensure(ctx, d.d_main, (total_bases + n + 1) * sizeof(int2)))) return rc;
+        if ((rc = ensure(ctx, d.d_seed, (n * (size_t)(p->seed_length + 1) + 1) * sizeof(int2)))) return rc;
+        CalcArgs c;
+        memset(&c, 0, sizeof c);
+        c.ix = a.ix; c.seq = a.seq; c.offsets = a.offsets; c.n_reads = a.n_reads;
+        c.seed_len = p->seed_length; c.max_len = max_len;
+        c.queue = (uint32_t *)(sm + 4);
+        c.glists = d.glists.p; c.list_cap = ctx->list_cap;
+        c.d_main = (int2 *)d.d_main.p; c.d_seed = (int2 *)d.d_seed.p;
+        c.status = a.status; c.counters = a.counters;
+        c.smem_per_group = G_LIST_SMEM + ((max_len + 15) & ~15);
+        const size_t smem3 = (size_t)(256 / GL) * c.smem_per_group;
+        if (wide) {
+            CU(cudaFuncSetAttribute(k_calc_d_g<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
+            k_calc_d_g<true><<<d.grid, 256, smem3, d.stream>>>(c);
+        } else {
+            CU(cudaFuncSetAttribute(k_calc_d_g<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
+            k_calc_d_g<false><<<d.grid, 256, smem3, d.stream>>>(c);
+        }
+        CU(cudaGetLastError());
+        // K4: the search proper
+        SearchArgs g;
+        memset(&g, 0, sizeof g);
+        g.ix = a.ix; g.seq = a.seq; g.offsets = a.offsets; g.n_reads = a.n_reads; g.read_id_base = a.read_id_base;
+        g.max_diff = a.max_diff; g.max_gapo = a.max_gapo; g.max_gape = a.max_gape; g.max_entries = a.max_entries;
+        g.mm_score = a.mm_score; g.gapo_score = a.gapo_score; g.gape_score = a.gape_score;
+        g.seed_len = a.seed_len; g.max_diff_seed = a.max_diff_seed; g.max_best = a.max_best; g.no_indel_len = a.no_indel_len;
+        g.nb = a.nb; g.max_len = a.max_len; g.queue = a.queue;
+        g.d_main = c.d_main; g.d_seed = c.d_seed;
+        g.glists = a.glists; g.list_cap = a.list_cap;
+        g.chunks = a.chunks; g.chunk_link = a.chunk_link; g.chunks_per_group = a.chunks_per_warp; g.n_chunks = a.n_chunks;
+        g.overflow_cursor = a.overflow_cursor;
+        g.stage = a.stage; g.hits_cap = a.hits_cap;
+        g.out_hits = a.out_hits; g.out_cap = a.out_cap; g.out_cursor = a.out_cursor;
+        g.read_off = a.read_off; g.read_cnt = a.read_cnt; g.status = a.status; g.counters = a.counters;
+        g.smem_per_group = L.per_warp; g.off_D = L.off_D; g.off_Ds = L.off_Ds; g.off_bk = L.off_bk; g.off_seq = L.off_seq;
+        if (wide) k_search_g<true><<<d.grid, 256, d.smem_bytes, d.stream>>>(g);
+        else k_search_g<false><<<d.grid, 256, d.smem_bytes, d.stream>>>(g);
         CU(cudaGetLastError());
     }
     CU(cudaEventRecord(d.ev1, d.stream));
@@ -655,7 +806,8 @@ static int align_impl(bwb_ctx *ctx, const bwb_params *p, const bwb_reads *R, bwb
     if (!ctx->have_index) return fail(ctx, BWB_ERR_NO_INDEX, "bwb_align before bwb_index_upload");
     int nb = 0, rc;
     if ((rc = check_params(ctx, p, R->max_len, nb))) return rc;
-    const SmemLayout L = k4_layout(R->max_len > 0 ? R->max_len : 1, p->seed_length, nb);
+    const SmemLayout L = ctx->engine == 1 ? k4_layout(R->max_len > 0 ? R->max_len : 1, p->seed_length, nb)
+                                          : g4_layout(R->max_len > 0 ? R->max_len : 1, p->seed_length, nb);
     // 16-byte entries + 32-bit coordinates unless the index or the gap-run count needs the wide format
     const bool wide = index_is_wide(ctx) || p->max_gapo > 1;
     const int G = (int)ctx->dev.size();
@@ -665,7 +817,8 @@ static int align_impl(bwb_ctx *ctx, const bwb_params *p, const bwb_reads *R, bwb
 
     std::vector<unsigned long long> cap(G);
     for (int g = 0; g < G; g++) {
-        if ((rc = prepare_search(ctx, ctx->dev[g], L, wide))) { delete res; return rc; }
+        rc = ctx->engine == 1 ? prepare_search(ctx, ctx->dev[g], L, wide) : prepare_search_group(ctx, ctx->dev[g], L, wide);
+        if (rc) { delete res; return rc; }
         cap[g] = (R->shard_lo[g + 1] - R->shard_lo[g]) * 2 + 65536;
     }
     std::vector<char> done(G, 0);
@@ -673,7 +826,7 @@ static int align_impl(bwb_ctx *ctx, const bwb_params *p, const bwb_reads *R, bwb
         for (int g = 0; g < G; g++) {
             if (done[g]) continue;
             const uint64_t lo = R->shard_lo[g], n = R->shard_lo[g + 1] - lo;
-            if ((rc = launch_shard(ctx, ctx->dev[g], p, nb, L, R->max_len > 0 ? R->max_len : 1, wide, R->d_seq[g], R->d_off[g], n, lo, cap[g]))) {
+            if ((rc = launch_shard(ctx, ctx->dev[g], p, nb, L, R->max_len > 0 ? R->max_len : 1, wide, R->d_seq[g], R->d_off[g], n, R->shard_bases[g], lo, cap[g]))) {
                 delete res;
                 return rc;
             }

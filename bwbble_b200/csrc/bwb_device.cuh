@@ -63,17 +63,29 @@ struct BlockBits {       // match mask of one code over the 128 rows of a block 
     uint32_t cnt, m0, m1, m2, m3;
 };
 
-__device__ __forceinline__ BlockBits load_block(const uint4 *__restrict__ blk, uint32_t c) {
+struct Planes { uint4 p0, p1, p2, p3; };   // the four bit planes of a block (64 B)
+
+__device__ __forceinline__ Planes load_planes(const uint4 *__restrict__ blk) {
+    Planes p;
+    p.p0 = __ldg(blk + 4); p.p1 = __ldg(blk + 5); p.p2 = __ldg(blk + 6); p.p3 = __ldg(blk + 7);
+    return p;
+}
+
+// counter of code c + the 128-bit mask of rows holding c
+__device__ __forceinline__ BlockBits match_code(const Planes &p, const uint4 *__restrict__ blk, uint32_t c) {
     BlockBits b;
     b.cnt = __ldg(reinterpret_cast<const uint32_t *>(blk) + c);
-    const uint4 p0 = __ldg(blk + 4), p1 = __ldg(blk + 5), p2 = __ldg(blk + 6), p3 = __ldg(blk + 7);
     const uint32_t x0 = 0u - (~c & 1u), x1 = 0u - ((~c >> 1) & 1u);      // all ones where bit k of c is 0
     const uint32_t x2 = 0u - ((~c >> 2) & 1u), x3 = 0u - ((~c >> 3) & 1u);
-    b.m0 = (p0.x ^ x0) & (p1.x ^ x1) & (p2.x ^ x2) & (p3.x ^ x3);
-    b.m1 = (p0.y ^ x0) & (p1.y ^ x1) & (p2.y ^ x2) & (p3.y ^ x3);
-    b.m2 = (p0.z ^ x0) & (p1.z ^ x1) & (p2.z ^ x2) & (p3.z ^ x3);
-    b.m3 = (p0.w ^ x0) & (p1.w ^ x1) & (p2.w ^ x2) & (p3.w ^ x3);
+    b.m0 = (p.p0.x ^ x0) & (p.p1.x ^ x1) & (p.p2.x ^ x2) & (p.p3.x ^ x3);
+    b.m1 = (p.p0.y ^ x0) & (p.p1.y ^ x1) & (p.p2.y ^ x2) & (p.p3.y ^ x3);
+    b.m2 = (p.p0.z ^ x0) & (p.p1.z ^ x1) & (p.p2.z ^ x2) & (p.p3.z ^ x3);
+    b.m3 = (p.p0.w ^ x0) & (p.p1.w ^ x1) & (p.p2.w ^ x2) & (p.p3.w ^ x3);
     return b;
+}
+
+__device__ __forceinline__ BlockBits load_block(const uint4 *__restrict__ blk, uint32_t c) {
+    return match_code(load_planes(blk), blk, c);
 }
 
 // cnt + #{rows p in [0, r] of the block holding the code}

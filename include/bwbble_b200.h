@@ -93,10 +93,12 @@ int bwb_device_count(const bwb_ctx *ctx);
 
 /* Options (before bwb_index_upload / first bwb_align):
  *   "heap_pool_mb"     device bytes for the bucket-heap chunk pool, per device (default 8192)
- *   "list_cap"         max SA intervals per list per read-slot (default 8192)
- *   "hits_per_read"    staging capacity for hits of one read (default 4096)
+ *   "list_cap"         max SA intervals per list per read-slot (default 4096)
+ *   "hits_per_read"    staging capacity for hits of one read (default 512)
  *   "warps_per_block"  search kernel block shape (default 8)
- *   "blocks_per_sm"    persistent blocks per SM (default: occupancy query)                      */
+ *   "blocks_per_sm"    persistent blocks per SM (default: occupancy query)
+ *   "engine"           1 = warp-per-read kernel k_align (A/B only; 2 = back to the default 8-lane groups)
+ *   "force_wide"       1 = 64-bit coordinates / 32-byte heap entries even on a small index (tests)  */
 int bwb_set_option(bwb_ctx *ctx, const char *key, long long value);
 /* Launch on a caller-owned cudaStream_t (e.g. torch's current stream) instead of the context's own. */
 int bwb_set_stream(bwb_ctx *ctx, int dev_slot, void *cuda_stream);
@@ -136,6 +138,13 @@ int bwb_exact_match(bwb_ctx *ctx, const uint8_t *seq, const uint64_t *offsets, u
  * 2*(offsets[r]+r) int32s. */
 int bwb_calculate_d(bwb_ctx *ctx, const uint8_t *seq, const uint64_t *offsets, uint64_t n_reads,
                     int use_len, int32_t *out);
+
+/* K3 of the production engine: for every read D = calculate_d(read, len) and, if seed_len > 0,
+ * D_seed = calculate_d(read, seed_len) (inexact_match.c:61-64).  d_main: (len+1) pairs per read at
+ * 2*(offsets[r]-offsets[0]+r) int32s; d_seed: (seed_len+1) pairs per read at 2*r*(seed_len+1); all
+ * zero for reads with len <= seed_len (the reference leaves a stale array there). */
+int bwb_lower_bounds(bwb_ctx *ctx, const uint8_t *seq, const uint64_t *offsets, uint64_t n_reads, int seed_len,
+                     int32_t *d_main, int32_t *d_seed);
 
 /* The hot path: calculate_d + inexact_match for every read (inexact_match.c:25-168), results in
  * input order.  Host buffers in, host-readable results out (H2D/D2H inside). */

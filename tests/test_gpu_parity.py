@@ -11,13 +11,16 @@ from bwbble_b200.aln import first_difference
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module", params=["idx32", "idx64"])
+@pytest.fixture(scope="module", params=["group-idx32", "group-idx64", "warp-idx32", "warp-idx64"])
 def gpu_case(small_case, request):
-    """idx32 = 32-bit SA coordinates + 16-byte heap entries (indexes < 2^32 rows, max_gapo <= 1);
+    """group = production engine (8 lanes per read: k_calc_d_g + k_search_g), warp = k_align (A/B);
+    idx32 = 32-bit SA coordinates + 16-byte heap entries (indexes < 2^32 rows, max_gapo <= 1);
     idx64 = the wide kernels (genome-scale format) forced onto the same small index."""
-    al = Aligner(heap_pool_mb=512, hits_per_read=512, list_cap=2048)
-    if request.param == "idx64":
+    al = Aligner(heap_pool_mb=512, hits_per_read=256, list_cap=1024)
+    if request.param.endswith("idx64"):
         al.set_option("force_wide", 1)
+    if request.param.startswith("warp"):
+        al.set_option("engine", 1)
     al.load_index(small_case["bwt"])
     orc = oracle.Oracle(small_case["bwt"])
     yield {"al": al, "orc": orc, **small_case}
@@ -116,7 +119,7 @@ def dense_case(tmp_path_factory):
     fa = str(d / "g.fa")
     g.write_fasta(fa)
     index.build_index(fa)
-    al = Aligner(heap_pool_mb=512, hits_per_read=512, list_cap=4096)
+    al = Aligner(heap_pool_mb=512, hits_per_read=256, list_cap=2048)
     al.load_index(fa + ".bwt")
     orc = oracle.Oracle(fa + ".bwt")
     yield {"al": al, "orc": orc, "genome": g}
@@ -163,6 +166,19 @@ def test_calculate_d(gpu_case, use_len):
     for r in range(reads.n):
         exp = orc.calculate_d(reads.read(r), use_len)
         assert got[r].shape == exp.shape and (got[r] == exp).all(), "read %d:\n got %s\n exp %s" % (r, got[r].T, exp.T)
+
+
+@pytest.mark.parametrize("seed_len", [0, 32, 20])
+def test_lower_bounds_k3(gpu_case, seed_len):
+    al, orc, reads = gpu_case["al"], gpu_case["orc"], gpu_case["reads"]
+    main, seed = al.lower_bounds(reads.seq, reads.offsets, seed_len)
+    for r in range(reads.n):
+        rd = reads.read(r)
+        exp = orc.calculate_d(rd)
+        assert main[r].shape == exp.shape and (main[r] == exp).all(), "D read %d:\n got %s\n exp %s" % (r, main[r].T, exp.T)
+        if seed_len:
+            exps = orc.calculate_d(rd, seed_len) if len(rd) > seed_len else np.zeros((seed_len + 1, 2), dtype=np.int32)
+            assert (seed[r] == exps).all(), "D_seed read %d:\n got %s\n exp %s" % (r, seed[r].T, exps.T)
 
 
 GRID = [
