@@ -14,6 +14,7 @@
 
 #include <cuda_runtime.h>
 
+#include "bwb_lane.cuh"
 #include "bwb_group.cuh"
 #include "bwb_kernels.cuh"
 #include "bwbble_b200.h"
@@ -43,7 +44,9 @@ struct Device {
     DevBuf glists, chunks, chunk_link, stage;
     uint32_t chunks_per_warp = 0, n_chunks = 0;
     // per-call buffers
-    DevBuf seq, offsets, read_off, read_cnt, ordered_off, unordered, ordered, cub_tmp, small, d_main, d_seed;
+    DevBuf seq, offsets, read_off, read_cnt, ordered_off, unordered, ordered, cub_tmp, small, d_main, d_seed, pool;
+    DevBuf pk_main, pk_seed, nxt, blk_link, heads;      // lane engine
+    uint32_t slots_per_lane = 0, total_slots = 0, priv_total = 0;
     int engine = -1;          // engine the scratch was sized for
     // pinned staging for small D2H
     unsigned long long *h_small = nullptr;
@@ -65,7 +68,8 @@ struct bwb_ctx {
     int hits_per_read = 512;
     int warps_per_block = 8;
     int blocks_per_sm = 0;
-    int engine = 0;           // 0 = 8-lane groups (k_calc_d_g + k_search_g), 1 = warp per read (k_align)
+    int engine = 0;           // 0 = read per lane (k_calc_d_g + k_search_l), 1 = warp per read (k_align),
+                              // 2 = 8-lane groups (k_calc_d_g + k_search_g); 1 and 2 are A/B baselines
     int force_wide = 0;       // tests: run the 64-bit / 32-byte-entry kernels on a small index
 };
 
@@ -206,23 +210,66 @@ int prepare_search_group(bwb_ctx *ctx, Device &d, const SmemLayout &L, bool wide
     const int grid = bps * d.sm_count;
     const int n_groups = grid * gpb;
     d.smem_bytes = smem;
-    if (n_groups != d.n_warps || d.engine != 0) {
+    if (n_groups != d.n_warps || d.engine != 2) {
         release(d.glists); release(d.chunks); release(d.chunk_link); release(d.stage);
-        d.n_warps = n_groups; d.engine = 0;
+        d.n_warps = n_groups; d.engine = 2;
     }
     d.grid = grid; d.wpb = tpb / 32;
     int rc;
     if ((rc = ensure(ctx, d.glists, (size_t)n_groups * 2 * ctx->list_cap * sizeof(ulonglong2), false))) return rc;
     if ((rc = ensure(ctx, d.stage, (size_t)n_groups * ctx->hits_per_read * sizeof(bwb_hit), false))) return rc;
-    if (!d.chunks.p) {
-        const size_t chunk_bytes = (size_t)CHUNK_ENTRIES * 32;
-        uint64_t n_chunks = ((uint64_t)ctx->heap_pool_mb << 20) / chunk_bytes;
-        if (n_chunks < (uint64_t)n_groups * 8) n_chunks = (uint64_t)n_groups * 8;
+    {
+        // chunk = 32 entries of 16 B (compact) or 32 B (wide); 3/4 of the pool is split into private
+        // ranges (no atomics on the common path), 1/4 is shared between all groups
+        uint64_t pool_bytes = (uint64_t)ctx->heap_pool_mb << 20;
+        if (pool_bytes < (uint64_t)n_groups * 16 * 1024) pool_bytes = (uint64_t)n_groups * 16 * 1024;
+        const size_t chunk_bytes = (size_t)CHUNK_ENTRIES * (wide ? 32 : 16);
+        uint64_t n_chunks = pool_bytes / chunk_bytes;
         if (n_chunks > 0xfffffff0ull) n_chunks = 0xfffffff0ull;
         d.n_chunks = (uint32_t)n_chunks;
-        d.chunks_per_warp = (uint32_t)((n_chunks - n_chunks / 4) / n_groups);
-        if ((rc = ensure(ctx, d.chunks, (size_t)n_chunks * chunk_bytes, false))) return rc;
-        if ((rc = ensure(ctx, d.chunk_link, (size_t)n_chunks * 4, false))) return rc;
+        d.chunks_per_warp = (uint32_t)((n_chunks - n_chunks / 4) / n_groups);      // 3/4 private, 1/4 shared
+        if ((rc = ensure(ctx, d.chunks, pool_bytes, false))) return rc;
+        if ((rc = ensure(ctx, d.chunk_link, (size_t)(pool_bytes / (CHUNK_ENTRIES * 16)) * 4, false))) return rc;
+    }
+    return BWB_OK;
+}
+
+// size the persistent grid and the per-lane arena for the lane engine (K3 groups + K4 lanes)
+int prepare_search_lane(bwb_ctx *ctx, Device &d, int nb, bool wide) {
+    CU(cudaSetDevice(d.id));
+    const int tpb = 128;
+    int bps = ctx->blocks_per_sm;
+    if (bps <= 0) {
+        if (wide) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_search_l<true>, tpb, 0));
+        else CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_search_l<false>, tpb, 0));
+        if (bps <= 0) return fail(ctx, BWB_ERR_CUDA, "k_search_l does not fit on an SM");
+    }
+    const int grid = bps * d.sm_count;
+    const int n_lanes = grid * tpb;
+    if (n_lanes != d.n_warps || d.engine != 0) {
+        release(d.glists); release(d.chunks); release(d.chunk_link); release(d.stage);
+        release(d.nxt); release(d.blk_link); release(d.heads);
+        d.n_warps = n_lanes; d.engine = 0;
+    }
+    d.grid = grid; d.wpb = tpb / 32; d.smem_bytes = 0;
+    int rc;
+    // K3 still runs 8-lane groups: its list scratch is sized for the same grid of 256-thread blocks
+    const int n_groups3 = (grid / 2 + 1) * (256 / GL);
+    if ((rc = ensure(ctx, d.glists, (size_t)n_groups3 * 2 * ctx->list_cap * sizeof(ulonglong2), false))) return rc;
+    if ((rc = ensure(ctx, d.heads, (size_t)n_lanes * nb * 4, false))) return rc;
+    {
+        // arena: 16-byte slot + 4-byte link; 3/4 split into private ranges, 1/4 shared in 64-slot blocks
+        uint64_t pool_bytes = (uint64_t)ctx->heap_pool_mb << 20;
+        uint64_t total = pool_bytes / 20;
+        if (total < (uint64_t)n_lanes * 256) total = (uint64_t)n_lanes * 256;
+        if (total > 0xfffff000ull) total = 0xfffff000ull;
+        total &= ~(uint64_t)(LBLK - 1);
+        uint32_t spl = (uint32_t)((total - total / 4) / n_lanes);
+        uint64_t priv = ((uint64_t)spl * n_lanes + LBLK - 1) & ~(uint64_t)(LBLK - 1);
+        d.slots_per_lane = spl; d.total_slots = (uint32_t)total; d.priv_total = (uint32_t)priv;
+        if ((rc = ensure(ctx, d.chunks, total * 16, false))) return rc;
+        if ((rc = ensure(ctx, d.nxt, total * 4, false))) return rc;
+        if ((rc = ensure(ctx, d.blk_link, (total / LBLK + 1) * 4, false))) return rc;
     }
     return BWB_OK;
 }
@@ -324,7 +371,7 @@ void bwb_destroy(bwb_ctx *ctx) {
         cudaDeviceSynchronize();
         if (d.blocks) cudaFree(d.blocks);
         DevBuf *bufs[] = {&d.glists, &d.chunks, &d.chunk_link, &d.stage, &d.seq, &d.offsets, &d.read_off, &d.read_cnt,
-                          &d.ordered_off, &d.unordered, &d.ordered, &d.cub_tmp, &d.small, &d.d_main, &d.d_seed};
+                          &d.ordered_off, &d.unordered, &d.ordered, &d.cub_tmp, &d.small, &d.d_main, &d.d_seed, &d.pool, &d.pk_main, &d.pk_seed, &d.nxt, &d.blk_link, &d.heads};
         for (DevBuf *b : bufs) release(*b);
         if (d.h_small) cudaFreeHost(d.h_small);
         if (d.ev0) cudaEventDestroy(d.ev0);
@@ -348,7 +395,7 @@ int bwb_set_option(bwb_ctx *ctx, const char *key, long long value) {
         ctx->warps_per_block = (int)value;
     } else if (k == "blocks_per_sm") ctx->blocks_per_sm = (int)value;
     else if (k == "force_wide") ctx->force_wide = value > 1 ? 0 : 1;
-    else if (k == "engine") ctx->engine = value > 1 ? 0 : 1;
+    else if (k == "engine") ctx->engine = (value == 1 || value == 2) ? (int)value : 0;
     else return fail(ctx, BWB_ERR_ARG, "unknown option %s", key);
     for (auto &d : ctx->dev) {       // scratch is re-sized lazily
         cudaSetDevice(d.id);
@@ -712,11 +759,37 @@ static int launch_shard(bwb_ctx *ctx, Device &d, const bwb_params *p, int nb, co
     if ((rc = ensure(ctx, d.unordered, out_cap * sizeof(bwb_hit)))) return rc;
     if ((rc = ensure(ctx, d.ordered, out_cap * sizeof(bwb_hit)))) return rc;
     if ((rc = ensure(ctx, d.small, 256))) return rc;
-    // small block: [0] queue u32 | [8] status 2xu32 | [16] out_cursor u64 | [24] overflow cursor u32 | [32..] counters 8xu64
+    // small block: [0] K4 queue u32 | [4] K3 queue u32 | [8] status 2xu32 | [16] out_cursor u64 |
+    // [24] shared-pool bump cursor u32 | [32..96) counters 8xu64 | [96] shared-pool free-list head u64
     unsigned char *sm = (unsigned char *)d.small.p;
     CU(cudaMemsetAsync(sm, 0, 256, d.stream));
     const uint32_t ovf0 = (uint32_t)d.n_warps * d.chunks_per_warp;
     CU(cudaMemcpyAsync(sm + 24, &ovf0, 4, cudaMemcpyHostToDevice, d.stream));
+    if (ctx->engine == 0) {        // lane engine: shared blocks of LBLK slots above the private ranges
+        if ((rc = ensure(ctx, d.pool, sizeof(PoolState)))) return rc;
+        static thread_local PoolState hp;
+        const uint32_t blk0 = d.priv_total / LBLK, blk1 = d.total_slots / LBLK;
+        const uint32_t per = (blk1 > blk0 ? blk1 - blk0 : 0u) / POOL_SHARDS;
+        for (int s = 0; s < POOL_SHARDS; s++) {
+            hp.head[s] = 0xffffffffull;
+            hp.bump[s] = blk0 + (uint32_t)s * per;
+            hp.limit[s] = blk0 + (uint32_t)(s + 1) * per;
+        }
+        hp.n_borrowed = 0;
+        CU(cudaMemcpyAsync(d.pool.p, &hp, sizeof hp, cudaMemcpyHostToDevice, d.stream));
+    }
+    if (ctx->engine == 2) {        // shared chunk pool: POOL_SHARDS regions above the private ranges
+        if ((rc = ensure(ctx, d.pool, sizeof(PoolState)))) return rc;
+        static thread_local PoolState hp;
+        const uint32_t shared = d.n_chunks > ovf0 ? d.n_chunks - ovf0 : 0u, per = shared / POOL_SHARDS;
+        for (int s = 0; s < POOL_SHARDS; s++) {
+            hp.head[s] = 0xffffffffull;                                      // tag 0, empty
+            hp.bump[s] = ovf0 + (uint32_t)s * per;
+            hp.limit[s] = ovf0 + (uint32_t)(s + 1) * per;
+        }
+        hp.n_borrowed = 0;
+        CU(cudaMemcpyAsync(d.pool.p, &hp, sizeof hp, cudaMemcpyHostToDevice, d.stream));
+    }
 
     AlignArgs a;
     memset(&a, 0, sizeof a);
@@ -745,6 +818,46 @@ static int launch_shard(bwb_ctx *ctx, Device &d, const bwb_params *p, int nb, co
     if (n && ctx->engine == 1) {
         if (wide) k_align<true><<<d.grid, d.wpb * 32, d.smem_bytes, d.stream>>>(a);
         else k_align<false><<<d.grid, d.wpb * 32, d.smem_bytes, d.stream>>>(a);
+        CU(cudaGetLastError());
+    } else if (n && ctx->engine == 0) {
+        // K3 (8-lane groups): packed lower-bound arrays of every read -> HBM
+        if ((rc = ensure(ctx, d.pk_main, (total_bases + n + 1) * 2))) return rc;
+        if ((rc = ensure(ctx, d.pk_seed, (n * (size_t)(p->seed_length + 1) + 1) * 2))) return rc;
+        CalcArgs c;
+        memset(&c, 0, sizeof c);
+        c.ix = a.ix; c.seq = a.seq; c.offsets = a.offsets; c.n_reads = a.n_reads;
+        c.seed_len = p->seed_length; c.max_len = max_len;
+        c.queue = (uint32_t *)(sm + 4);
+        c.glists = d.glists.p; c.list_cap = ctx->list_cap;
+        c.pk_main = (uint16_t *)d.pk_main.p; c.pk_seed = (uint16_t *)d.pk_seed.p;
+        c.status = a.status; c.counters = a.counters;
+        c.smem_per_group = G_LIST_SMEM + ((max_len + 15) & ~15);
+        const size_t smem3 = (size_t)(256 / GL) * c.smem_per_group;
+        const int grid3 = d.grid / 2 + 1;
+        if (wide) {
+            CU(cudaFuncSetAttribute(k_calc_d_g<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
+            k_calc_d_g<true><<<grid3, 256, smem3, d.stream>>>(c);
+        } else {
+            CU(cudaFuncSetAttribute(k_calc_d_g<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
+            k_calc_d_g<false><<<grid3, 256, smem3, d.stream>>>(c);
+        }
+        CU(cudaGetLastError());
+        // K4: one read per lane
+        LaneArgs g;
+        memset(&g, 0, sizeof g);
+        g.ix = a.ix; g.seq = a.seq; g.offsets = a.offsets; g.n_reads = a.n_reads; g.read_id_base = a.read_id_base;
+        g.max_diff = a.max_diff; g.max_gapo = a.max_gapo; g.max_gape = a.max_gape; g.max_entries = a.max_entries;
+        g.mm_score = a.mm_score; g.gapo_score = a.gapo_score; g.gape_score = a.gape_score;
+        g.seed_len = a.seed_len; g.max_diff_seed = a.max_diff_seed; g.max_best = a.max_best; g.no_indel_len = a.no_indel_len;
+        g.nb = a.nb; g.queue = a.queue;
+        g.pk_main = c.pk_main; g.pk_seed = c.pk_seed;
+        g.slots = (uint4 *)d.chunks.p; g.nxt = (uint32_t *)d.nxt.p;
+        g.slots_per_lane = d.slots_per_lane; g.priv_total = d.priv_total;
+        g.pool = (PoolState *)d.pool.p; g.blk_link = (uint32_t *)d.blk_link.p; g.heads = (uint32_t *)d.heads.p;
+        g.out_hits = a.out_hits; g.out_cap = a.out_cap; g.out_cursor = a.out_cursor;
+        g.read_off = a.read_off; g.read_cnt = a.read_cnt; g.status = a.status; g.counters = a.counters;
+        if (wide) k_search_l<true><<<d.grid, 128, 0, d.stream>>>(g);
+        else k_search_l<false><<<d.grid, 128, 0, d.stream>>>(g);
         CU(cudaGetLastError());
     } else if (n) {
         // K3: lower-bound arrays of every read -> HBM
@@ -779,7 +892,7 @@ static int launch_shard(bwb_ctx *ctx, Device &d, const bwb_params *p, int nb, co
         g.d_main = c.d_main; g.d_seed = c.d_seed;
         g.glists = a.glists; g.list_cap = a.list_cap;
         g.chunks = a.chunks; g.chunk_link = a.chunk_link; g.chunks_per_group = a.chunks_per_warp; g.n_chunks = a.n_chunks;
-        g.overflow_cursor = a.overflow_cursor;
+        g.priv_total = ovf0; g.pool = (PoolState *)d.pool.p;
         g.stage = a.stage; g.hits_cap = a.hits_cap;
         g.out_hits = a.out_hits; g.out_cap = a.out_cap; g.out_cursor = a.out_cursor;
         g.read_off = a.read_off; g.read_cnt = a.read_cnt; g.status = a.status; g.counters = a.counters;
@@ -807,7 +920,7 @@ static int align_impl(bwb_ctx *ctx, const bwb_params *p, const bwb_reads *R, bwb
     int nb = 0, rc;
     if ((rc = check_params(ctx, p, R->max_len, nb))) return rc;
     const SmemLayout L = ctx->engine == 1 ? k4_layout(R->max_len > 0 ? R->max_len : 1, p->seed_length, nb)
-                                          : g4_layout(R->max_len > 0 ? R->max_len : 1, p->seed_length, nb);
+                                          : g4_layout(R->max_len > 0 ? R->max_len : 1, p->seed_length, nb);   // engine 0: unused
     // 16-byte entries + 32-bit coordinates unless the index or the gap-run count needs the wide format
     const bool wide = index_is_wide(ctx) || p->max_gapo > 1;
     const int G = (int)ctx->dev.size();
@@ -817,7 +930,9 @@ static int align_impl(bwb_ctx *ctx, const bwb_params *p, const bwb_reads *R, bwb
 
     std::vector<unsigned long long> cap(G);
     for (int g = 0; g < G; g++) {
-        rc = ctx->engine == 1 ? prepare_search(ctx, ctx->dev[g], L, wide) : prepare_search_group(ctx, ctx->dev[g], L, wide);
+        rc = ctx->engine == 1 ? prepare_search(ctx, ctx->dev[g], L, wide)
+           : ctx->engine == 2 ? prepare_search_group(ctx, ctx->dev[g], L, wide)
+                              : prepare_search_lane(ctx, ctx->dev[g], nb, wide);
         if (rc) { delete res; return rc; }
         cap[g] = (R->shard_lo[g + 1] - R->shard_lo[g]) * 2 + 65536;
     }
@@ -856,6 +971,7 @@ static int align_impl(bwb_ctx *ctx, const bwb_params *p, const bwb_reads *R, bwb
             if (ms > res->kernel_ms) res->kernel_ms = ms;
             const unsigned long long *ctr = (const unsigned long long *)(hs + 32);
             for (int k = 0; k < 4; k++) res->counters[k] += ctr[k];
+
             for (int k = 4; k < 6; k++) if (ctr[k] > res->counters[k]) res->counters[k] = ctr[k];
         }
         if (!again) break;

@@ -155,6 +155,7 @@ struct CalcArgs {
     int list_cap;
     int2 *d_main;            // per read (len+1) entries at offsets[r] + r
     int2 *d_seed;            // per read (seed_len+1) entries at r*(seed_len+1); zeros if len <= seed_len (Q6)
+    uint16_t *pk_main, *pk_seed;   // same arrays packed for K4: num_diff | (width == previous width) << 15
     uint32_t *status;
     unsigned long long *counters;   // [3] rank queries, [5] max list
     int smem_per_group;
@@ -183,6 +184,8 @@ __global__ void __launch_bounds__(256) k_calc_d_g(const __grid_constant__ CalcAr
     int len = 0, dlen = 0, phase = 0, i = 0, z = 0;
     uint64_t off = 0;
     int2 *D = nullptr;
+    uint16_t *PK = nullptr;
+    uint32_t prev_w = 0;
     StepState<T> st;
     st.cur = 0; st.n_cur = 0;
     step_begin(st);
@@ -204,7 +207,8 @@ __global__ void __launch_bounds__(256) k_calc_d_g(const __grid_constant__ CalcAr
             }
             g_stage_read(got, a.seq + off, len, sseq);
             if (got) {
-                phase = 0; dlen = len; D = a.d_main + off + r;
+                phase = 0; dlen = len; D = a.d_main ? a.d_main + off + r : nullptr;
+                PK = a.pk_main ? a.pk_main + off + r : nullptr;
                 i = dlen - 1; z = 0; st.cur = 0; st.n_cur = 1; in_step = false;
                 if (gl == 0) glset<T>(ls, 0, 0, (T)0, fullU);
                 mode = RUN;
@@ -244,22 +248,34 @@ __global__ void __launch_bounds__(256) k_calc_d_g(const __grid_constant__ CalcAr
                 num = (uint32_t)a.ix.length;
             }
             st.n_cur = nn;
-            if (gl == 0) D[dlen - 1 - i] = make_int2(z, (int)num);
+            if (gl == 0) {
+                const int k = dlen - 1 - i;
+                if (D) D[k] = make_int2(z, (int)num);
+                if (PK) PK[k] = (uint16_t)((z & 0x1ff) | ((k && num == prev_w) ? 0x8000 : 0));
+            }
+            prev_w = num;
             i--;
             in_step = false;
         }
         if (run && !in_step && i < 0) {              // array complete
-            if (gl == 0) D[dlen] = make_int2(z + 1, 0);
+            if (gl == 0) {
+                if (D) D[dlen] = make_int2(z + 1, 0);
+                if (PK) PK[dlen] = (uint16_t)(((z + 1) & 0x1ff) | ((dlen && prev_w == 0u) ? 0x8000 : 0));
+            }
             if (phase == 0 && a.seed_len > 0) {
-                int2 *Ds = a.d_seed + (size_t)r * (a.seed_len + 1);
+                int2 *Ds = a.d_seed ? a.d_seed + (size_t)r * (a.seed_len + 1) : nullptr;
+                uint16_t *PKs = a.pk_seed ? a.pk_seed + (size_t)r * (a.seed_len + 1) : nullptr;
                 if (len > a.seed_len) {
-                    phase = 1; dlen = a.seed_len; D = Ds;
+                    phase = 1; dlen = a.seed_len; D = Ds; PK = PKs;
                     i = dlen - 1; z = 0; st.cur = 0; st.n_cur = 1;
                     if (gl == 0) glset<T>(ls, 0, 0, (T)0, fullU);
                 } else {
                     // Q6: the reference consults a stale per-thread D_seed for such reads; the defined
                     // behaviour here is the freshly calloc'ed array (all zero)
-                    for (int k = gl; k <= a.seed_len; k += GL) Ds[k] = make_int2(0, 0);
+                    for (int k = gl; k <= a.seed_len; k += GL) {
+                        if (Ds) Ds[k] = make_int2(0, 0);
+                        if (PKs) PKs[k] = (uint16_t)(k ? 0x8000 : 0);
+                    }
                     mode = NEED;
                 }
             } else {
@@ -278,6 +294,15 @@ __global__ void __launch_bounds__(256) k_calc_d_g(const __grid_constant__ CalcAr
 // ---------------------------------------------------------------------------------------------
 // K4: inexact_match, 8 lanes per read
 // ---------------------------------------------------------------------------------------------
+constexpr int POOL_SHARDS = 128;
+constexpr int POOL_BATCH = 8;
+struct PoolState {
+    unsigned long long head[POOL_SHARDS];
+    uint32_t bump[POOL_SHARDS];
+    uint32_t limit[POOL_SHARDS];
+    unsigned long long n_borrowed;      // diagnostics
+};
+
 struct SearchArgs {
     IndexView ix;
     const uint8_t *seq;
@@ -296,7 +321,8 @@ struct SearchArgs {
     uint32_t *chunk_link;
     uint32_t chunks_per_group;
     uint32_t n_chunks;
-    uint32_t *overflow_cursor;
+    uint32_t priv_total;             // chunk ids below this belong to private ranges
+    PoolState *pool;                 // shared pool above them
     bwb_hit *stage;
     int hits_cap;
     bwb_hit *out_hits;
@@ -323,29 +349,92 @@ __device__ __forceinline__ void g_load_bounds(bool on, const int2 *__restrict__ 
 struct GHeap {
     uint32_t *cnt, *top, *bot;    // shared memory, nb each (per group)
     uint32_t priv_hi, bump, free_head;
+    bool took_shared;             // the group holds chunks of the shared pool (returned at flush)
     int n, best;
 };
 
-// group-level chunk allocation for the groups with `need`; every lane of such a group gets the id
-__device__ __forceinline__ uint32_t g_chunk_alloc(bool need, GHeap &h, uint32_t *link, uint32_t *overflow_cursor,
-                                                  uint32_t n_chunks) {
-    uint32_t id = NO_CHUNK, nx = 0;
+// Shared chunk pool = every chunk above the private ranges, split into POOL_SHARDS regions so that no
+// single address serialises the atomics.  Per shard: a lock-free LIFO of returned chunks
+// (head = tag<<32 | chunk id; the tag defeats ABA) in front of a bump cursor.  Chunks move in
+// batches: one CAS pops up to POOL_BATCH chunks or returns a whole chain.  Group leaders only.
+// pops up to POOL_BATCH chunks as a chain first -> ... -> last (links intact); returns the count
+__device__ __forceinline__ int pool_pop_chain(unsigned long long *head, uint32_t *link, uint32_t &first, uint32_t &last) {
+    unsigned long long old = atomicAdd(head, 0ull);
+    for (;;) {
+        first = (uint32_t)old;
+        if (first == NO_CHUNK) return 0;
+        uint32_t cur = first;
+        int n = 1;
+        while (n < POOL_BATCH) {
+            const uint32_t nxt = *reinterpret_cast<volatile uint32_t *>(link + cur);
+            if (nxt == NO_CHUNK) break;
+            cur = nxt;
+            n++;
+        }
+        last = cur;
+        const uint32_t after = *reinterpret_cast<volatile uint32_t *>(link + last);
+        const unsigned long long nw = (((old >> 32) + 1ull) << 32) | after;
+        const unsigned long long prev = atomicCAS(head, old, nw);
+        if (prev == old) return n;
+        old = prev;
+    }
+}
+__device__ __forceinline__ void pool_push_chain(unsigned long long *head, uint32_t *link, uint32_t first, uint32_t last) {
+    unsigned long long old = atomicAdd(head, 0ull);
+    for (;;) {
+        *reinterpret_cast<volatile uint32_t *>(link + last) = (uint32_t)old;
+        __threadfence();
+        const unsigned long long nw = (((old >> 32) + 1ull) << 32) | first;
+        const unsigned long long prev = atomicCAS(head, old, nw);
+        if (prev == old) return;
+        old = prev;
+    }
+}
+
+// leader: refill the group's free list from the shared pool (own shard first); false if exhausted
+__device__ __forceinline__ bool pool_borrow(PoolState *ps, uint32_t *link, uint32_t gid, uint32_t &free_head) {
+    for (int t = 0; t < POOL_SHARDS; t++) {
+        const uint32_t sh = (gid + (uint32_t)t) % POOL_SHARDS;
+        uint32_t first, last;
+        if (pool_pop_chain(&ps->head[sh], link, first, last) > 0) {
+            link[last] = free_head;
+            free_head = first;
+            return true;
+        }
+        if (*reinterpret_cast<volatile uint32_t *>(&ps->bump[sh]) + POOL_BATCH <= ps->limit[sh]) {
+            const uint32_t o = atomicAdd(&ps->bump[sh], (uint32_t)POOL_BATCH);
+            if (o + POOL_BATCH <= ps->limit[sh]) {
+                for (int k = 0; k < POOL_BATCH - 1; k++) link[o + k] = o + k + 1;
+                link[o + POOL_BATCH - 1] = free_head;
+                free_head = o;
+                return true;
+            }
+        }
+    }
+    return false;
+}
+
+// group-level chunk allocation for the groups with `need`; every lane of such a group gets the id.
+// Order: the group's free list, its private range, then a batch from the shared pool.
+__device__ __forceinline__ uint32_t g_chunk_alloc(bool need, GHeap &h, uint32_t *link, PoolState *ps, uint32_t gid) {
+    uint32_t id = NO_CHUNK, nx = 0, how = 0;
     if (need && g_lane() == 0) {
         if (h.free_head != NO_CHUNK) {
-            id = h.free_head;
-            nx = link[id];
+            id = h.free_head; nx = link[id]; how = 1;
         } else if (h.bump < h.priv_hi) {
-            id = h.bump;
+            id = h.bump; how = 2;
         } else {
-            const uint32_t o = atomicAdd(overflow_cursor, 1u);
-            id = o < n_chunks ? o : NO_CHUNK;
+            uint32_t fh = NO_CHUNK;
+            if (pool_borrow(ps, link, gid, fh)) { id = fh; nx = link[id]; how = 3; }
         }
     }
     id = gshfl(id, 0);
     nx = gshfl(nx, 0);
+    how = gshfl(how, 0);
     if (need) {
-        if (h.free_head != NO_CHUNK) h.free_head = nx;
-        else if (h.bump < h.priv_hi) h.bump++;
+        if (how == 1) h.free_head = nx;
+        else if (how == 2) h.bump++;
+        else if (how == 3) { h.free_head = nx; h.took_shared = true; }
     }
     return id;
 }
@@ -375,6 +464,7 @@ __global__ void __launch_bounds__(256, BWB_K4_MIN_BLOCKS) k_search_g(const __gri
     h.bump = gid * a.chunks_per_group;
     h.priv_hi = h.bump + a.chunks_per_group;
     h.free_head = NO_CHUNK;
+    h.took_shared = false;
     h.n = 0; h.best = a.nb;
     bwb_hit *stage = a.stage + (size_t)gid * a.hits_cap;
     const T lastrow = (T)(a.ix.length - 1);
@@ -807,7 +897,7 @@ __global__ void __launch_bounds__(256, BWB_K4_MIN_BLOCKS) k_search_g(const __gri
                         const bool need_new = pg && ((cnt == 0u) || (((cnt + k - 1u) >> 5) != topidx));
                         uint32_t newc = NO_CHUNK;
                         if (__any_sync(FULL, need_new)) {
-                            newc = g_chunk_alloc(need_new, h, a.chunk_link, a.overflow_cursor, a.n_chunks);
+                            newc = g_chunk_alloc(need_new, h, a.chunk_link, a.pool, gid);
                             if (need_new) {
                                 if (newc == NO_CHUNK) err = BWB_ERR_CAPACITY;
                                 else if (gl == 0) {
@@ -857,13 +947,29 @@ __global__ void __launch_bounds__(256, BWB_K4_MIN_BLOCKS) k_search_g(const __gri
                     for (int k = gl; k < n_hits * 3; k += GL) dst[k] = src[k];
                 }
                 if (gl == 0) { a.read_off[r] = base; a.read_cnt[r] = (uint32_t)n_hits; }
-                // give the chunks still held by buckets back to the group's free list
+                // give the chunks still held by buckets back to the group's free list; after a read that
+                // borrowed from the shared pool, hand every shared chunk back (walk of the free list)
                 uint32_t fh = h.free_head;
                 if (gl == 0) {
                     for (int b = 0; b < a.nb; b++)
                         if (h.cnt[b]) { a.chunk_link[h.bot[b]] = fh; fh = h.top[b]; }
+                    if (h.took_shared) {
+                        uint32_t keep = NO_CHUNK, cur = fh, sfirst = NO_CHUNK, slast = NO_CHUNK;
+                        while (cur != NO_CHUNK) {
+                            const uint32_t nxt = a.chunk_link[cur];
+                            if (cur >= a.priv_total) {
+                                if (sfirst == NO_CHUNK) slast = cur;
+                                else a.chunk_link[cur] = sfirst;
+                                sfirst = cur;
+                            } else { a.chunk_link[cur] = keep; keep = cur; }
+                            cur = nxt;
+                        }
+                        if (sfirst != NO_CHUNK) pool_push_chain(&a.pool->head[gid % POOL_SHARDS], a.chunk_link, sfirst, slast);
+                        fh = keep;
+                    }
                 }
                 h.free_head = fh;
+                h.took_shared = false;
             }
             h.free_head = gshfl(h.free_head, 0);
             if (on) { have_next = false; mode = NEED; }

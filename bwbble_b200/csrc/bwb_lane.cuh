@@ -1,0 +1,649 @@
+// bwb_lane.cuh -- K4 "lane engine": one read per LANE, 32 independent reads per warp.
+//
+// Evidence for this mapping (profiles/): with a warp (k_align) or an 8-lane group (k_search_g)
+// per read the kernel is instruction-issue bound (IPC 1.7/SM, DRAM < 2 % of peak) and ~95 % of the
+// issued instructions are per-read *bookkeeping* (entry unpacking, pruning, BWA heuristics, bucket
+// maintenance) that is uniform across the lanes serving the read: ~400 warp instructions per pop.
+// Giving every lane its own read turns that bookkeeping into ordinary SIMT work over 32 reads, and
+// the 2 x 15 rank computations of an expansion into a fully unrolled 15-code loop per lane
+// (compile-time code => the plane XOR folds into LOP3, counters at immediate offsets).
+//
+// Per lane, in HBM (L1/L2 cached):
+//   * one arena of 16-byte slots + a `next` word per slot: heap entries, exact-tail interval
+//     nodes and hit records are all singly linked slot chains; freed slots go to a per-lane free
+//     list; a lane that outgrows its private range borrows 64-slot blocks from a sharded
+//     lock-free pool and returns them when the read is done;
+//   * the bucket heap (priority_heap_t, inexact_match.h:16-34) as nb LIFO linked lists: push =
+//     link in front of the bucket head, pop = unlink the head of the lowest non-empty bucket --
+//     exactly "last entry of the lowest non-empty bucket" (inexact_match.c:594-610).
+// Each loop iteration of a lane is: [take a read] -> [pop + prune + classify] -> [one interval
+// task: the 15-code rank loop, feeding either heap children or the next exact-tail list] ->
+// [flush].  No warp-synchronous intrinsic is needed anywhere: lanes are independent.
+#pragma once
+#include "bwb_group.cuh"
+
+namespace bwb {
+
+constexpr uint32_t NIL = 0xffffffffu;
+constexpr int LBLK = 64;                    // slots per borrowed block
+
+struct LaneArgs {
+    IndexView ix;
+    const uint8_t *seq;
+    const uint64_t *offsets;
+    uint32_t n_reads;
+    uint32_t read_id_base;
+    int max_diff, max_gapo, max_gape, max_entries, mm_score, gapo_score, gape_score;
+    int seed_len, max_diff_seed, max_best, no_indel_len;
+    int nb;
+    uint32_t *queue;
+    const uint16_t *pk_main, *pk_seed;       // packed lower bounds from K3 (see g_pack_bound)
+    uint4 *slots;                            // arena
+    uint32_t *nxt;                           // link word per slot
+    uint32_t slots_per_lane;                 // private range of lane-slot s: [s*spl, (s+1)*spl)
+    uint32_t priv_total;                     // first slot of the shared region (multiple of LBLK)
+    PoolState *pool;                         // shared region, in blocks of LBLK slots
+    uint32_t *blk_link;                      // link word per block (pool free lists, borrowed lists)
+    uint32_t *heads;                         // [n_lanes][nb] bucket heads
+    bwb_hit *out_hits;
+    unsigned long long out_cap;
+    unsigned long long *out_cursor;
+    unsigned long long *read_off;
+    uint32_t *read_cnt;
+    uint32_t *status;
+    unsigned long long *counters;
+};
+
+// ---- per-lane slot allocator --------------------------------------------------------------------
+struct LaneAlloc {
+    uint32_t priv_lo, priv_hi, bump, free_head;
+    uint32_t ov_cur, ov_end;                 // current borrowed block
+    uint32_t borrowed;                       // list of borrowed blocks (through blk_link)
+    uint32_t borrowed_last;
+};
+
+__device__ __forceinline__ uint32_t lane_alloc(LaneAlloc &al, const LaneArgs &a, uint32_t lane_slot) {
+    if (al.free_head != NIL) {
+        const uint32_t s = al.free_head;
+        al.free_head = a.nxt[s];
+        return s;
+    }
+    if (al.bump < al.priv_hi) return al.bump++;
+    if (al.ov_cur < al.ov_end) return al.ov_cur++;
+    // borrow a block from the shared pool (own shard first)
+    for (int t = 0; t < POOL_SHARDS; t++) {
+        const uint32_t sh = (lane_slot + (uint32_t)t) % POOL_SHARDS;
+        uint32_t blk = NIL;
+        {   // pop one block
+            unsigned long long *head = &a.pool->head[sh];
+            unsigned long long old = atomicAdd(head, 0ull);
+            for (;;) {
+                const uint32_t id = (uint32_t)old;
+                if (id == NIL) break;
+                const uint32_t nx = *reinterpret_cast<volatile uint32_t *>(a.blk_link + id);
+                const unsigned long long prev = atomicCAS(head, old, (((old >> 32) + 1ull) << 32) | nx);
+                if (prev == old) { blk = id; break; }
+                old = prev;
+            }
+        }
+        if (blk == NIL && *reinterpret_cast<volatile uint32_t *>(&a.pool->bump[sh]) < a.pool->limit[sh]) {
+            const uint32_t o = atomicAdd(&a.pool->bump[sh], 1u);
+            if (o < a.pool->limit[sh]) blk = o;
+        }
+        if (blk != NIL) {
+            a.blk_link[blk] = al.borrowed;
+            if (al.borrowed == NIL) al.borrowed_last = blk;
+            al.borrowed = blk;
+            al.ov_cur = blk * LBLK;
+            al.ov_end = al.ov_cur + LBLK;
+            return al.ov_cur++;
+        }
+    }
+    return NIL;
+}
+__device__ __forceinline__ void lane_free(LaneAlloc &al, const LaneArgs &a, uint32_t s) {
+    a.nxt[s] = al.free_head;
+    al.free_head = s;
+}
+// end of a read: every slot is dead; hand borrowed blocks back with one CAS
+__device__ __forceinline__ void lane_alloc_reset(LaneAlloc &al, const LaneArgs &a, uint32_t lane_slot) {
+    if (al.borrowed != NIL) {
+        unsigned long long *head = &a.pool->head[lane_slot % POOL_SHARDS];
+        unsigned long long old = atomicAdd(head, 0ull);
+        for (;;) {
+            *reinterpret_cast<volatile uint32_t *>(a.blk_link + al.borrowed_last) = (uint32_t)old;
+            __threadfence();
+            const unsigned long long prev = atomicCAS(head, old, (((old >> 32) + 1ull) << 32) | al.borrowed);
+            if (prev == old) break;
+            old = prev;
+        }
+    }
+    al.bump = al.priv_lo;
+    al.free_head = NIL;
+    al.ov_cur = al.ov_end = 0;
+    al.borrowed = NIL;
+    al.borrowed_last = NIL;
+}
+
+// ---- slot payloads ------------------------------------------------------------------------------
+// heap entry: compact = {L, U, z, w}; wide = {Llo, Ulo, Lhi|Uhi<<8, z} + {w, r1, r2, r3} in a 2nd slot
+// interval node: {Llo, Ulo, Lhi|Uhi<<8, -}
+// hit: slot A = interval node layout with .w = z, slot B = {w, r1, r2, r3}, slot C = {score, alen, -, -}
+template <class T>
+__device__ __forceinline__ uint4 pack_lu(T L, T U, uint32_t last) {
+    if constexpr (sizeof(T) == 8)
+        return make_uint4((uint32_t)L, (uint32_t)U, ((uint32_t)(L >> 32) & 0xffu) | (((uint32_t)(U >> 32) & 0xffu) << 8), last);
+    else
+        return make_uint4((uint32_t)L, (uint32_t)U, 0u, last);
+}
+template <class T>
+__device__ __forceinline__ void unpack_lu(const uint4 &v, T &L, T &U) {
+    if constexpr (sizeof(T) == 8) {
+        L = (uint64_t)v.x | ((uint64_t)(v.z & 0xffu) << 32);
+        U = (uint64_t)v.y | ((uint64_t)((v.z >> 8) & 0xffu) << 32);
+    } else {
+        L = v.x; U = v.y;
+    }
+}
+
+template <bool WIDE>
+struct LaneHeap {
+    typedef typename Coord<WIDE>::type T;
+    uint32_t *heads;
+    int n, best, nb;
+
+    __device__ __forceinline__ bool push(LaneAlloc &al, const LaneArgs &a, uint32_t lane_slot, int sc, T L, T U,
+                                         uint32_t z, uint32_t w, uint32_t r1, uint32_t r2, uint32_t r3) {
+        const uint32_t s = lane_alloc(al, a, lane_slot);
+        if (s == NIL) return false;
+        if constexpr (WIDE) {
+            const uint32_t s2 = lane_alloc(al, a, lane_slot);
+            if (s2 == NIL) return false;
+            a.slots[s] = pack_lu<T>(L, U, z);
+            a.slots[s2] = make_uint4(w, r1, r2, r3);
+            a.nxt[s2] = heads[sc];
+            a.nxt[s] = s2;
+        } else {
+            a.slots[s] = make_uint4(L, U, z, w);
+            a.nxt[s] = heads[sc];
+        }
+        heads[sc] = s;
+        n++;
+        best = min(best, sc);
+        return true;
+    }
+    // heap_pop (inexact_match.c:594-610); returns the bucket
+    __device__ __forceinline__ int pop(LaneAlloc &al, const LaneArgs &a, PE<T> &e) {
+        const int b = best;
+        const uint32_t s = heads[b];
+        const uint4 v = a.slots[s];
+        uint32_t rest;
+        if constexpr (WIDE) {
+            unpack_lu<T>(v, e.L, e.U);
+            e.z = v.w;
+            const uint32_t s2 = a.nxt[s];
+            const uint4 v2 = a.slots[s2];
+            e.w = v2.x; e.r1 = v2.y; e.r2 = v2.z; e.r3 = v2.w;
+            rest = a.nxt[s2];
+            lane_free(al, a, s2);
+        } else {
+            e.L = v.x; e.U = v.y; e.z = v.z; e.w = v.w; e.r1 = e.r2 = e.r3 = 0;
+            rest = a.nxt[s];
+        }
+        lane_free(al, a, s);
+        heads[b] = rest;
+        n--;
+        if (rest == NIL) {
+            int nbst = nb;
+            if (n)
+                for (int q = b + 1; q < nb; q++)
+                    if (heads[q] != NIL) { nbst = q; break; }
+            best = nbst;
+        }
+        return b;
+    }
+};
+
+#ifndef BWB_LANE_MIN_BLOCKS
+#define BWB_LANE_MIN_BLOCKS 4
+#endif
+
+template <bool WIDE>
+__global__ void __launch_bounds__(128, BWB_LANE_MIN_BLOCKS) k_search_l(const __grid_constant__ LaneArgs a) {
+    typedef typename Coord<WIDE>::type T;
+    __shared__ T sC[17];
+    stage_C<T>(a.ix, sC);
+
+    const uint32_t lane_slot = blockIdx.x * blockDim.x + threadIdx.x;
+    const T lastrow = (T)(a.ix.length - 1);
+    LaneAlloc al;
+    al.priv_lo = lane_slot * a.slots_per_lane;
+    al.priv_hi = al.priv_lo + a.slots_per_lane;
+    al.bump = al.priv_lo;
+    al.free_head = NIL;
+    al.ov_cur = al.ov_end = 0;
+    al.borrowed = NIL;
+    al.borrowed_last = NIL;
+    LaneHeap<WIDE> h;
+    h.heads = a.heads + (size_t)lane_slot * a.nb;
+    h.nb = a.nb;
+    h.n = 0;
+    h.best = a.nb;
+
+    enum { NEED = 0, SEARCH = 1, TAIL = 2, FLUSH = 3 };
+    int mode = NEED;
+    uint32_t r = 0, read_id = 0;
+    int len = 0, err = 0;
+    uint64_t off = 0;
+    const uint16_t *D = nullptr, *Ds = nullptr;
+    const uint8_t *rseq = nullptr;
+    int best_score = 0, max_diff = 0, num_best = 0, n_hits = 0;
+    uint32_t hit_head = NIL, hit_tail = NIL;
+    // the interval task of this iteration
+    bool have_task = false, task_tail = false;
+    PE<T> e;                                  // expansion: the popped entry; tail: its L,U hold the interval
+    e.L = 0; e.U = 0; e.z = 0; e.w = 0; e.r1 = e.r2 = e.r3 = 0;
+    int eb = 0;                               // bucket (= score) of e
+    uint32_t t_flags = 0;                     // expansion flags, see below
+    uint32_t cbase = 0;                       // read base of this step (rc[i-1])
+    // exact tail in progress
+    PE<T> te = e;
+    int t_bucket = 0, t_r = 0;
+    uint32_t cur_head = NIL, nx_head = NIL, nx_tail = NIL;
+    int nx_n = 0;
+    T nx_tailL = 0, nx_tailU = 0;
+
+    unsigned long long c_pops = 0, c_push = 0, c_tails = 0, c_rank = 0;
+    uint32_t c_maxheap = 0, c_maxlist = 0;
+
+    for (;;) {
+        // ================= take the next read =================
+        if (mode == NEED) {
+            r = atomicAdd(a.queue, 1u);
+            if (r >= a.n_reads) break;
+            off = a.offsets[r];
+            len = (int)(a.offsets[r + 1] - off);
+            read_id = a.read_id_base + r;
+            rseq = a.seq + off;
+            D = a.pk_main + off + r;
+            Ds = a.pk_seed + (size_t)r * (a.seed_len + 1);
+            int nN = 0;
+            for (int k = 0; k < len; k++) nN += (rseq[k] > 3);
+            for (int b = 0; b < a.nb; b++) h.heads[b] = NIL;
+            h.n = 0; h.best = a.nb;
+            n_hits = 0; hit_head = hit_tail = NIL; err = 0;
+            best_score = a.nb; max_diff = a.max_diff; num_best = 0;
+            have_task = false;
+            if (nN <= a.max_diff) {                                   // N pre-check, inexact_match.c:259-266
+                if (!h.push(al, a, lane_slot, 0, (T)0, lastrow, (uint32_t)len, 0u, 0u, 0u, 0u)) err = BWB_ERR_CAPACITY;
+                c_push++;
+                mode = err ? FLUSH : SEARCH;
+            } else {
+                mode = FLUSH;
+            }
+        }
+
+        // ================= pop + prune + classify (inexact_match.c:293-375) =================
+        if (mode == SEARCH) {
+            if ((uint32_t)h.n > c_maxheap) c_maxheap = (uint32_t)h.n;
+            if (h.n == 0 || h.n > a.max_entries) {
+                mode = FLUSH;
+            } else {
+                eb = h.pop(al, a, e);
+                c_pops++;
+                const uint32_t z = e.z;
+                const int ei = (int)(z & 0xffu);
+                const int go = (int)((z >> 24) & 15u), ge = (int)((z >> 16) & 0xffu);
+                const int used = (int)((z >> 8) & 0xffu) + go + ge;
+                const uint32_t state = (z >> 28) & 3u;
+                const int dl = max_diff - used;
+                const int dls = a.max_diff_seed - used;
+                const int si = ei - (len - a.seed_len);
+                if ((eb & 0xff) > best_score + a.mm_score) {
+                    mode = FLUSH;                                       // inexact_match.c:309
+                } else if (dl < 0 || (ei > 0 && dl < (int)(D[ei - 1] & 0x1ff)) ||
+                           (si > 0 && dls < (int)(Ds[si - 1] & 0x1ff))) {
+                    // pruned
+                } else if (ei == 0) {                                   // a hit (inexact_match.c:331-344)
+                    bool add = true;
+                    if (n_hits == 0) {
+                        best_score = eb;
+                        max_diff = (used + 1 > a.max_diff) ? a.max_diff : used + 1;
+                    }
+                    if (eb == best_score) num_best = (int)((uint32_t)num_best + (uint32_t)(e.U - e.L + 1));
+                    else if (num_best > a.max_best) { mode = FLUSH; add = false; }
+                    if (add && go) {                                    // align.c:273-280
+                        for (uint32_t q = hit_head; q != NIL;) {
+                            T hL, hU;
+                            unpack_lu<T>(a.slots[q], hL, hU);
+                            if (hL == e.L && hU == e.U) { add = false; break; }
+                            q = a.nxt[a.nxt[a.nxt[q]]];
+                        }
+                    }
+                    if (add) {
+                        const uint32_t alen = ((uint32_t)(len - ei) + (e.w & 0xffu)) & 0xffu;
+                        const uint32_t sa = lane_alloc(al, a, lane_slot), sb = lane_alloc(al, a, lane_slot),
+                                       scs = lane_alloc(al, a, lane_slot);
+                        if (sa == NIL || sb == NIL || scs == NIL) { err = BWB_ERR_CAPACITY; mode = FLUSH; }
+                        else {
+                            a.slots[sa] = pack_lu<T>(e.L, e.U, z);
+                            a.slots[sb] = make_uint4(e.w, e.r1, e.r2, e.r3);
+                            a.slots[scs] = make_uint4((uint32_t)eb, alen, 0u, 0u);
+                            a.nxt[sa] = sb; a.nxt[sb] = scs; a.nxt[scs] = NIL;
+                            if (hit_tail == NIL) hit_head = sa; else a.nxt[hit_tail] = sa;
+                            hit_tail = scs;
+                            n_hits++;
+                        }
+                    }
+                } else if (dl == 0) {                                   // exact tail (inexact_match.c:345-375)
+                    c_tails++;
+                    te = e; t_bucket = eb; t_r = ei - 1;
+                    const uint32_t s = lane_alloc(al, a, lane_slot);
+                    if (s == NIL) { err = BWB_ERR_CAPACITY; mode = FLUSH; }
+                    else {
+                        a.slots[s] = pack_lu<T>(e.L, e.U, 0u);
+                        a.nxt[s] = NIL;
+                        cur_head = s; nx_head = nx_tail = NIL; nx_n = 0;
+                        mode = TAIL;
+                    }
+                } else {
+                    // ---- expansion: BWA heuristics (inexact_match.c:391-430) -> flags for the task
+                    bool allow_diff = true, allow_mm = true;
+                    const int i1 = ei - 1;
+                    if (i1 > 0) {
+                        const uint32_t d1 = D[i1], d0 = D[i1 - 1];
+                        if (dl - 1 < (int)(d0 & 0x1ff)) allow_diff = false;
+                        else if ((int)(d1 & 0x1ff) == dl - 1 && (int)(d0 & 0x1ff) == dl - 1 && (d1 & 0x8000u)) allow_mm = false;
+                    }
+                    if (si - 1 > 0) {
+                        const uint32_t s1 = Ds[si - 1], s0 = Ds[si - 2];
+                        if (dls - 1 < (int)(s0 & 0x1ff)) allow_diff = false;
+                        else if ((int)(s1 & 0x1ff) == dls - 1 && (int)(s0 & 0x1ff) == dls - 1 && (s1 & 0x8000u)) allow_mm = false;
+                    }
+                    const int gaps = go + ge;
+                    const bool allow_indels = !(i1 < a.no_indel_len + gaps || len - i1 < a.no_indel_len + gaps) &&
+                                              !(go >= a.max_gapo && ge >= a.max_gape);
+                    const bool opening = (state == 0u);
+                    const bool gap_allowed = allow_diff && allow_indels && (opening ? (go < a.max_gapo) : (ge < a.max_gape));
+                    // bit0 full (mismatch children allowed), bit1 deletions allowed, bit2 insertion allowed
+                    t_flags = ((allow_diff && allow_mm) ? 1u : 0u) | ((gap_allowed && state != 1u) ? 2u : 0u) |
+                              ((gap_allowed && state != 2u) ? 4u : 0u);
+                    cbase = nt4_compl(rseq[len - 1 - i1]);              // rc[i-1]
+                    have_task = true;
+                    task_tail = false;
+                }
+            }
+        }
+
+        // ================= exact tail: next interval of the current level, or level end =================
+        if (mode == TAIL && !have_task) {
+            if (cur_head != NIL) {
+                const uint32_t s = cur_head;
+                unpack_lu<T>(a.slots[s], e.L, e.U);
+                cur_head = a.nxt[s];
+                lane_free(al, a, s);
+                cbase = nt4_compl(rseq[len - 1 - t_r]);
+                if (cbase > 3u) {                                       // N never matches (exact_match.c:84-87):
+                    while (cur_head != NIL) { const uint32_t q = cur_head; cur_head = a.nxt[q]; lane_free(al, a, q); }
+                    while (nx_head != NIL) { const uint32_t q = nx_head; nx_head = a.nxt[q]; lane_free(al, a, q); }
+                    mode = SEARCH;                                      // empty result
+                } else {
+                    have_task = true;
+                    task_tail = true;
+                }
+            } else {                                                    // level finished
+                if (nx_n) { a.slots[nx_tail] = pack_lu<T>(nx_tailL, nx_tailU, 0u); }
+                if ((uint32_t)nx_n > c_maxlist) c_maxlist = (uint32_t)nx_n;
+                if (nx_n == 0) {
+                    mode = SEARCH;                                      // no match
+                } else if (t_r > 0) {
+                    t_r--;
+                    cur_head = nx_head; nx_head = nx_tail = NIL; nx_n = 0;
+                } else {
+                    // tail matched: bookkeeping of a hit, once per interval (inexact_match.c:347-371)
+                    const uint32_t z = te.z;
+                    const int ei = (int)(z & 0xffu);
+                    const int go = (int)((z >> 24) & 15u);
+                    const int used = (int)((z >> 8) & 0xffu) + go + (int)((z >> 16) & 0xffu);
+                    bool stop = false;
+                    if (n_hits == 0) {
+                        best_score = t_bucket;
+                        max_diff = (used + 1 > a.max_diff) ? a.max_diff : used + 1;
+                    }
+                    if (t_bucket == best_score) {
+                        uint32_t wsum = 0;
+                        for (uint32_t q = nx_head; q != NIL; q = a.nxt[q]) {
+                            T L, U;
+                            unpack_lu<T>(a.slots[q], L, U);
+                            wsum += (uint32_t)(U - L + 1);
+                        }
+                        num_best = (int)((uint32_t)num_best + wsum);
+                    } else if (num_best > a.max_best) stop = true;
+                    const uint32_t alen2 = ((uint32_t)(len - ei) + (te.w & 0xffu) + (uint32_t)ei) & 0xffu;
+                    const uint32_t old_tail = hit_tail;                 // dedupe only against earlier hits
+                    uint32_t q = nx_head;
+                    while (q != NIL) {
+                        const uint32_t qn = a.nxt[q];
+                        bool add = !stop && !err;
+                        T L, U;
+                        unpack_lu<T>(a.slots[q], L, U);
+                        if (add && go && old_tail != NIL) {
+                            for (uint32_t p = hit_head;;) {
+                                T hL, hU;
+                                unpack_lu<T>(a.slots[p], hL, hU);
+                                if (hL == L && hU == U) { add = false; break; }
+                                const uint32_t pc = a.nxt[a.nxt[p]];
+                                if (pc == old_tail) break;
+                                p = a.nxt[pc];
+                            }
+                        }
+                        if (add) {
+                            // re-use the node as slot A of the hit
+                            const uint32_t sb = lane_alloc(al, a, lane_slot), scs = lane_alloc(al, a, lane_slot);
+                            if (sb == NIL || scs == NIL) { err = BWB_ERR_CAPACITY; lane_free(al, a, q); }
+                            else {
+                                a.slots[q] = pack_lu<T>(L, U, z);
+                                a.slots[sb] = make_uint4(te.w, te.r1, te.r2, te.r3);
+                                a.slots[scs] = make_uint4((uint32_t)t_bucket, alen2, 0u, 0u);
+                                a.nxt[q] = sb; a.nxt[sb] = scs; a.nxt[scs] = NIL;
+                                if (hit_tail == NIL) hit_head = q; else a.nxt[hit_tail] = q;
+                                hit_tail = scs;
+                                n_hits++;
+                            }
+                        } else {
+                            lane_free(al, a, q);
+                        }
+                        q = qn;
+                    }
+                    nx_head = nx_tail = NIL; nx_n = 0;
+                    mode = (stop || err) ? FLUSH : SEARCH;
+                }
+            }
+        }
+
+        // ================= the interval task: 15-code rank loop =================
+        if (have_task) {
+            have_task = false;
+            const T iL = (T)(e.L - 1), iU = e.U;
+            const bool negL = (e.L == 0), topU = (iU == lastrow);
+            const T aL = negL ? (T)0 : iL, aU = topU ? (T)0 : iU;
+            const uint4 *blkU = a.ix.blocks + (size_t)(aU >> 7) * 8;
+            const uint4 *blkL = a.ix.blocks + (size_t)(aL >> 7) * 8;
+            const Planes pu = load_planes(blkU);
+            Planes pl = pu;
+            if (blkL != blkU) pl = load_planes(blkL);
+            c_rank += 2;
+            // 128-bit masks of rows 0..r of both blocks
+            uint32_t kU0, kU1, kU2, kU3, kL0, kL1, kL2, kL3;
+            {
+                const int n = (int)(aU & 127u) + 1;
+                kU0 = n >= 32 ? ~0u : ((1u << n) - 1u);
+                kU1 = n >= 64 ? ~0u : (n <= 32 ? 0u : ((1u << (n - 32)) - 1u));
+                kU2 = n >= 96 ? ~0u : (n <= 64 ? 0u : ((1u << (n - 64)) - 1u));
+                kU3 = n >= 128 ? ~0u : (n <= 96 ? 0u : ((1u << (n - 96)) - 1u));
+                const int m = (int)(aL & 127u) + 1;
+                kL0 = m >= 32 ? ~0u : ((1u << m) - 1u);
+                kL1 = m >= 64 ? ~0u : (m <= 32 ? 0u : ((1u << (m - 32)) - 1u));
+                kL2 = m >= 96 ? ~0u : (m <= 64 ? 0u : ((1u << (m - 64)) - 1u));
+                kL3 = m >= 128 ? ~0u : (m <= 96 ? 0u : ((1u << (m - 96)) - 1u));
+            }
+            const uint32_t *cntU = reinterpret_cast<const uint32_t *>(blkU);
+            const uint32_t *cntL = reinterpret_cast<const uint32_t *>(blkL);
+
+            // expansion-only values
+            const uint32_t z = e.z;
+            const int go = (int)((z >> 24) & 15u);
+            const bool opening = ((z >> 28) & 3u) == 0u;
+            const uint32_t cmask = (0x01428u >> (4u * cbase)) & 15u;       // nt4_gray_val; 0 for N
+            const uint32_t compat = task_tail ? compat_codes(cbase & 3u) : 0u;
+            // set of codes the tail may extend with, as a bit mask
+            uint32_t cset = 0;
+            if (task_tail) {
+#pragma unroll
+                for (int k = 0; k < 7; k++) cset |= 1u << ((compat >> (4 * k)) & 15u);
+            }
+            const int b0 = eb, b1 = eb + a.mm_score, b2 = eb + (opening ? a.gapo_score : a.gape_score);
+            const bool full = t_flags & 1u, del_ok = t_flags & 2u, ins_ok = t_flags & 4u;
+            const uint32_t alen = task_tail ? 0u : (((uint32_t)(len - (int)(z & 0xffu)) + (e.w & 0xffu)) & 0xffu);
+            // gap children share everything but L,U,state
+            const uint32_t zg = (z & ~(3u << 28)) + (opening ? (1u << 24) : (1u << 16));
+            uint32_t wI = e.w, wD = e.w + 1u, r1I = e.r1, r2I = e.r2, r3I = e.r3, r1D = e.r1, r2D = e.r2, r3D = e.r3;
+            if (!task_tail) {
+                const uint32_t newrunI = alen | (1u << 8) | (1u << 16), newrunD = alen | (1u << 8) | (2u << 16);
+                if (opening) {
+                    if (go == 0) { wI = (wI & 0xffu) | (newrunI << 8); wD = (wD & 0xffu) | (newrunD << 8); }
+                    else if (WIDE && go == 1) { r1I = newrunI; r1D = newrunD; }
+                    else if (WIDE && go == 2) { r2I = newrunI; r2D = newrunD; }
+                    else if (WIDE) { r3I = newrunI; r3D = newrunD; }
+                } else {
+                    if (go == 1) { wI += 1u << 16; wD += 1u << 16; }
+                    else if (WIDE && go == 2) { r1I += 1u << 8; r1D += 1u << 8; }
+                    else if (WIDE && go == 3) { r2I += 1u << 8; r2D += 1u << 8; }
+                    else if (WIDE && go == 4) { r3I += 1u << 8; r3D += 1u << 8; }
+                }
+            }
+            const uint32_t zm = (z - 1u) & ~(3u << 28);
+            // When a gap bucket coincides with a match/mismatch bucket the reference's push order
+            // (insertion, all deletions, then all matches/mismatches, :433-504) needs two passes.
+            const bool two_pass = !task_tail && (del_ok || ins_ok) && (b2 == b0 || b2 == b1);
+            bool ok_all = true;
+            if (!task_tail && ins_ok) {                                  // insertion child first (:435-444)
+                ok_all = h.push(al, a, lane_slot, b2, e.L, e.U, (zg | (1u << 28)) - 1u, wI, r1I, r2I, r3I);
+                c_push++;
+            }
+            for (int pass = 0; pass < (two_pass ? 2 : 1); pass++) {
+                const bool do_del = del_ok && (pass == 0);
+                const bool do_mm = !two_pass || pass == 1;
+#pragma unroll
+                for (int j = 1; j < 16; j++) {
+                    const uint32_t x0 = (j & 1) ? 0u : ~0u, x1 = (j & 2) ? 0u : ~0u, x2 = (j & 4) ? 0u : ~0u, x3 = (j & 8) ? 0u : ~0u;
+                    const uint32_t u0 = (pu.p0.x ^ x0) & (pu.p1.x ^ x1) & (pu.p2.x ^ x2) & (pu.p3.x ^ x3);
+                    const uint32_t u1 = (pu.p0.y ^ x0) & (pu.p1.y ^ x1) & (pu.p2.y ^ x2) & (pu.p3.y ^ x3);
+                    const uint32_t u2 = (pu.p0.z ^ x0) & (pu.p1.z ^ x1) & (pu.p2.z ^ x2) & (pu.p3.z ^ x3);
+                    const uint32_t u3 = (pu.p0.w ^ x0) & (pu.p1.w ^ x1) & (pu.p2.w ^ x2) & (pu.p3.w ^ x3);
+                    const uint32_t l0 = (pl.p0.x ^ x0) & (pl.p1.x ^ x1) & (pl.p2.x ^ x2) & (pl.p3.x ^ x3);
+                    const uint32_t l1 = (pl.p0.y ^ x0) & (pl.p1.y ^ x1) & (pl.p2.y ^ x2) & (pl.p3.y ^ x3);
+                    const uint32_t l2 = (pl.p0.z ^ x0) & (pl.p1.z ^ x1) & (pl.p2.z ^ x2) & (pl.p3.z ^ x3);
+                    const uint32_t l3 = (pl.p0.w ^ x0) & (pl.p1.w ^ x1) & (pl.p2.w ^ x2) & (pl.p3.w ^ x3);
+                    const uint32_t vU = __ldg(cntU + j) + __popc(u0 & kU0) + __popc(u1 & kU1) + __popc(u2 & kU2) + __popc(u3 & kU3);
+                    const uint32_t vL = __ldg(cntL + j) + __popc(l0 & kL0) + __popc(l1 & kL1) + __popc(l2 & kL2) + __popc(l3 & kL3);
+                    // Q1: O_alphabet skips codes 5,9,11,13 except for the checkpoint-symbol decrement
+                    // (bwt.c:427-435,780); the exact search's O() counts them (bwt.c:348-372)
+                    const bool quirk = (j == 5 || j == 9 || j == 11 || j == 13);
+                    const T Cj = sC[j], Cj1 = sC[j + 1];
+                    T Lj, Uj;
+                    if (quirk && !task_tail) {
+                        Lj = (T)((negL ? Cj : (T)(Cj - (T)(l0 & 1u))) + 1);
+                        Uj = topU ? Cj1 : (T)(Cj - (T)(u0 & 1u));
+                    } else {
+                        Lj = (T)(Cj + (negL ? (T)0 : (T)vL) + 1);
+                        Uj = topU ? Cj1 : (T)(Cj + (T)vU);
+                    }
+                    if (Lj <= Uj) {
+                        if (task_tail) {
+                            if ((cset >> j) & 1u) {                      // ordered append with adjacent merge (align.c:93-110)
+                                if (nx_n && Lj == (T)(nx_tailU + 1)) {
+                                    nx_tailU = Uj;
+                                } else {
+                                    const uint32_t s = lane_alloc(al, a, lane_slot);
+                                    if (s == NIL) { ok_all = false; }
+                                    else {
+                                        if (nx_n) { a.slots[nx_tail] = pack_lu<T>(nx_tailL, nx_tailU, 0u); a.nxt[nx_tail] = s; }
+                                        else nx_head = s;
+                                        a.nxt[s] = NIL;
+                                        nx_tail = s; nx_tailL = Lj; nx_tailU = Uj;
+                                        nx_n++;
+                                    }
+                                }
+                            }
+                        } else {
+                            if (do_del) {                                // deletion of code j (:445-461)
+                                ok_all &= h.push(al, a, lane_slot, b2, Lj, Uj, zg | (2u << 28), wD, r1D, r2D, r3D);
+                                c_push++;
+                            }
+                            if (do_mm) {                                 // match / mismatch (:467-497)
+                                const uint32_t gray = (uint32_t)((0x89BAEFDC45762310ull >> (4 * j)) & 15ull);
+                                const bool is_mm = (j == 10) || ((cmask & gray) == 0u);
+                                if (full || !is_mm) {
+                                    ok_all &= h.push(al, a, lane_slot, is_mm ? b1 : b0, Lj, Uj, zm + (is_mm ? 0x100u : 0u),
+                                                     e.w, e.r1, e.r2, e.r3);
+                                    c_push++;
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+            if (!ok_all) { err = BWB_ERR_CAPACITY; mode = FLUSH; }
+        }
+
+        // ================= flush: hits -> output group (K5 restores input order) =================
+        if (mode == FLUSH) {
+            if (err) {
+                if (atomicCAS(a.status, 0u, (uint32_t)(-err)) == 0u) a.status[1] = read_id;
+                n_hits = 0;
+            }
+            const unsigned long long base = atomicAdd(a.out_cursor, (unsigned long long)n_hits);
+            if (base + n_hits <= a.out_cap) {
+                uint32_t q = hit_head;
+                for (int k = 0; k < n_hits; k++) {
+                    const uint4 va = a.slots[q];
+                    const uint32_t sb = a.nxt[q];
+                    const uint4 vb = a.slots[sb];
+                    const uint32_t scs = a.nxt[sb];
+                    const uint4 vc = a.slots[scs];
+                    T L, U;
+                    unpack_lu<T>(va, L, U);
+                    const uint32_t z = va.w, go = (z >> 24) & 15u;
+                    bwb_hit ht;
+                    ht.L = (uint64_t)L; ht.U = (uint64_t)U; ht.score = (int32_t)vc.x;
+                    ht.num_mm = (uint8_t)((z >> 8) & 0xffu); ht.num_gapo = (uint8_t)go; ht.num_gape = (uint8_t)((z >> 16) & 0xffu);
+                    ht.aln_length = (uint8_t)vc.y; ht.n_runs = (uint8_t)go; ht.pad[0] = ht.pad[1] = ht.pad[2] = 0;
+                    ht.read_id = read_id;
+                    const uint32_t rr4[BWB_MAX_GAP_RUNS] = {vb.x >> 8, vb.y, vb.z, vb.w};
+#pragma unroll
+                    for (int t = 0; t < BWB_MAX_GAP_RUNS; t++) {
+                        const uint32_t v = (uint32_t)t < go ? rr4[t] : 0u;
+                        ht.runs[t].start = (uint8_t)(v & 0xffu); ht.runs[t].len = (uint8_t)((v >> 8) & 0xffu);
+                        ht.runs[t].state = (uint8_t)((v >> 16) & 0xffu); ht.runs[t].pad = 0;
+                    }
+                    a.out_hits[base + k] = ht;
+                    q = a.nxt[scs];
+                }
+            }
+            a.read_off[r] = base;
+            a.read_cnt[r] = (uint32_t)n_hits;
+            lane_alloc_reset(al, a, lane_slot);
+            mode = NEED;
+        }
+    }
+
+    atomicAdd(a.counters + 0, c_pops);
+    atomicAdd(a.counters + 1, c_push);
+    atomicAdd(a.counters + 2, c_tails);
+    atomicAdd(a.counters + 3, c_rank);
+    atomicMax(a.counters + 4, (unsigned long long)c_maxheap);
+    atomicMax(a.counters + 5, (unsigned long long)c_maxlist);
+}
+
+}  // namespace bwb

@@ -11,16 +11,16 @@ from bwbble_b200.aln import first_difference
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module", params=["group-idx32", "group-idx64", "warp-idx32", "warp-idx64"])
+@pytest.fixture(scope="module", params=["lane-idx32", "lane-idx64", "group-idx32", "group-idx64", "warp-idx32", "warp-idx64"])
 def gpu_case(small_case, request):
-    """group = production engine (8 lanes per read: k_calc_d_g + k_search_g), warp = k_align (A/B);
+    """lane = production engine (one read per lane: k_calc_d_g + k_search_l); group (8 lanes per read)
+    and warp (k_align) are the A/B baselines the profiles compare against;
     idx32 = 32-bit SA coordinates + 16-byte heap entries (indexes < 2^32 rows, max_gapo <= 1);
     idx64 = the wide kernels (genome-scale format) forced onto the same small index."""
     al = Aligner(heap_pool_mb=512, hits_per_read=256, list_cap=1024)
     if request.param.endswith("idx64"):
         al.set_option("force_wide", 1)
-    if request.param.startswith("warp"):
-        al.set_option("engine", 1)
+    al.set_option("engine", {"lane": 0, "warp": 1, "group": 2}[request.param.split("-")[0]])
     al.load_index(small_case["bwt"])
     orc = oracle.Oracle(small_case["bwt"])
     yield {"al": al, "orc": orc, **small_case}
@@ -203,6 +203,23 @@ def test_align_aln_bytes_equal_oracle(gpu_case, kw):
     assert ctr["exact_tails"] == st["exact_tail_calls"]
     assert ctr["max_heap"] == st["max_heap"]
     res.close()
+
+
+def test_tiny_private_ranges_use_the_shared_chunk_pool(small_case):
+    """heap_pool_mb=1 shrinks every private chunk range to the minimum, so the bucket heaps live
+    on the shared lock-free pool (borrow at push, hand back at flush)."""
+    al = Aligner(heap_pool_mb=1, hits_per_read=256, list_cap=1024)
+    al.load_index(small_case["bwt"])
+    orc = oracle.Oracle(small_case["bwt"])
+    reads = small_case["reads"]
+    p = default_params(n=5)
+    for _ in range(2):          # second call re-uses the pool after the per-call reset
+        got = al.align(reads.seq, reads.offsets, p).aln_bytes()
+        exp, st = orc.align(reads.seq, reads.offsets, p)
+        assert got == exp, first_difference(got, exp)
+    assert st["max_heap"] > 1024
+    orc.close()
+    al.close()
 
 
 def test_align_ragged_lengths_and_n_reads(gpu_case):
