@@ -41,7 +41,7 @@ class AlignResult:
         self._h = C.c_void_p(handle)
 
     def close(self):
-        if self._h:
+        if self._h and _lib is not None and _lib.lib is not None:
             _lib.lib().bwb_results_free(self._h)
             self._h = None
 
@@ -111,7 +111,7 @@ class DeviceReads:
         self.n = n
 
     def close(self):
-        if self._h:
+        if self._h and _lib is not None and _lib.lib is not None:
             _lib.lib().bwb_reads_free(self._h)
             self._h = None
 
@@ -137,7 +137,7 @@ class Aligner:
         self.index: Optional[BwtIndex] = None
 
     def close(self):
-        if getattr(self, "_ctx", None):
+        if getattr(self, "_ctx", None) and _lib is not None and _lib.lib is not None:
             _lib.lib().bwb_destroy(self._ctx)
             self._ctx = None
 

@@ -45,8 +45,9 @@ struct Device {
     uint32_t chunks_per_warp = 0, n_chunks = 0;
     // per-call buffers
     DevBuf seq, offsets, read_off, read_cnt, ordered_off, unordered, ordered, cub_tmp, small, d_main, d_seed, pool;
-    DevBuf pk_main, pk_seed, nxt, blk_link, heads;      // lane engine
+    DevBuf pk_main, pk_seed, n_count, nxt, blk_link, heads;      // lane engine
     uint32_t slots_per_lane = 0, total_slots = 0, priv_total = 0;
+    uint64_t auto_pool_bytes = 0;
     int engine = -1;          // engine the scratch was sized for
     // pinned staging for small D2H
     unsigned long long *h_small = nullptr;
@@ -63,7 +64,7 @@ struct bwb_ctx {
     uint64_t length = 0, num_blocks = 0, sa0 = 0;
     uint64_t C[17] = {0};
     // options
-    long long heap_pool_mb = 8192;
+    long long heap_pool_mb = 0;      // 0 = auto: half of the free device memory, at most 64 GB
     int list_cap = 4096;
     int hits_per_read = 512;
     int warps_per_block = 8;
@@ -221,7 +222,7 @@ int prepare_search_group(bwb_ctx *ctx, Device &d, const SmemLayout &L, bool wide
     {
         // chunk = 32 entries of 16 B (compact) or 32 B (wide); 3/4 of the pool is split into private
         // ranges (no atomics on the common path), 1/4 is shared between all groups
-        uint64_t pool_bytes = (uint64_t)ctx->heap_pool_mb << 20;
+        uint64_t pool_bytes = (uint64_t)(ctx->heap_pool_mb > 0 ? ctx->heap_pool_mb : 8192) << 20;
         if (pool_bytes < (uint64_t)n_groups * 16 * 1024) pool_bytes = (uint64_t)n_groups * 16 * 1024;
         const size_t chunk_bytes = (size_t)CHUNK_ENTRIES * (wide ? 32 : 16);
         uint64_t n_chunks = pool_bytes / chunk_bytes;
@@ -236,39 +237,51 @@ int prepare_search_group(bwb_ctx *ctx, Device &d, const SmemLayout &L, bool wide
 
 // size the persistent grid and the per-lane arena for the lane engine (K3 groups + K4 lanes)
 int prepare_search_lane(bwb_ctx *ctx, Device &d, int nb, bool wide) {
+    if (nb > 128) return fail(ctx, BWB_ERR_UNSUPPORTED, "%d score buckets: the lane engine keeps the occupancy of at most 128 in registers", nb);
     CU(cudaSetDevice(d.id));
     const int tpb = 128;
+    const size_t smem = (size_t)nb * tpb * 4;                 // bucket heads [nb][128]
+    if (wide) CU(cudaFuncSetAttribute(k_search_l<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    else CU(cudaFuncSetAttribute(k_search_l<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int bps = ctx->blocks_per_sm;
     if (bps <= 0) {
-        if (wide) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_search_l<true>, tpb, 0));
-        else CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_search_l<false>, tpb, 0));
+        if (wide) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_search_l<true>, tpb, smem));
+        else CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_search_l<false>, tpb, smem));
         if (bps <= 0) return fail(ctx, BWB_ERR_CUDA, "k_search_l does not fit on an SM");
     }
     const int grid = bps * d.sm_count;
     const int n_lanes = grid * tpb;
     if (n_lanes != d.n_warps || d.engine != 0) {
         release(d.glists); release(d.chunks); release(d.chunk_link); release(d.stage);
-        release(d.nxt); release(d.blk_link); release(d.heads);
+        release(d.blk_link);
         d.n_warps = n_lanes; d.engine = 0;
     }
-    d.grid = grid; d.wpb = tpb / 32; d.smem_bytes = 0;
+    d.grid = grid; d.wpb = tpb / 32; d.smem_bytes = smem;
     int rc;
-    // K3 still runs 8-lane groups: its list scratch is sized for the same grid of 256-thread blocks
+    // K3 still runs 8-lane groups: its list scratch is sized for its own grid of 256-thread blocks
     const int n_groups3 = (grid / 2 + 1) * (256 / GL);
     if ((rc = ensure(ctx, d.glists, (size_t)n_groups3 * 2 * ctx->list_cap * sizeof(ulonglong2), false))) return rc;
-    if ((rc = ensure(ctx, d.heads, (size_t)n_lanes * nb * 4, false))) return rc;
     {
-        // arena: 16-byte slot + 4-byte link; 3/4 split into private ranges, 1/4 shared in 64-slot blocks
+        // arena of 32-byte slots: 3/4 split into private ranges, 1/4 shared in blocks of LBLK slots
         uint64_t pool_bytes = (uint64_t)ctx->heap_pool_mb << 20;
-        uint64_t total = pool_bytes / 20;
-        if (total < (uint64_t)n_lanes * 256) total = (uint64_t)n_lanes * 256;
+        if (ctx->heap_pool_mb <= 0) {
+            if (d.chunks.p) pool_bytes = d.auto_pool_bytes;           // keep the size chosen at first use
+            else {
+                size_t fr = 0, tot = 0;
+                CU(cudaMemGetInfo(&fr, &tot));
+                pool_bytes = (uint64_t)fr / 2;
+                if (pool_bytes > (64ull << 30)) pool_bytes = 64ull << 30;
+                d.auto_pool_bytes = pool_bytes;
+            }
+        }
+        uint64_t total = pool_bytes / 32;
+        if (total < (uint64_t)n_lanes * 512) total = (uint64_t)n_lanes * 512;
         if (total > 0xfffff000ull) total = 0xfffff000ull;
         total &= ~(uint64_t)(LBLK - 1);
         uint32_t spl = (uint32_t)((total - total / 4) / n_lanes);
         uint64_t priv = ((uint64_t)spl * n_lanes + LBLK - 1) & ~(uint64_t)(LBLK - 1);
         d.slots_per_lane = spl; d.total_slots = (uint32_t)total; d.priv_total = (uint32_t)priv;
-        if ((rc = ensure(ctx, d.chunks, total * 16, false))) return rc;
-        if ((rc = ensure(ctx, d.nxt, total * 4, false))) return rc;
+        if ((rc = ensure(ctx, d.chunks, total * 32, false))) return rc;
         if ((rc = ensure(ctx, d.blk_link, (total / LBLK + 1) * 4, false))) return rc;
     }
     return BWB_OK;
@@ -301,7 +314,7 @@ int prepare_search(bwb_ctx *ctx, Device &d, const SmemLayout &L, bool wide) {
     if ((rc = ensure(ctx, d.stage, (size_t)n_warps * ctx->hits_per_read * sizeof(bwb_hit), false))) return rc;
     if (!d.chunks.p) {
         const size_t chunk_bytes = (size_t)CHUNK_ENTRIES * 32;   // sized for the 32-byte entry format
-        uint64_t n_chunks = ((uint64_t)ctx->heap_pool_mb << 20) / chunk_bytes;
+        uint64_t n_chunks = ((uint64_t)(ctx->heap_pool_mb > 0 ? ctx->heap_pool_mb : 8192) << 20) / chunk_bytes;
         if (n_chunks < (uint64_t)n_warps * 8) n_chunks = (uint64_t)n_warps * 8;
         if (n_chunks > 0xfffffff0ull) n_chunks = 0xfffffff0ull;
         d.n_chunks = (uint32_t)n_chunks;
@@ -371,7 +384,7 @@ void bwb_destroy(bwb_ctx *ctx) {
         cudaDeviceSynchronize();
         if (d.blocks) cudaFree(d.blocks);
         DevBuf *bufs[] = {&d.glists, &d.chunks, &d.chunk_link, &d.stage, &d.seq, &d.offsets, &d.read_off, &d.read_cnt,
-                          &d.ordered_off, &d.unordered, &d.ordered, &d.cub_tmp, &d.small, &d.d_main, &d.d_seed, &d.pool, &d.pk_main, &d.pk_seed, &d.nxt, &d.blk_link, &d.heads};
+                          &d.ordered_off, &d.unordered, &d.ordered, &d.cub_tmp, &d.small, &d.d_main, &d.d_seed, &d.pool, &d.pk_main, &d.pk_seed, &d.n_count, &d.nxt, &d.blk_link, &d.heads};
         for (DevBuf *b : bufs) release(*b);
         if (d.h_small) cudaFreeHost(d.h_small);
         if (d.ev0) cudaEventDestroy(d.ev0);
@@ -386,7 +399,7 @@ int bwb_device_count(const bwb_ctx *ctx) { return ctx ? (int)ctx->dev.size() : 0
 int bwb_set_option(bwb_ctx *ctx, const char *key, long long value) {
     if (!ctx || !key) return BWB_ERR_ARG;
     std::string k(key);
-    if (value <= 0 && k != "blocks_per_sm" && k != "force_wide" && k != "engine") return fail(ctx, BWB_ERR_ARG, "option %s needs a positive value", key);
+    if (value <= 0 && k != "blocks_per_sm" && k != "force_wide" && k != "engine" && k != "heap_pool_mb") return fail(ctx, BWB_ERR_ARG, "option %s needs a positive value", key);
     if (k == "heap_pool_mb") ctx->heap_pool_mb = value;
     else if (k == "list_cap") ctx->list_cap = (int)(value < SL + 4 ? SL + 4 : value);
     else if (k == "hits_per_read") ctx->hits_per_read = (int)value;
@@ -823,13 +836,14 @@ static int launch_shard(bwb_ctx *ctx, Device &d, const bwb_params *p, int nb, co
         // K3 (8-lane groups): packed lower-bound arrays of every read -> HBM
         if ((rc = ensure(ctx, d.pk_main, (total_bases + n + 1) * 2))) return rc;
         if ((rc = ensure(ctx, d.pk_seed, (n * (size_t)(p->seed_length + 1) + 1) * 2))) return rc;
+        if ((rc = ensure(ctx, d.n_count, (n + 1) * 2))) return rc;
         CalcArgs c;
         memset(&c, 0, sizeof c);
         c.ix = a.ix; c.seq = a.seq; c.offsets = a.offsets; c.n_reads = a.n_reads;
         c.seed_len = p->seed_length; c.max_len = max_len;
         c.queue = (uint32_t *)(sm + 4);
         c.glists = d.glists.p; c.list_cap = ctx->list_cap;
-        c.pk_main = (uint16_t *)d.pk_main.p; c.pk_seed = (uint16_t *)d.pk_seed.p;
+        c.pk_main = (uint16_t *)d.pk_main.p; c.pk_seed = (uint16_t *)d.pk_seed.p; c.n_count = (uint16_t *)d.n_count.p;
         c.status = a.status; c.counters = a.counters;
         c.smem_per_group = G_LIST_SMEM + ((max_len + 15) & ~15);
         const size_t smem3 = (size_t)(256 / GL) * c.smem_per_group;
@@ -850,14 +864,14 @@ static int launch_shard(bwb_ctx *ctx, Device &d, const bwb_params *p, int nb, co
         g.mm_score = a.mm_score; g.gapo_score = a.gapo_score; g.gape_score = a.gape_score;
         g.seed_len = a.seed_len; g.max_diff_seed = a.max_diff_seed; g.max_best = a.max_best; g.no_indel_len = a.no_indel_len;
         g.nb = a.nb; g.queue = a.queue;
-        g.pk_main = c.pk_main; g.pk_seed = c.pk_seed;
-        g.slots = (uint4 *)d.chunks.p; g.nxt = (uint32_t *)d.nxt.p;
+        g.pk_main = c.pk_main; g.pk_seed = c.pk_seed; g.n_count = c.n_count;
+        g.slots = (uint4 *)d.chunks.p;
         g.slots_per_lane = d.slots_per_lane; g.priv_total = d.priv_total;
-        g.pool = (PoolState *)d.pool.p; g.blk_link = (uint32_t *)d.blk_link.p; g.heads = (uint32_t *)d.heads.p;
+        g.pool = (PoolState *)d.pool.p; g.blk_link = (uint32_t *)d.blk_link.p;
         g.out_hits = a.out_hits; g.out_cap = a.out_cap; g.out_cursor = a.out_cursor;
         g.read_off = a.read_off; g.read_cnt = a.read_cnt; g.status = a.status; g.counters = a.counters;
-        if (wide) k_search_l<true><<<d.grid, 128, 0, d.stream>>>(g);
-        else k_search_l<false><<<d.grid, 128, 0, d.stream>>>(g);
+        if (wide) k_search_l<true><<<d.grid, 128, d.smem_bytes, d.stream>>>(g);
+        else k_search_l<false><<<d.grid, 128, d.smem_bytes, d.stream>>>(g);
         CU(cudaGetLastError());
     } else if (n) {
         // K3: lower-bound arrays of every read -> HBM
@@ -960,7 +974,7 @@ static int align_impl(bwb_ctx *ctx, const bwb_params *p, const bwb_reads *R, bwb
             memcpy(&used, hs + 16, 8);
             if (st[0]) {
                 delete res;
-                return fail(ctx, -(int)st[0], "device pool overflow while aligning read %u (heap_pool_mb=%lld list_cap=%d hits_per_read=%d)",
+                return fail(ctx, -(int)st[0], "device pool overflow while aligning read %u (heap_pool_mb=%lld [0=auto] list_cap=%d hits_per_read=%d)",
                             st[1], ctx->heap_pool_mb, ctx->list_cap, ctx->hits_per_read);
             }
             if (used > cap[g]) { cap[g] = used + used / 8 + 1024; again = true; continue; }

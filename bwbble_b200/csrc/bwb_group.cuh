@@ -156,6 +156,7 @@ struct CalcArgs {
     int2 *d_main;            // per read (len+1) entries at offsets[r] + r
     int2 *d_seed;            // per read (seed_len+1) entries at r*(seed_len+1); zeros if len <= seed_len (Q6)
     uint16_t *pk_main, *pk_seed;   // same arrays packed for K4: num_diff | (width == previous width) << 15
+    uint16_t *n_count;             // number of N bases per read (inexact_match.c:259-263)
     uint32_t *status;
     unsigned long long *counters;   // [3] rank queries, [5] max list
     int smem_per_group;
@@ -205,8 +206,9 @@ __global__ void __launch_bounds__(256) k_calc_d_g(const __grid_constant__ CalcAr
                 off = a.offsets[r];
                 len = (int)(a.offsets[r + 1] - off);
             }
-            g_stage_read(got, a.seq + off, len, sseq);
+            const uint32_t nN = g_stage_read(got, a.seq + off, len, sseq);
             if (got) {
+                if (a.n_count && gl == 0) a.n_count[r] = (uint16_t)nN;
                 phase = 0; dlen = len; D = a.d_main ? a.d_main + off + r : nullptr;
                 PK = a.pk_main ? a.pk_main + off + r : nullptr;
                 i = dlen - 1; z = 0; st.cur = 0; st.n_cur = 1; in_step = false;

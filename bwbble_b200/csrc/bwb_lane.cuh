@@ -9,13 +9,16 @@
 // (compile-time code => the plane XOR folds into LOP3, counters at immediate offsets).
 //
 // Per lane, in HBM (L1/L2 cached):
-//   * one arena of 16-byte slots + a `next` word per slot: heap entries, exact-tail interval
-//     nodes and hit records are all singly linked slot chains; freed slots go to a per-lane free
-//     list; a lane that outgrows its private range borrows 64-slot blocks from a sharded
-//     lock-free pool and returns them when the read is done;
+//   * one arena of 32-byte slots {L, U, z, w | next, r1, r2, r3}: heap entries, exact-tail interval
+//     nodes and hit records are all singly linked slot chains (one sector per pop / push).  Slots
+//     are bump-allocated and never recycled within a read -- allocation costs no memory access,
+//     so the pushes of an expansion are pure stores; the cursor rewinds when the read is done.
+//     A lane that outgrows its private range borrows 256-slot blocks from a sharded lock-free
+//     pool and returns them at the end of the read;
 //   * the bucket heap (priority_heap_t, inexact_match.h:16-34) as nb LIFO linked lists: push =
 //     link in front of the bucket head, pop = unlink the head of the lowest non-empty bucket --
-//     exactly "last entry of the lowest non-empty bucket" (inexact_match.c:594-610).
+//     exactly "last entry of the lowest non-empty bucket" (inexact_match.c:594-610).  Bucket
+//     heads live in shared memory ([bucket][lane], conflict-free), occupancy bits in registers.
 // Each loop iteration of a lane is: [take a read] -> [pop + prune + classify] -> [one interval
 // task: the 15-code rank loop, feeding either heap children or the next exact-tail list] ->
 // [flush].  No warp-synchronous intrinsic is needed anywhere: lanes are independent.
@@ -25,7 +28,7 @@
 namespace bwb {
 
 constexpr uint32_t NIL = 0xffffffffu;
-constexpr int LBLK = 64;                    // slots per borrowed block
+constexpr int LBLK = 256;                   // slots per borrowed block
 
 struct LaneArgs {
     IndexView ix;
@@ -37,14 +40,13 @@ struct LaneArgs {
     int seed_len, max_diff_seed, max_best, no_indel_len;
     int nb;
     uint32_t *queue;
-    const uint16_t *pk_main, *pk_seed;       // packed lower bounds from K3 (see g_pack_bound)
-    uint4 *slots;                            // arena
-    uint32_t *nxt;                           // link word per slot
+    const uint16_t *pk_main, *pk_seed;       // packed lower bounds from K3
+    const uint16_t *n_count;                 // N bases per read, from K3
+    uint4 *slots;                            // arena: 2 x uint4 per slot
     uint32_t slots_per_lane;                 // private range of lane-slot s: [s*spl, (s+1)*spl)
     uint32_t priv_total;                     // first slot of the shared region (multiple of LBLK)
     PoolState *pool;                         // shared region, in blocks of LBLK slots
     uint32_t *blk_link;                      // link word per block (pool free lists, borrowed lists)
-    uint32_t *heads;                         // [n_lanes][nb] bucket heads
     bwb_hit *out_hits;
     unsigned long long out_cap;
     unsigned long long *out_cursor;
@@ -54,23 +56,16 @@ struct LaneArgs {
     unsigned long long *counters;
 };
 
-// ---- per-lane slot allocator --------------------------------------------------------------------
+// ---- per-lane slot allocator: bump only ---------------------------------------------------------
 struct LaneAlloc {
-    uint32_t priv_lo, priv_hi, bump, free_head;
+    uint32_t priv_lo, priv_hi, bump;
     uint32_t ov_cur, ov_end;                 // current borrowed block
     uint32_t borrowed;                       // list of borrowed blocks (through blk_link)
     uint32_t borrowed_last;
 };
 
-__device__ __forceinline__ uint32_t lane_alloc(LaneAlloc &al, const LaneArgs &a, uint32_t lane_slot) {
-    if (al.free_head != NIL) {
-        const uint32_t s = al.free_head;
-        al.free_head = a.nxt[s];
-        return s;
-    }
-    if (al.bump < al.priv_hi) return al.bump++;
-    if (al.ov_cur < al.ov_end) return al.ov_cur++;
-    // borrow a block from the shared pool (own shard first)
+// slow path: borrow a block of LBLK slots from the shared pool (own shard first)
+__device__ __noinline__ uint32_t lane_borrow(LaneAlloc &al, const LaneArgs &a, uint32_t lane_slot) {
     for (int t = 0; t < POOL_SHARDS; t++) {
         const uint32_t sh = (lane_slot + (uint32_t)t) % POOL_SHARDS;
         uint32_t blk = NIL;
@@ -101,9 +96,11 @@ __device__ __forceinline__ uint32_t lane_alloc(LaneAlloc &al, const LaneArgs &a,
     }
     return NIL;
 }
-__device__ __forceinline__ void lane_free(LaneAlloc &al, const LaneArgs &a, uint32_t s) {
-    a.nxt[s] = al.free_head;
-    al.free_head = s;
+
+__device__ __forceinline__ uint32_t lane_alloc(LaneAlloc &al, const LaneArgs &a, uint32_t lane_slot) {
+    if (al.bump < al.priv_hi) return al.bump++;
+    if (al.ov_cur < al.ov_end) return al.ov_cur++;
+    return lane_borrow(al, a, lane_slot);
 }
 // end of a read: every slot is dead; hand borrowed blocks back with one CAS
 __device__ __forceinline__ void lane_alloc_reset(LaneAlloc &al, const LaneArgs &a, uint32_t lane_slot) {
@@ -119,87 +116,94 @@ __device__ __forceinline__ void lane_alloc_reset(LaneAlloc &al, const LaneArgs &
         }
     }
     al.bump = al.priv_lo;
-    al.free_head = NIL;
     al.ov_cur = al.ov_end = 0;
     al.borrowed = NIL;
     al.borrowed_last = NIL;
 }
 
-// ---- slot payloads ------------------------------------------------------------------------------
-// heap entry: compact = {L, U, z, w}; wide = {Llo, Ulo, Lhi|Uhi<<8, z} + {w, r1, r2, r3} in a 2nd slot
-// interval node: {Llo, Ulo, Lhi|Uhi<<8, -}
-// hit: slot A = interval node layout with .w = z, slot B = {w, r1, r2, r3}, slot C = {score, alen, -, -}
+// ---- slot payloads (2 x uint4) --------------------------------------------------------------------
+//   first  = {L[31:0], U[31:0], z, w}
+//   second = {next, r1, r2 | L[39:32]<<24, r3 | U[39:32]<<24}        (r1..r3 use 24 bits)
+// heap entry: as is.  interval node: L, U, next.  hit: slot A = the entry, slot B.first = {score, alen}.
 template <class T>
-__device__ __forceinline__ uint4 pack_lu(T L, T U, uint32_t last) {
-    if constexpr (sizeof(T) == 8)
-        return make_uint4((uint32_t)L, (uint32_t)U, ((uint32_t)(L >> 32) & 0xffu) | (((uint32_t)(U >> 32) & 0xffu) << 8), last);
-    else
-        return make_uint4((uint32_t)L, (uint32_t)U, 0u, last);
+__device__ __forceinline__ void slot_write(uint4 *slots, uint32_t s, T L, T U, uint32_t z, uint32_t w, uint32_t nxt,
+                                           uint32_t r1, uint32_t r2, uint32_t r3) {
+    uint32_t hl = 0, hu = 0;
+    if constexpr (sizeof(T) == 8) { hl = (uint32_t)(L >> 32) << 24; hu = (uint32_t)(U >> 32) << 24; }
+    slots[2 * (size_t)s] = make_uint4((uint32_t)L, (uint32_t)U, z, w);
+    slots[2 * (size_t)s + 1] = make_uint4(nxt, r1, (r2 & 0xffffffu) | hl, (r3 & 0xffffffu) | hu);
 }
 template <class T>
-__device__ __forceinline__ void unpack_lu(const uint4 &v, T &L, T &U) {
+__device__ __forceinline__ uint32_t slot_read(const uint4 *slots, uint32_t s, PE<T> &e) {
+    const uint4 a = slots[2 * (size_t)s], b = slots[2 * (size_t)s + 1];
+    e.z = a.z; e.w = a.w; e.r1 = b.y; e.r2 = b.z & 0xffffffu; e.r3 = b.w & 0xffffffu;
     if constexpr (sizeof(T) == 8) {
-        L = (uint64_t)v.x | ((uint64_t)(v.z & 0xffu) << 32);
-        U = (uint64_t)v.y | ((uint64_t)((v.z >> 8) & 0xffu) << 32);
+        e.L = (uint64_t)a.x | ((uint64_t)(b.z >> 24) << 32);
+        e.U = (uint64_t)a.y | ((uint64_t)(b.w >> 24) << 32);
     } else {
-        L = v.x; U = v.y;
+        e.L = a.x; e.U = a.y;
     }
+    return b.x;
+}
+__device__ __forceinline__ void slot_set_next(uint4 *slots, uint32_t s, uint32_t nxt) {
+    reinterpret_cast<uint32_t *>(slots + 2 * (size_t)s + 1)[0] = nxt;
+}
+__device__ __forceinline__ uint32_t slot_next(const uint4 *slots, uint32_t s) {
+    return reinterpret_cast<const uint32_t *>(slots + 2 * (size_t)s + 1)[0];
 }
 
+// Bucket heap of one lane.  heads = shared memory, column of this lane ([bucket][lane]);
+// bm0..bm3 = occupancy bits of up to 128 buckets, so heads never need resetting between reads and
+// "next non-empty bucket" is a find-first-set.
 template <bool WIDE>
 struct LaneHeap {
     typedef typename Coord<WIDE>::type T;
-    uint32_t *heads;
-    int n, best, nb;
+    uint32_t *heads;       // &sm_heads[0][lane]; bucket b at heads[b * 128]
+    uint32_t bm0, bm1, bm2, bm3;
+    int n;
+
+    __device__ __forceinline__ void clear() { bm0 = bm1 = bm2 = bm3 = 0u; n = 0; }
+    __device__ __forceinline__ bool occupied(int b) const {
+        const uint32_t w = b < 64 ? (b < 32 ? bm0 : bm1) : (b < 96 ? bm2 : bm3);
+        return (w >> (b & 31)) & 1u;
+    }
+    __device__ __forceinline__ void set_bit(int b) {
+        const uint32_t bit = 1u << (b & 31);
+        bm0 |= (b < 32) ? bit : 0u;
+        bm1 |= (b >= 32 && b < 64) ? bit : 0u;
+        bm2 |= (b >= 64 && b < 96) ? bit : 0u;
+        bm3 |= (b >= 96) ? bit : 0u;
+    }
+    __device__ __forceinline__ void clear_bit(int b) {
+        const uint32_t bit = 1u << (b & 31);
+        bm0 &= ~((b < 32) ? bit : 0u);
+        bm1 &= ~((b >= 32 && b < 64) ? bit : 0u);
+        bm2 &= ~((b >= 64 && b < 96) ? bit : 0u);
+        bm3 &= ~((b >= 96) ? bit : 0u);
+    }
+    __device__ __forceinline__ int best() const {        // lowest non-empty bucket (n > 0)
+        return bm0 ? __ffs(bm0) - 1 : (bm1 ? 31 + __ffs(bm1) : (bm2 ? 63 + __ffs(bm2) : 95 + __ffs(bm3)));
+    }
 
     __device__ __forceinline__ bool push(LaneAlloc &al, const LaneArgs &a, uint32_t lane_slot, int sc, T L, T U,
                                          uint32_t z, uint32_t w, uint32_t r1, uint32_t r2, uint32_t r3) {
         const uint32_t s = lane_alloc(al, a, lane_slot);
         if (s == NIL) return false;
-        if constexpr (WIDE) {
-            const uint32_t s2 = lane_alloc(al, a, lane_slot);
-            if (s2 == NIL) return false;
-            a.slots[s] = pack_lu<T>(L, U, z);
-            a.slots[s2] = make_uint4(w, r1, r2, r3);
-            a.nxt[s2] = heads[sc];
-            a.nxt[s] = s2;
-        } else {
-            a.slots[s] = make_uint4(L, U, z, w);
-            a.nxt[s] = heads[sc];
-        }
-        heads[sc] = s;
+        const uint32_t old = occupied(sc) ? heads[sc * 128] : NIL;
+        slot_write<T>(a.slots, s, L, U, z, w, old, r1, r2, r3);
+        heads[sc * 128] = s;
+        set_bit(sc);
         n++;
-        best = min(best, sc);
         return true;
     }
     // heap_pop (inexact_match.c:594-610); returns the bucket
-    __device__ __forceinline__ int pop(LaneAlloc &al, const LaneArgs &a, PE<T> &e) {
-        const int b = best;
-        const uint32_t s = heads[b];
-        const uint4 v = a.slots[s];
-        uint32_t rest;
-        if constexpr (WIDE) {
-            unpack_lu<T>(v, e.L, e.U);
-            e.z = v.w;
-            const uint32_t s2 = a.nxt[s];
-            const uint4 v2 = a.slots[s2];
-            e.w = v2.x; e.r1 = v2.y; e.r2 = v2.z; e.r3 = v2.w;
-            rest = a.nxt[s2];
-            lane_free(al, a, s2);
-        } else {
-            e.L = v.x; e.U = v.y; e.z = v.z; e.w = v.w; e.r1 = e.r2 = e.r3 = 0;
-            rest = a.nxt[s];
-        }
-        lane_free(al, a, s);
-        heads[b] = rest;
+    __device__ __forceinline__ int pop(const LaneArgs &a, PE<T> &e) {
+        const int b = best();
+        const uint32_t s = heads[b * 128];
+        const uint32_t rest = slot_read<T>(a.slots, s, e);
+        if (rest == NIL) clear_bit(b);
+        else heads[b * 128] = rest;
         n--;
-        if (rest == NIL) {
-            int nbst = nb;
-            if (n)
-                for (int q = b + 1; q < nb; q++)
-                    if (heads[q] != NIL) { nbst = q; break; }
-            best = nbst;
-        }
         return b;
     }
 };
@@ -212,6 +216,8 @@ template <bool WIDE>
 __global__ void __launch_bounds__(128, BWB_LANE_MIN_BLOCKS) k_search_l(const __grid_constant__ LaneArgs a) {
     typedef typename Coord<WIDE>::type T;
     __shared__ T sC[17];
+    __shared__ T sLj[16][128], sUj[16][128];      // per-lane child intervals of the current task
+    extern __shared__ uint32_t sm_heads[];        // [nb][128] bucket heads
     stage_C<T>(a.ix, sC);
 
     const uint32_t lane_slot = blockIdx.x * blockDim.x + threadIdx.x;
@@ -220,17 +226,14 @@ __global__ void __launch_bounds__(128, BWB_LANE_MIN_BLOCKS) k_search_l(const __g
     al.priv_lo = lane_slot * a.slots_per_lane;
     al.priv_hi = al.priv_lo + a.slots_per_lane;
     al.bump = al.priv_lo;
-    al.free_head = NIL;
     al.ov_cur = al.ov_end = 0;
     al.borrowed = NIL;
     al.borrowed_last = NIL;
     LaneHeap<WIDE> h;
-    h.heads = a.heads + (size_t)lane_slot * a.nb;
-    h.nb = a.nb;
-    h.n = 0;
-    h.best = a.nb;
+    h.heads = sm_heads + threadIdx.x;
+    h.clear();
 
-    enum { NEED = 0, SEARCH = 1, TAIL = 2, FLUSH = 3 };
+    enum { NEED = 0, SEARCH = 1, TAIL = 2, FLUSH = 3, TADD = 4, DONE = 5 };
     int mode = NEED;
     uint32_t r = 0, read_id = 0;
     int len = 0, err = 0;
@@ -251,26 +254,30 @@ __global__ void __launch_bounds__(128, BWB_LANE_MIN_BLOCKS) k_search_l(const __g
     int t_bucket = 0, t_r = 0;
     uint32_t cur_head = NIL, nx_head = NIL, nx_tail = NIL;
     int nx_n = 0;
+    uint32_t nx_w = 0, old_tail = NIL;        // wrapped width sum of the level being built
     T nx_tailL = 0, nx_tailU = 0;
 
     unsigned long long c_pops = 0, c_push = 0, c_tails = 0, c_rank = 0;
     uint32_t c_maxheap = 0, c_maxlist = 0;
 
-    for (;;) {
+    // Lanes are independent, but without forced reconvergence they drift apart for good (the loop
+    // back-edge is not a reconvergence point): the warp-wide vote at the loop head and the
+    // __syncwarp() before the rank loop keep the 32 reads of a warp in lock-step.
+    while (!__all_sync(FULL, mode == DONE)) {
         // ================= take the next read =================
         if (mode == NEED) {
             r = atomicAdd(a.queue, 1u);
-            if (r >= a.n_reads) break;
+            if (r >= a.n_reads) mode = DONE;
+        }
+        if (mode == NEED) {
             off = a.offsets[r];
             len = (int)(a.offsets[r + 1] - off);
             read_id = a.read_id_base + r;
             rseq = a.seq + off;
             D = a.pk_main + off + r;
             Ds = a.pk_seed + (size_t)r * (a.seed_len + 1);
-            int nN = 0;
-            for (int k = 0; k < len; k++) nN += (rseq[k] > 3);
-            for (int b = 0; b < a.nb; b++) h.heads[b] = NIL;
-            h.n = 0; h.best = a.nb;
+            const int nN = (int)a.n_count[r];                           // counted by K3
+            h.clear();
             n_hits = 0; hit_head = hit_tail = NIL; err = 0;
             best_score = a.nb; max_diff = a.max_diff; num_best = 0;
             have_task = false;
@@ -289,7 +296,7 @@ __global__ void __launch_bounds__(128, BWB_LANE_MIN_BLOCKS) k_search_l(const __g
             if (h.n == 0 || h.n > a.max_entries) {
                 mode = FLUSH;
             } else {
-                eb = h.pop(al, a, e);
+                eb = h.pop(a, e);
                 c_pops++;
                 const uint32_t z = e.z;
                 const int ei = (int)(z & 0xffu);
@@ -314,24 +321,21 @@ __global__ void __launch_bounds__(128, BWB_LANE_MIN_BLOCKS) k_search_l(const __g
                     else if (num_best > a.max_best) { mode = FLUSH; add = false; }
                     if (add && go) {                                    // align.c:273-280
                         for (uint32_t q = hit_head; q != NIL;) {
-                            T hL, hU;
-                            unpack_lu<T>(a.slots[q], hL, hU);
-                            if (hL == e.L && hU == e.U) { add = false; break; }
-                            q = a.nxt[a.nxt[a.nxt[q]]];
+                            PE<T> hh;
+                            const uint32_t qb = slot_read<T>(a.slots, q, hh);
+                            if (hh.L == e.L && hh.U == e.U) { add = false; break; }
+                            q = slot_next(a.slots, qb);
                         }
                     }
                     if (add) {
                         const uint32_t alen = ((uint32_t)(len - ei) + (e.w & 0xffu)) & 0xffu;
-                        const uint32_t sa = lane_alloc(al, a, lane_slot), sb = lane_alloc(al, a, lane_slot),
-                                       scs = lane_alloc(al, a, lane_slot);
-                        if (sa == NIL || sb == NIL || scs == NIL) { err = BWB_ERR_CAPACITY; mode = FLUSH; }
+                        const uint32_t sa = lane_alloc(al, a, lane_slot), sb = lane_alloc(al, a, lane_slot);
+                        if (sa == NIL || sb == NIL) { err = BWB_ERR_CAPACITY; mode = FLUSH; }
                         else {
-                            a.slots[sa] = pack_lu<T>(e.L, e.U, z);
-                            a.slots[sb] = make_uint4(e.w, e.r1, e.r2, e.r3);
-                            a.slots[scs] = make_uint4((uint32_t)eb, alen, 0u, 0u);
-                            a.nxt[sa] = sb; a.nxt[sb] = scs; a.nxt[scs] = NIL;
-                            if (hit_tail == NIL) hit_head = sa; else a.nxt[hit_tail] = sa;
-                            hit_tail = scs;
+                            slot_write<T>(a.slots, sa, e.L, e.U, z, e.w, sb, e.r1, e.r2, e.r3);
+                            slot_write<T>(a.slots, sb, (T)eb, (T)alen, 0u, 0u, NIL, 0u, 0u, 0u);
+                            if (hit_tail == NIL) hit_head = sa; else slot_set_next(a.slots, hit_tail, sa);
+                            hit_tail = sb;
                             n_hits++;
                         }
                     }
@@ -341,9 +345,8 @@ __global__ void __launch_bounds__(128, BWB_LANE_MIN_BLOCKS) k_search_l(const __g
                     const uint32_t s = lane_alloc(al, a, lane_slot);
                     if (s == NIL) { err = BWB_ERR_CAPACITY; mode = FLUSH; }
                     else {
-                        a.slots[s] = pack_lu<T>(e.L, e.U, 0u);
-                        a.nxt[s] = NIL;
-                        cur_head = s; nx_head = nx_tail = NIL; nx_n = 0;
+                        slot_write<T>(a.slots, s, e.L, e.U, 0u, 0u, NIL, 0u, 0u, 0u);
+                        cur_head = s; nx_head = nx_tail = NIL; nx_n = 0; nx_w = 0;
                         mode = TAIL;
                     }
                 } else {
@@ -378,90 +381,82 @@ __global__ void __launch_bounds__(128, BWB_LANE_MIN_BLOCKS) k_search_l(const __g
         // ================= exact tail: next interval of the current level, or level end =================
         if (mode == TAIL && !have_task) {
             if (cur_head != NIL) {
-                const uint32_t s = cur_head;
-                unpack_lu<T>(a.slots[s], e.L, e.U);
-                cur_head = a.nxt[s];
-                lane_free(al, a, s);
+                {
+                    PE<T> nd;
+                    cur_head = slot_read<T>(a.slots, cur_head, nd);
+                    e.L = nd.L; e.U = nd.U;
+                }
                 cbase = nt4_compl(rseq[len - 1 - t_r]);
                 if (cbase > 3u) {                                       // N never matches (exact_match.c:84-87):
-                    while (cur_head != NIL) { const uint32_t q = cur_head; cur_head = a.nxt[q]; lane_free(al, a, q); }
-                    while (nx_head != NIL) { const uint32_t q = nx_head; nx_head = a.nxt[q]; lane_free(al, a, q); }
+                    cur_head = nx_head = nx_tail = NIL; nx_n = 0;
                     mode = SEARCH;                                      // empty result
                 } else {
                     have_task = true;
                     task_tail = true;
                 }
             } else {                                                    // level finished
-                if (nx_n) { a.slots[nx_tail] = pack_lu<T>(nx_tailL, nx_tailU, 0u); }
+                if (nx_n) slot_write<T>(a.slots, nx_tail, nx_tailL, nx_tailU, 0u, 0u, NIL, 0u, 0u, 0u);
                 if ((uint32_t)nx_n > c_maxlist) c_maxlist = (uint32_t)nx_n;
                 if (nx_n == 0) {
                     mode = SEARCH;                                      // no match
                 } else if (t_r > 0) {
                     t_r--;
-                    cur_head = nx_head; nx_head = nx_tail = NIL; nx_n = 0;
+                    cur_head = nx_head; nx_head = nx_tail = NIL; nx_n = 0; nx_w = 0;
                 } else {
-                    // tail matched: bookkeeping of a hit, once per interval (inexact_match.c:347-371)
+                    // tail matched: bookkeeping of a hit (inexact_match.c:347-362); the intervals are
+                    // then added one per iteration (mode TADD)
                     const uint32_t z = te.z;
-                    const int ei = (int)(z & 0xffu);
-                    const int go = (int)((z >> 24) & 15u);
-                    const int used = (int)((z >> 8) & 0xffu) + go + (int)((z >> 16) & 0xffu);
+                    const int used = (int)((z >> 8) & 0xffu) + (int)((z >> 24) & 15u) + (int)((z >> 16) & 0xffu);
                     bool stop = false;
                     if (n_hits == 0) {
                         best_score = t_bucket;
                         max_diff = (used + 1 > a.max_diff) ? a.max_diff : used + 1;
                     }
-                    if (t_bucket == best_score) {
-                        uint32_t wsum = 0;
-                        for (uint32_t q = nx_head; q != NIL; q = a.nxt[q]) {
-                            T L, U;
-                            unpack_lu<T>(a.slots[q], L, U);
-                            wsum += (uint32_t)(U - L + 1);
-                        }
-                        num_best = (int)((uint32_t)num_best + wsum);
-                    } else if (num_best > a.max_best) stop = true;
-                    const uint32_t alen2 = ((uint32_t)(len - ei) + (te.w & 0xffu) + (uint32_t)ei) & 0xffu;
-                    const uint32_t old_tail = hit_tail;                 // dedupe only against earlier hits
-                    uint32_t q = nx_head;
-                    while (q != NIL) {
-                        const uint32_t qn = a.nxt[q];
-                        bool add = !stop && !err;
-                        T L, U;
-                        unpack_lu<T>(a.slots[q], L, U);
-                        if (add && go && old_tail != NIL) {
-                            for (uint32_t p = hit_head;;) {
-                                T hL, hU;
-                                unpack_lu<T>(a.slots[p], hL, hU);
-                                if (hL == L && hU == U) { add = false; break; }
-                                const uint32_t pc = a.nxt[a.nxt[p]];
-                                if (pc == old_tail) break;
-                                p = a.nxt[pc];
-                            }
-                        }
-                        if (add) {
-                            // re-use the node as slot A of the hit
-                            const uint32_t sb = lane_alloc(al, a, lane_slot), scs = lane_alloc(al, a, lane_slot);
-                            if (sb == NIL || scs == NIL) { err = BWB_ERR_CAPACITY; lane_free(al, a, q); }
-                            else {
-                                a.slots[q] = pack_lu<T>(L, U, z);
-                                a.slots[sb] = make_uint4(te.w, te.r1, te.r2, te.r3);
-                                a.slots[scs] = make_uint4((uint32_t)t_bucket, alen2, 0u, 0u);
-                                a.nxt[q] = sb; a.nxt[sb] = scs; a.nxt[scs] = NIL;
-                                if (hit_tail == NIL) hit_head = q; else a.nxt[hit_tail] = q;
-                                hit_tail = scs;
-                                n_hits++;
-                            }
-                        } else {
-                            lane_free(al, a, q);
-                        }
-                        q = qn;
+                    if (t_bucket == best_score) num_best = (int)((uint32_t)num_best + nx_w);
+                    else if (num_best > a.max_best) stop = true;
+                    old_tail = hit_tail;                                // dedupe only against earlier hits
+                    cur_head = nx_head; nx_head = nx_tail = NIL; nx_n = 0; nx_w = 0;
+                    mode = stop ? FLUSH : TADD;
+                }
+            }
+        } else if (mode == TADD) {                                      // add_alignment per interval (:366-370)
+            if (cur_head == NIL) {
+                mode = SEARCH;
+            } else {
+                const uint32_t q = cur_head;
+                PE<T> nd;
+                cur_head = slot_read<T>(a.slots, q, nd);
+                const T L = nd.L, U = nd.U;
+                const uint32_t z = te.z;
+                const int ei = (int)(z & 0xffu);
+                const int go = (int)((z >> 24) & 15u);
+                const uint32_t alen2 = ((uint32_t)(len - ei) + (te.w & 0xffu) + (uint32_t)ei) & 0xffu;
+                bool add = true;
+                if (go && old_tail != NIL) {
+                    for (uint32_t p = hit_head;;) {
+                        PE<T> hh;
+                        const uint32_t pb = slot_read<T>(a.slots, p, hh);
+                        if (hh.L == L && hh.U == U) { add = false; break; }
+                        if (pb == old_tail) break;
+                        p = slot_next(a.slots, pb);
                     }
-                    nx_head = nx_tail = NIL; nx_n = 0;
-                    mode = (stop || err) ? FLUSH : SEARCH;
+                }
+                if (add) {                                              // the node becomes slot A of the hit
+                    const uint32_t sb = lane_alloc(al, a, lane_slot);
+                    if (sb == NIL) { err = BWB_ERR_CAPACITY; mode = FLUSH; }
+                    else {
+                        slot_write<T>(a.slots, q, L, U, z, te.w, sb, te.r1, te.r2, te.r3);
+                        slot_write<T>(a.slots, sb, (T)t_bucket, (T)alen2, 0u, 0u, NIL, 0u, 0u, 0u);
+                        if (hit_tail == NIL) hit_head = q; else slot_set_next(a.slots, hit_tail, q);
+                        hit_tail = sb;
+                        n_hits++;
+                    }
                 }
             }
         }
 
         // ================= the interval task: 15-code rank loop =================
+        __syncwarp();
         if (have_task) {
             have_task = false;
             const T iL = (T)(e.L - 1), iU = e.U;
@@ -494,14 +489,6 @@ __global__ void __launch_bounds__(128, BWB_LANE_MIN_BLOCKS) k_search_l(const __g
             const uint32_t z = e.z;
             const int go = (int)((z >> 24) & 15u);
             const bool opening = ((z >> 28) & 3u) == 0u;
-            const uint32_t cmask = (0x01428u >> (4u * cbase)) & 15u;       // nt4_gray_val; 0 for N
-            const uint32_t compat = task_tail ? compat_codes(cbase & 3u) : 0u;
-            // set of codes the tail may extend with, as a bit mask
-            uint32_t cset = 0;
-            if (task_tail) {
-#pragma unroll
-                for (int k = 0; k < 7; k++) cset |= 1u << ((compat >> (4 * k)) & 15u);
-            }
             const int b0 = eb, b1 = eb + a.mm_score, b2 = eb + (opening ? a.gapo_score : a.gape_score);
             const bool full = t_flags & 1u, del_ok = t_flags & 2u, ins_ok = t_flags & 4u;
             const uint32_t alen = task_tail ? 0u : (((uint32_t)(len - (int)(z & 0xffu)) + (e.w & 0xffu)) & 0xffu);
@@ -523,75 +510,82 @@ __global__ void __launch_bounds__(128, BWB_LANE_MIN_BLOCKS) k_search_l(const __g
                 }
             }
             const uint32_t zm = (z - 1u) & ~(3u << 28);
-            // When a gap bucket coincides with a match/mismatch bucket the reference's push order
-            // (insertion, all deletions, then all matches/mismatches, :433-504) needs two passes.
-            const bool two_pass = !task_tail && (del_ok || ins_ok) && (b2 == b0 || b2 == b1);
-            bool ok_all = true;
-            if (!task_tail && ins_ok) {                                  // insertion child first (:435-444)
-                ok_all = h.push(al, a, lane_slot, b2, e.L, e.U, (zg | (1u << 28)) - 1u, wI, r1I, r2I, r3I);
-                c_push++;
-            }
-            for (int pass = 0; pass < (two_pass ? 2 : 1); pass++) {
-                const bool do_del = del_ok && (pass == 0);
-                const bool do_mm = !two_pass || pass == 1;
+            // ---- (1) ranks of all 15 codes at both ends: straight-line code, results to shared memory
+            uint32_t okmask = 0;
 #pragma unroll
-                for (int j = 1; j < 16; j++) {
-                    const uint32_t x0 = (j & 1) ? 0u : ~0u, x1 = (j & 2) ? 0u : ~0u, x2 = (j & 4) ? 0u : ~0u, x3 = (j & 8) ? 0u : ~0u;
-                    const uint32_t u0 = (pu.p0.x ^ x0) & (pu.p1.x ^ x1) & (pu.p2.x ^ x2) & (pu.p3.x ^ x3);
-                    const uint32_t u1 = (pu.p0.y ^ x0) & (pu.p1.y ^ x1) & (pu.p2.y ^ x2) & (pu.p3.y ^ x3);
-                    const uint32_t u2 = (pu.p0.z ^ x0) & (pu.p1.z ^ x1) & (pu.p2.z ^ x2) & (pu.p3.z ^ x3);
-                    const uint32_t u3 = (pu.p0.w ^ x0) & (pu.p1.w ^ x1) & (pu.p2.w ^ x2) & (pu.p3.w ^ x3);
-                    const uint32_t l0 = (pl.p0.x ^ x0) & (pl.p1.x ^ x1) & (pl.p2.x ^ x2) & (pl.p3.x ^ x3);
-                    const uint32_t l1 = (pl.p0.y ^ x0) & (pl.p1.y ^ x1) & (pl.p2.y ^ x2) & (pl.p3.y ^ x3);
-                    const uint32_t l2 = (pl.p0.z ^ x0) & (pl.p1.z ^ x1) & (pl.p2.z ^ x2) & (pl.p3.z ^ x3);
-                    const uint32_t l3 = (pl.p0.w ^ x0) & (pl.p1.w ^ x1) & (pl.p2.w ^ x2) & (pl.p3.w ^ x3);
-                    const uint32_t vU = __ldg(cntU + j) + __popc(u0 & kU0) + __popc(u1 & kU1) + __popc(u2 & kU2) + __popc(u3 & kU3);
-                    const uint32_t vL = __ldg(cntL + j) + __popc(l0 & kL0) + __popc(l1 & kL1) + __popc(l2 & kL2) + __popc(l3 & kL3);
-                    // Q1: O_alphabet skips codes 5,9,11,13 except for the checkpoint-symbol decrement
-                    // (bwt.c:427-435,780); the exact search's O() counts them (bwt.c:348-372)
-                    const bool quirk = (j == 5 || j == 9 || j == 11 || j == 13);
-                    const T Cj = sC[j], Cj1 = sC[j + 1];
-                    T Lj, Uj;
-                    if (quirk && !task_tail) {
-                        Lj = (T)((negL ? Cj : (T)(Cj - (T)(l0 & 1u))) + 1);
-                        Uj = topU ? Cj1 : (T)(Cj - (T)(u0 & 1u));
+            for (int j = 1; j < 16; j++) {
+                const uint32_t x0 = (j & 1) ? 0u : ~0u, x1 = (j & 2) ? 0u : ~0u, x2 = (j & 4) ? 0u : ~0u, x3 = (j & 8) ? 0u : ~0u;
+                const uint32_t u0 = (pu.p0.x ^ x0) & (pu.p1.x ^ x1) & (pu.p2.x ^ x2) & (pu.p3.x ^ x3);
+                const uint32_t u1 = (pu.p0.y ^ x0) & (pu.p1.y ^ x1) & (pu.p2.y ^ x2) & (pu.p3.y ^ x3);
+                const uint32_t u2 = (pu.p0.z ^ x0) & (pu.p1.z ^ x1) & (pu.p2.z ^ x2) & (pu.p3.z ^ x3);
+                const uint32_t u3 = (pu.p0.w ^ x0) & (pu.p1.w ^ x1) & (pu.p2.w ^ x2) & (pu.p3.w ^ x3);
+                const uint32_t l0 = (pl.p0.x ^ x0) & (pl.p1.x ^ x1) & (pl.p2.x ^ x2) & (pl.p3.x ^ x3);
+                const uint32_t l1 = (pl.p0.y ^ x0) & (pl.p1.y ^ x1) & (pl.p2.y ^ x2) & (pl.p3.y ^ x3);
+                const uint32_t l2 = (pl.p0.z ^ x0) & (pl.p1.z ^ x1) & (pl.p2.z ^ x2) & (pl.p3.z ^ x3);
+                const uint32_t l3 = (pl.p0.w ^ x0) & (pl.p1.w ^ x1) & (pl.p2.w ^ x2) & (pl.p3.w ^ x3);
+                const uint32_t vU = __ldg(cntU + j) + __popc(u0 & kU0) + __popc(u1 & kU1) + __popc(u2 & kU2) + __popc(u3 & kU3);
+                const uint32_t vL = __ldg(cntL + j) + __popc(l0 & kL0) + __popc(l1 & kL1) + __popc(l2 & kL2) + __popc(l3 & kL3);
+                // Q1: O_alphabet skips codes 5,9,11,13 except for the checkpoint-symbol decrement
+                // (bwt.c:427-435,780); the exact search's O() counts them (bwt.c:348-372)
+                const bool quirk = (j == 5 || j == 9 || j == 11 || j == 13);
+                const T Cj = sC[j], Cj1 = sC[j + 1];
+                T Lj, Uj;
+                if (quirk) {
+                    const T qL = task_tail ? (T)vL : (T)0 - (T)(l0 & 1u);
+                    const T qU = task_tail ? (T)vU : (T)0 - (T)(u0 & 1u);
+                    Lj = (T)(Cj + (negL ? (T)0 : qL) + 1);
+                    Uj = topU ? Cj1 : (T)(Cj + qU);
+                } else {
+                    Lj = (T)(Cj + (negL ? (T)0 : (T)vL) + 1);
+                    Uj = topU ? Cj1 : (T)(Cj + (T)vU);
+                }
+                sLj[j][threadIdx.x] = Lj;
+                sUj[j][threadIdx.x] = Uj;
+                okmask |= (Lj <= Uj) ? (1u << j) : 0u;
+            }
+            // codes whose base set contains the read base, N excluded = nucl_bases_table[c] (io.h:102-106)
+            const uint32_t compat_set = cbase == 0 ? 0xFB00u : (cbase == 1 ? 0x383Cu : (cbase == 2 ? 0x0BF0u : (cbase == 3 ? 0x6266u : 0u)));
+            bool ok_all = true;
+            if (task_tail) {
+                // ---- (2a) exact tail: ordered append with adjacent merge (align.c:93-110)
+                uint32_t m = okmask & compat_set;
+                while (m) {
+                    const int j = __ffs(m) - 1;
+                    m &= m - 1;
+                    const T Lj = sLj[j][threadIdx.x], Uj = sUj[j][threadIdx.x];
+                    nx_w += (uint32_t)(Uj - Lj + 1);
+                    if (nx_n && Lj == (T)(nx_tailU + 1)) {
+                        nx_tailU = Uj;
                     } else {
-                        Lj = (T)(Cj + (negL ? (T)0 : (T)vL) + 1);
-                        Uj = topU ? Cj1 : (T)(Cj + (T)vU);
+                        const uint32_t sl = lane_alloc(al, a, lane_slot);
+                        if (sl == NIL) { ok_all = false; break; }
+                        if (nx_n) slot_write<T>(a.slots, nx_tail, nx_tailL, nx_tailU, 0u, 0u, sl, 0u, 0u, 0u);
+                        else nx_head = sl;
+                        nx_tail = sl; nx_tailL = Lj; nx_tailU = Uj;
+                        nx_n++;
                     }
-                    if (Lj <= Uj) {
-                        if (task_tail) {
-                            if ((cset >> j) & 1u) {                      // ordered append with adjacent merge (align.c:93-110)
-                                if (nx_n && Lj == (T)(nx_tailU + 1)) {
-                                    nx_tailU = Uj;
-                                } else {
-                                    const uint32_t s = lane_alloc(al, a, lane_slot);
-                                    if (s == NIL) { ok_all = false; }
-                                    else {
-                                        if (nx_n) { a.slots[nx_tail] = pack_lu<T>(nx_tailL, nx_tailU, 0u); a.nxt[nx_tail] = s; }
-                                        else nx_head = s;
-                                        a.nxt[s] = NIL;
-                                        nx_tail = s; nx_tailL = Lj; nx_tailU = Uj;
-                                        nx_n++;
-                                    }
-                                }
-                            }
-                        } else {
-                            if (do_del) {                                // deletion of code j (:445-461)
-                                ok_all &= h.push(al, a, lane_slot, b2, Lj, Uj, zg | (2u << 28), wD, r1D, r2D, r3D);
-                                c_push++;
-                            }
-                            if (do_mm) {                                 // match / mismatch (:467-497)
-                                const uint32_t gray = (uint32_t)((0x89BAEFDC45762310ull >> (4 * j)) & 15ull);
-                                const bool is_mm = (j == 10) || ((cmask & gray) == 0u);
-                                if (full || !is_mm) {
-                                    ok_all &= h.push(al, a, lane_slot, is_mm ? b1 : b0, Lj, Uj, zm + (is_mm ? 0x100u : 0u),
-                                                     e.w, e.r1, e.r2, e.r3);
-                                    c_push++;
-                                }
-                            }
-                        }
-                    }
+                }
+            } else {
+                // ---- (2b) children in the reference's push order (:433-504): insertion, deletions by
+                // code, then matches/mismatches by code; the k-th child of every lane is pushed together
+                if (ins_ok) {
+                    ok_all = h.push(al, a, lane_slot, b2, e.L, e.U, (zg | (1u << 28)) - 1u, wI, r1I, r2I, r3I);
+                    c_push++;
+                }
+                uint32_t md = del_ok ? okmask : 0u;
+                uint32_t mmk = full ? okmask : (okmask & compat_set);
+                c_push += __popc(md) + __popc(mmk);
+                while (md | mmk) {
+                    const bool isdel = md != 0u;
+                    const uint32_t cm = isdel ? md : mmk;
+                    const int j = __ffs(cm) - 1;
+                    if (isdel) md &= md - 1; else mmk &= mmk - 1;
+                    const T Lj = sLj[j][threadIdx.x], Uj = sUj[j][threadIdx.x];
+                    const bool is_mm = !((compat_set >> j) & 1u);
+                    const int sc = isdel ? b2 : (is_mm ? b1 : b0);
+                    const uint32_t cz = isdel ? (zg | (2u << 28)) : (zm + (is_mm ? 0x100u : 0u));
+                    ok_all &= h.push(al, a, lane_slot, sc, Lj, Uj, cz, isdel ? wD : e.w, isdel ? r1D : e.r1,
+                                     isdel ? r2D : e.r2, isdel ? r3D : e.r3);
                 }
             }
             if (!ok_all) { err = BWB_ERR_CAPACITY; mode = FLUSH; }
@@ -607,20 +601,16 @@ __global__ void __launch_bounds__(128, BWB_LANE_MIN_BLOCKS) k_search_l(const __g
             if (base + n_hits <= a.out_cap) {
                 uint32_t q = hit_head;
                 for (int k = 0; k < n_hits; k++) {
-                    const uint4 va = a.slots[q];
-                    const uint32_t sb = a.nxt[q];
-                    const uint4 vb = a.slots[sb];
-                    const uint32_t scs = a.nxt[sb];
-                    const uint4 vc = a.slots[scs];
-                    T L, U;
-                    unpack_lu<T>(va, L, U);
-                    const uint32_t z = va.w, go = (z >> 24) & 15u;
+                    PE<T> hh, hb;
+                    const uint32_t sb = slot_read<T>(a.slots, q, hh);
+                    q = slot_read<T>(a.slots, sb, hb);
+                    const uint32_t z = hh.z, go = (z >> 24) & 15u;
                     bwb_hit ht;
-                    ht.L = (uint64_t)L; ht.U = (uint64_t)U; ht.score = (int32_t)vc.x;
+                    ht.L = (uint64_t)hh.L; ht.U = (uint64_t)hh.U; ht.score = (int32_t)hb.L;
                     ht.num_mm = (uint8_t)((z >> 8) & 0xffu); ht.num_gapo = (uint8_t)go; ht.num_gape = (uint8_t)((z >> 16) & 0xffu);
-                    ht.aln_length = (uint8_t)vc.y; ht.n_runs = (uint8_t)go; ht.pad[0] = ht.pad[1] = ht.pad[2] = 0;
+                    ht.aln_length = (uint8_t)hb.U; ht.n_runs = (uint8_t)go; ht.pad[0] = ht.pad[1] = ht.pad[2] = 0;
                     ht.read_id = read_id;
-                    const uint32_t rr4[BWB_MAX_GAP_RUNS] = {vb.x >> 8, vb.y, vb.z, vb.w};
+                    const uint32_t rr4[BWB_MAX_GAP_RUNS] = {hh.w >> 8, hh.r1, hh.r2, hh.r3};
 #pragma unroll
                     for (int t = 0; t < BWB_MAX_GAP_RUNS; t++) {
                         const uint32_t v = (uint32_t)t < go ? rr4[t] : 0u;
@@ -628,7 +618,6 @@ __global__ void __launch_bounds__(128, BWB_LANE_MIN_BLOCKS) k_search_l(const __g
                         ht.runs[t].state = (uint8_t)((v >> 16) & 0xffu); ht.runs[t].pad = 0;
                     }
                     a.out_hits[base + k] = ht;
-                    q = a.nxt[scs];
                 }
             }
             a.read_off[r] = base;

@@ -92,7 +92,8 @@ const char *bwb_last_error(const bwb_ctx *ctx);
 int bwb_device_count(const bwb_ctx *ctx);
 
 /* Options (before bwb_index_upload / first bwb_align):
- *   "heap_pool_mb"     device bytes for the bucket-heap chunk pool, per device (default 8192)
+ *   "heap_pool_mb"     device MB for the search arena (heap entries, tail lists, hits), per device
+ *                      (default 0 = auto: half of the free device memory, at most 64 GB)
  *   "list_cap"         max SA intervals per list per read-slot (default 4096)
  *   "hits_per_read"    staging capacity for hits of one read (default 512)
  *   "warps_per_block"  search kernel block shape (default 8)
