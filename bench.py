@@ -41,7 +41,7 @@ WORKLOADS = {
     # name: genome kwargs, reads kwargs, reads per step (per GPU)
     "chr21": dict(genome=dict(seed=21, n_bases=48_100_000, n_records=1, snp_rate=0.012, tri_frac=0.03,
                               n_bubbles=40_000, n_frac=0.27),
-                  reads=dict(read_len=100, max_sub=2), batch=1 << 19, total_reads=10_000_000,
+                  reads=dict(read_len=100, max_sub=2), batch=1 << 21, total_reads=10_000_000,
                   desc="synthetic chr21-scale multi-genome (48.1 Mbp, 27% N, 1.2% SNP, 40k bubbles); 10M x 100bp reads, 0-2 subs"),
     "small": dict(genome=dict(seed=5, n_bases=2_000_000, n_records=2, snp_rate=0.012, tri_frac=0.03,
                               n_bubbles=1000, n_frac=0.05),

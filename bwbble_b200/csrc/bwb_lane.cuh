@@ -185,31 +185,42 @@ struct LaneHeap {
         return bm0 ? __ffs(bm0) - 1 : (bm1 ? 31 + __ffs(bm1) : (bm2 ? 63 + __ffs(bm2) : 95 + __ffs(bm3)));
     }
 
+    // link a new entry in front of bucket sc; the caller sets the occupancy bit (mark) afterwards
     __device__ __forceinline__ bool push(LaneAlloc &al, const LaneArgs &a, uint32_t lane_slot, int sc, T L, T U,
                                          uint32_t z, uint32_t w, uint32_t r1, uint32_t r2, uint32_t r3) {
         const uint32_t s = lane_alloc(al, a, lane_slot);
         if (s == NIL) return false;
-        const uint32_t old = occupied(sc) ? heads[sc * 128] : NIL;
-        slot_write<T>(a.slots, s, L, U, z, w, old, r1, r2, r3);
+        slot_write<T>(a.slots, s, L, U, z, w, heads[sc * 128], r1, r2, r3);
         heads[sc * 128] = s;
-        set_bit(sc);
         n++;
         return true;
     }
+    __device__ __forceinline__ void mark(int b) { set_bit(b); }
     // heap_pop (inexact_match.c:594-610); returns the bucket
     __device__ __forceinline__ int pop(const LaneArgs &a, PE<T> &e) {
         const int b = best();
         const uint32_t s = heads[b * 128];
         const uint32_t rest = slot_read<T>(a.slots, s, e);
+        heads[b * 128] = rest;
         if (rest == NIL) clear_bit(b);
-        else heads[b * 128] = rest;
         n--;
         return b;
     }
 };
 
+// A/B on B200 (chr21-scale, -n 5): 3 blocks of 128 lanes per SM (168 registers, no spills) with the
+// checkpoint counters fetched as 128-bit loads beat 4 blocks (128 registers, spills) by 1.4x.
+#ifndef BWB_LANE_CNT32
+#define BWB_LANE_CNT128 1
+#endif
+#ifdef BWB_LANE_CNT128
+#define BWB_CNT(c, j) (c)[j]
+#else
+#define BWB_CNT(c, j) __ldg((c) + (j))
+#endif
+
 #ifndef BWB_LANE_MIN_BLOCKS
-#define BWB_LANE_MIN_BLOCKS 4
+#define BWB_LANE_MIN_BLOCKS 3
 #endif
 
 template <bool WIDE>
@@ -247,6 +258,12 @@ __global__ void __launch_bounds__(128, BWB_LANE_MIN_BLOCKS) k_search_l(const __g
     PE<T> e;                                  // expansion: the popped entry; tail: its L,U hold the interval
     e.L = 0; e.U = 0; e.z = 0; e.w = 0; e.r1 = e.r2 = e.r3 = 0;
     int eb = 0;                               // bucket (= score) of e
+    // The entry the next heap_pop would return is kept in registers whenever it is a child of the
+    // current expansion: the parent came from the lowest bucket, so its last MATCH child (same
+    // score) would be pushed on top of that bucket and popped straight back.
+    bool have_next = false;
+    PE<T> nx = e;
+    int nx_bucket = 0;
     uint32_t t_flags = 0;                     // expansion flags, see below
     uint32_t cbase = 0;                       // read base of this step (rc[i-1])
     // exact tail in progress
@@ -281,22 +298,29 @@ __global__ void __launch_bounds__(128, BWB_LANE_MIN_BLOCKS) k_search_l(const __g
             n_hits = 0; hit_head = hit_tail = NIL; err = 0;
             best_score = a.nb; max_diff = a.max_diff; num_best = 0;
             have_task = false;
+            for (int b = 0; b < a.nb; b++) h.heads[b * 128] = NIL;
             if (nN <= a.max_diff) {                                   // N pre-check, inexact_match.c:259-266
-                if (!h.push(al, a, lane_slot, 0, (T)0, lastrow, (uint32_t)len, 0u, 0u, 0u, 0u)) err = BWB_ERR_CAPACITY;
+                // root entry (inexact_match.c:281): straight into the next-pop registers
+                have_next = true;
+                nx.L = 0; nx.U = lastrow; nx.z = (uint32_t)len; nx.w = 0; nx.r1 = nx.r2 = nx.r3 = 0;
+                nx_bucket = 0;
                 c_push++;
-                mode = err ? FLUSH : SEARCH;
+                mode = SEARCH;
             } else {
+                have_next = false;
                 mode = FLUSH;
             }
         }
 
         // ================= pop + prune + classify (inexact_match.c:293-375) =================
         if (mode == SEARCH) {
-            if ((uint32_t)h.n > c_maxheap) c_maxheap = (uint32_t)h.n;
-            if (h.n == 0 || h.n > a.max_entries) {
+            const int nvirt = h.n + (have_next ? 1 : 0);              // heap->num_entries of the reference
+            if ((uint32_t)nvirt > c_maxheap) c_maxheap = (uint32_t)nvirt;
+            if (nvirt == 0 || nvirt > a.max_entries) {
                 mode = FLUSH;
             } else {
-                eb = h.pop(a, e);
+                if (have_next) { e = nx; eb = nx_bucket; have_next = false; }
+                else eb = h.pop(a, e);
                 c_pops++;
                 const uint32_t z = e.z;
                 const int ei = (int)(z & 0xffu);
@@ -482,9 +506,21 @@ __global__ void __launch_bounds__(128, BWB_LANE_MIN_BLOCKS) k_search_l(const __g
                 kL2 = m >= 96 ? ~0u : (m <= 64 ? 0u : ((1u << (m - 64)) - 1u));
                 kL3 = m >= 128 ? ~0u : (m <= 96 ? 0u : ((1u << (m - 96)) - 1u));
             }
-            const uint32_t *cntU = reinterpret_cast<const uint32_t *>(blkU);
-            const uint32_t *cntL = reinterpret_cast<const uint32_t *>(blkL);
-
+#ifdef BWB_LANE_CNT128
+            // the 16 checkpoint counters of both blocks, four 128-bit loads each
+            uint32_t cU[16], cL[16];
+            {
+                const uint4 q0 = __ldg(blkU), q1 = __ldg(blkU + 1), q2 = __ldg(blkU + 2), q3 = __ldg(blkU + 3);
+                cU[0] = q0.x; cU[1] = q0.y; cU[2] = q0.z; cU[3] = q0.w; cU[4] = q1.x; cU[5] = q1.y; cU[6] = q1.z; cU[7] = q1.w;
+                cU[8] = q2.x; cU[9] = q2.y; cU[10] = q2.z; cU[11] = q2.w; cU[12] = q3.x; cU[13] = q3.y; cU[14] = q3.z; cU[15] = q3.w;
+                const uint4 p0 = __ldg(blkL), p1 = __ldg(blkL + 1), p2 = __ldg(blkL + 2), p3 = __ldg(blkL + 3);
+                cL[0] = p0.x; cL[1] = p0.y; cL[2] = p0.z; cL[3] = p0.w; cL[4] = p1.x; cL[5] = p1.y; cL[6] = p1.z; cL[7] = p1.w;
+                cL[8] = p2.x; cL[9] = p2.y; cL[10] = p2.z; cL[11] = p2.w; cL[12] = p3.x; cL[13] = p3.y; cL[14] = p3.z; cL[15] = p3.w;
+            }
+#else
+            const uint32_t *cU = reinterpret_cast<const uint32_t *>(blkU);   // checkpoint counters (same line as the planes)
+            const uint32_t *cL = reinterpret_cast<const uint32_t *>(blkL);
+#endif
             // expansion-only values
             const uint32_t z = e.z;
             const int go = (int)((z >> 24) & 15u);
@@ -523,8 +559,8 @@ __global__ void __launch_bounds__(128, BWB_LANE_MIN_BLOCKS) k_search_l(const __g
                 const uint32_t l1 = (pl.p0.y ^ x0) & (pl.p1.y ^ x1) & (pl.p2.y ^ x2) & (pl.p3.y ^ x3);
                 const uint32_t l2 = (pl.p0.z ^ x0) & (pl.p1.z ^ x1) & (pl.p2.z ^ x2) & (pl.p3.z ^ x3);
                 const uint32_t l3 = (pl.p0.w ^ x0) & (pl.p1.w ^ x1) & (pl.p2.w ^ x2) & (pl.p3.w ^ x3);
-                const uint32_t vU = __ldg(cntU + j) + __popc(u0 & kU0) + __popc(u1 & kU1) + __popc(u2 & kU2) + __popc(u3 & kU3);
-                const uint32_t vL = __ldg(cntL + j) + __popc(l0 & kL0) + __popc(l1 & kL1) + __popc(l2 & kL2) + __popc(l3 & kL3);
+                const uint32_t vU = BWB_CNT(cU, j) + __popc(u0 & kU0) + __popc(u1 & kU1) + __popc(u2 & kU2) + __popc(u3 & kU3);
+                const uint32_t vL = BWB_CNT(cL, j) + __popc(l0 & kL0) + __popc(l1 & kL1) + __popc(l2 & kL2) + __popc(l3 & kL3);
                 // Q1: O_alphabet skips codes 5,9,11,13 except for the checkpoint-symbol decrement
                 // (bwt.c:427-435,780); the exact search's O() counts them (bwt.c:348-372)
                 const bool quirk = (j == 5 || j == 9 || j == 11 || j == 13);
@@ -568,13 +604,26 @@ __global__ void __launch_bounds__(128, BWB_LANE_MIN_BLOCKS) k_search_l(const __g
             } else {
                 // ---- (2b) children in the reference's push order (:433-504): insertion, deletions by
                 // code, then matches/mismatches by code; the k-th child of every lane is pushed together
-                if (ins_ok) {
-                    ok_all = h.push(al, a, lane_slot, b2, e.L, e.U, (zg | (1u << 28)) - 1u, wI, r1I, r2I, r3I);
-                    c_push++;
-                }
                 uint32_t md = del_ok ? okmask : 0u;
                 uint32_t mmk = full ? okmask : (okmask & compat_set);
-                c_push += __popc(md) + __popc(mmk);
+                c_push += __popc(md) + __popc(mmk) + (ins_ok ? 1u : 0u);
+                // occupancy bits once per score class instead of once per child
+                if (ins_ok || md) h.mark(b2);
+                if (mmk & ~compat_set) h.mark(b1);
+                // last match child = next pop: keep it in registers (see have_next)
+                // (with mm_score == 0 mismatch children share the parent's bucket and count as well)
+                const uint32_t cand = (b1 == b0) ? mmk : (mmk & compat_set);
+                if (cand) {
+                    const int jk = 31 - __clz(cand);
+                    mmk &= ~(1u << jk);
+                    have_next = true;
+                    nx.L = sLj[jk][threadIdx.x]; nx.U = sUj[jk][threadIdx.x];
+                    nx.z = zm + (((compat_set >> jk) & 1u) ? 0u : 0x100u);
+                    nx.w = e.w; nx.r1 = e.r1; nx.r2 = e.r2; nx.r3 = e.r3;
+                    nx_bucket = b0;
+                    if (mmk & compat_set) h.mark(b0);
+                }
+                if (ins_ok) ok_all = h.push(al, a, lane_slot, b2, e.L, e.U, (zg | (1u << 28)) - 1u, wI, r1I, r2I, r3I);
                 while (md | mmk) {
                     const bool isdel = md != 0u;
                     const uint32_t cm = isdel ? md : mmk;
@@ -623,6 +672,7 @@ __global__ void __launch_bounds__(128, BWB_LANE_MIN_BLOCKS) k_search_l(const __g
             a.read_off[r] = base;
             a.read_cnt[r] = (uint32_t)n_hits;
             lane_alloc_reset(al, a, lane_slot);
+            have_next = false;
             mode = NEED;
         }
     }

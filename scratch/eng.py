@@ -1,5 +1,5 @@
 import sys, json, time, os
-sys.path.insert(0, '/root/repo')
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 import bench
 from bwbble_b200 import Aligner, default_params
@@ -14,5 +14,5 @@ al.load_index(fa+'.bwt')
 dr=al.upload_reads(b.seq,b.offsets)
 p=default_params(n=5)
 for it in range(2):
-    t=time.time(); r=al.align_resident(dr,p,fetch=False); ms=r.kernel_ms; r.close()
-print(json.dumps({'engine':eng,'batch':batch,'bps':bps,'kernel_ms':ms,'reads_per_s':batch/ms*1e3}))
+    r=al.align_resident(dr,p,fetch=False); ms=r.kernel_ms; c=r.counters(); r.close()
+print("RESULT "+json.dumps({'lib':os.environ.get('BWBBLE_B200_LIB','default').split('/')[-1],'engine':eng,'batch':batch,'bps':bps,'kernel_ms':ms,'reads_per_s':batch/ms*1e3,'pops':c['pops']}))
