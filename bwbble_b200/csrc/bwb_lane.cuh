@@ -607,10 +607,7 @@ __global__ void __launch_bounds__(128, BWB_LANE_MIN_BLOCKS) k_search_l(const __g
                 uint32_t md = del_ok ? okmask : 0u;
                 uint32_t mmk = full ? okmask : (okmask & compat_set);
                 c_push += __popc(md) + __popc(mmk) + (ins_ok ? 1u : 0u);
-                // occupancy bits once per score class instead of once per child
-                if (ins_ok || md) h.mark(b2);
-                if (mmk & ~compat_set) h.mark(b1);
-                // last match child = next pop: keep it in registers (see have_next)
+                // last match child = next pop: keep it in registers (see have_next);
                 // (with mm_score == 0 mismatch children share the parent's bucket and count as well)
                 const uint32_t cand = (b1 == b0) ? mmk : (mmk & compat_set);
                 if (cand) {
@@ -621,8 +618,11 @@ __global__ void __launch_bounds__(128, BWB_LANE_MIN_BLOCKS) k_search_l(const __g
                     nx.z = zm + (((compat_set >> jk) & 1u) ? 0u : 0x100u);
                     nx.w = e.w; nx.r1 = e.r1; nx.r2 = e.r2; nx.r3 = e.r3;
                     nx_bucket = b0;
-                    if (mmk & compat_set) h.mark(b0);
                 }
+                // occupancy bits once per score class (of what is really pushed) instead of once per child
+                if (ins_ok || md) h.mark(b2);
+                if (mmk & ~compat_set) h.mark(b1);
+                if (mmk & compat_set) h.mark(b0);
                 if (ins_ok) ok_all = h.push(al, a, lane_slot, b2, e.L, e.U, (zg | (1u << 28)) - 1u, wI, r1I, r2I, r3I);
                 while (md | mmk) {
                     const bool isdel = md != 0u;

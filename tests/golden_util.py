@@ -1,0 +1,34 @@
+"""Access to tests/golden/ (outputs of the UNMODIFIED reference, see tests/golden/make_golden.py)."""
+import gzip
+import json
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLDEN = os.path.join(HERE, "golden")
+MANIFEST = json.load(open(os.path.join(GOLDEN, "manifest.json")))
+_FLAG2FIELD = {"-M": "mm_score", "-O": "gapo_score", "-E": "gape_score", "-n": "max_diff", "-k": "max_diff_seed",
+               "-o": "max_gapo", "-e": "max_gape", "-l": "seed_length", "-m": "max_entries", "-t": "n_threads"}
+
+
+def grid():
+    return MANIFEST["grid"]
+
+
+def flags_to_kwargs(flags):
+    return {_FLAG2FIELD[flags[i]]: int(flags[i + 1]) for i in range(0, len(flags), 2)}
+
+
+def golden_bytes(name):
+    return open(os.path.join(GOLDEN, name), "rb").read()
+
+
+def materialise_index(tmpdir):
+    """g.fa + g.fa.bwt (+ .ann) as the reference wrote them, in tmpdir; returns the fasta path."""
+    fa = os.path.join(str(tmpdir), "g.fa")
+    with open(fa, "wb") as f:
+        f.write(golden_bytes("g.fa"))
+    with open(fa + ".bwt", "wb") as f:
+        f.write(gzip.decompress(golden_bytes("g.fa.bwt.gz")))
+    with open(fa + ".ann", "wb") as f:
+        f.write(golden_bytes("g.fa.ann"))
+    return fa

@@ -1,0 +1,35 @@
+"""End to end through the reference's OWN host: oracle/_ref/bwbble_gpu = the reference's main.o, align.o,
+bwt.o, io.o, is.o, exact_match.o linked with bwbble_b200/csrc/shim/bwbble_shim.c + libbwbble_b200.so
+(`make -C oracle dropin`, built where /root/reference exists; the binary travels to the GPU box).
+CLI, index files, .aln and SAM must be indistinguishable from the reference's."""
+import os
+import subprocess
+
+import pytest
+
+import golden_util as G
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GPU_BIN = os.path.join(ROOT, "oracle", "_ref", "bwbble_gpu")
+REF_BIN = os.path.join(ROOT, "oracle", "_ref", "bwbble")
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(not (os.path.exists(GPU_BIN) and os.path.exists(REF_BIN)),
+                                 reason="drop-in binaries not built (make -C oracle ref dropin needs /root/reference)")]
+
+
+@pytest.mark.parametrize("tag", ["n0", "n3", "n4_o2_e3_k3_l20", "n3_t4"])
+def test_dropin_cli_writes_the_reference_aln_and_sam(tmp_path, tag):
+    fa = G.materialise_index(tmp_path)
+    fq = os.path.join(G.GOLDEN, "r.fq")
+    flags = G.grid()[tag]
+    aln = str(tmp_path / "out.aln")
+    r = subprocess.run([GPU_BIN, "align", *flags, fa, fq, aln], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "Processed" in r.stdout
+    assert open(aln, "rb").read() == G.golden_bytes("aln_%s.aln" % tag)
+    if "sam_%s.sam" % tag in G.MANIFEST["md5"]:
+        sam = str(tmp_path / "out.sam")
+        n = flags[flags.index("-n") + 1]
+        subprocess.run([REF_BIN, "aln2sam", "-n", n, fa, fq, aln, sam], check=True, stdout=subprocess.DEVNULL, timeout=600)
+        assert open(sam, "rb").read() == G.golden_bytes("sam_%s.sam" % tag)

@@ -185,6 +185,7 @@ GRID = [
     dict(n=0), dict(n=1), dict(n=2), dict(n=3), dict(n=5),
     dict(n=4, o=2, e=3, k=3, l=20), dict(n=3, M=2, O=5, E=2), dict(n=4, l=0), dict(n=3, k=1),
     dict(n=6, o=2, M=4, O=4, E=4), dict(n=3, o=0), dict(n=2, e=0), dict(n=4, m=200),
+    dict(n=4, M=0, m=3000), dict(n=4, E=0, o=2), dict(n=3, M=11), dict(n=3, O=3, E=3),     # score classes sharing a bucket
 ]
 
 
@@ -260,3 +261,20 @@ def test_unsupported_params_fail_loudly(gpu_case):
     for kw in (dict(use_precalc=1), dict(is_multiref=0), dict(o=9)):
         with pytest.raises(BwbError):
             al.align(reads.seq, reads.offsets, default_params(n=2, **kw))
+
+
+def test_gpu_reproduces_the_reference_golden_files(tmp_path):
+    """K0..K5 against the files the UNMODIFIED reference wrote (tests/golden/), no oracle involved."""
+    import golden_util as G
+    from bwbble_b200.fastx import read_fastq
+    import os
+    fa = G.materialise_index(tmp_path)
+    reads = read_fastq(os.path.join(G.GOLDEN, "r.fq"))
+    with Aligner(heap_pool_mb=512) as al:
+        al.load_index(fa + ".bwt")
+        for tag, flags in sorted(G.grid().items()):
+            kw = G.flags_to_kwargs(flags)
+            kw.pop("n_threads", None)
+            got = al.align(reads.seq, reads.offsets, default_params(**kw)).aln_bytes()
+            exp = G.golden_bytes("aln_%s.aln" % tag)
+            assert got == exp, "%s: %s" % (tag, first_difference(got, exp))
