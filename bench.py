@@ -249,7 +249,7 @@ def main():
 
     # ---- value: reads resident in HBM ------------------------------------------------------
     dev_reads = [al.upload_reads(b.seq, b.offsets) for b in batches]
-    kernel_ms, hits_total, ctr_sum = [], 0, {}
+    kernel_ms, k3_ms, hits_total, ctr_sum = [], [], 0, {}
     for s in range(args.warmup):
         al.align_resident(dev_reads[s], p, fetch=False).close()
     torch.cuda.synchronize()
@@ -261,6 +261,7 @@ def main():
     for s in range(args.warmup, n_steps):
         r = al.align_resident(dev_reads[s], p, fetch=False)
         kernel_ms.append(r.kernel_ms)
+        k3_ms.append(r.k3_ms)
         hits_total += r.num_hits
         for k, v in r.counters().items():
             ctr_sum[k] = max(ctr_sum.get(k, 0), v) if k.startswith("max") else ctr_sum.get(k, 0) + v
@@ -323,9 +324,19 @@ def main():
             q_per_read = (stats["n_O"] + stats["n_Oalpha"]) / n_s
             k_ms = float(np.mean(kernel_ms))
             achieved = w["batch"] * q_per_read * 128 / (k_ms / 1e3) / 1e9
+            traffic, traffic_src = None, None
+            try:
+                tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["k_search_l"]
+                traffic = tj["dram_bytes_per_read"] * w["batch"] / 1e9      # GB per launch, from the ncu capture
+                traffic_src = tj["source"]
+            except Exception:
+                pass
             roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": None, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
-                    "kernel": "k_align", "kernel_ms_per_launch": k_ms, "rank_queries_per_read_reference": q_per_read,
+                    "traffic": traffic, "traffic_unit": "GB of DRAM read+write per launch", "traffic_source": traffic_src,
+                    "algorithmic_gb_per_launch": w["batch"] * q_per_read * 128 / 1e9, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
+                    "kernel": "k_search_l (K4: inexact search, one read per lane)", "kernel_ms_per_launch": k_ms,
+                    "k3_ms_per_launch": float(np.mean(k3_ms)), "kernel_share_of_step": k_ms / (dev_ms / args.steps),
+                    "rank_queries_per_read_reference": q_per_read,
                     "bytes_per_query": 128,
                     "physical_block_loads_per_read": ctr_sum.get("rank_queries", 0) / (w["batch"] * args.steps)}
         line = {"metric": "reads/sec (100bp, BWA-default diffs)", "value": value, "unit": "reads/s", "n_gpus": world,
@@ -338,7 +349,7 @@ def main():
                            "parallelism": "reads sharded x%d, index replicated, no collective" % world},
                 "e2e": {"value": e2e, "unit": "reads/s", "h2d_bytes_per_step": h2d * world,
                         "d2h_bytes_per_step": int(np.mean(d2h_bytes)) * world},
-                "gpu_launches": 3 * args.steps,
+                "gpu_launches": 4 * args.steps,
                 "clocks": sampler.summary(),
                 "roofline": roof, "cpu_baseline": None if cpu is None else
                 {"value": cpu["value"], "unit": "reads/s", "cores": cpu["cores"], "kind": cpu["kind"], "sample": cpu["sample"],

@@ -72,6 +72,7 @@ SIGNATURES = {
     "bwb_results_hits": (C.c_void_p, [C.c_void_p]),
     "bwb_results_counters": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64 * 8)]),
     "bwb_results_kernel_ms": (C.c_double, [C.c_void_p]),
+    "bwb_results_k3_ms": (C.c_double, [C.c_void_p]),
     "bwb_results_aln_bytes": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]),
     "bwb_results_write_aln": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int]),
     "bwb_results_free": (None, [C.c_void_p]),

@@ -89,6 +89,10 @@ class AlignResult:
     def kernel_ms(self) -> float:
         return float(_lib.lib().bwb_results_kernel_ms(self._h))
 
+    @property
+    def k3_ms(self) -> float:
+        return float(_lib.lib().bwb_results_k3_ms(self._h))
+
     def aln_bytes(self) -> bytes:
         buf = C.c_void_p()
         ln = C.c_uint64()

@@ -173,6 +173,8 @@ int bwb_results_counters(const bwb_results *r, uint64_t out[8]);
 /* Duration of the search kernel (K4) of the call that produced r, in ms: CUDA events on the launch
  * stream, max over the context's devices. */
 double bwb_results_kernel_ms(const bwb_results *r);
+/* Same for the lower-bound kernel K3 (0 for the fused warp engine). */
+double bwb_results_k3_ms(const bwb_results *r);
 /* Serialise exactly as alns2alnf_bin (align.c:345-382) does for each read in order. */
 int bwb_results_aln_bytes(const bwb_results *r, uint8_t **buf, uint64_t *len);   /* free with bwb_free */
 int bwb_results_write_aln(const bwb_results *r, const char *path, int append);
