@@ -306,13 +306,20 @@ def main():
     e2e = reads_per_step * args.steps / (e2e_ms / 1e3)
 
     if rank == 0:
-        cpu, stats = None, None
+        cpu, stats, n_s = None, None, 0
         if not args.no_cpu and world == 1:
             n_s = args.cpu_sample or max(2048, min(cores * 512, 65536))
             cpu, stats = run_cpu_reference(fa, batches[args.warmup], n_s, PARAMS, cores, want_stats=True)
         elif not args.no_cpu:
-            n_s = 4096
+            # N > 1: no CPU timing (rank 0 at N=1 only), but Q of the reference algorithm is still
+            # counted on a small sample so that the roofline can be reported
             sys.path.insert(0, os.path.join(ROOT, "tests"))
+            import oracle
+            n_s = 4096
+            sub = batches[args.warmup].slice(0, n_s)
+            orc = oracle.Oracle(fa + ".bwt")
+            _, stats = orc.align(sub.seq, sub.offsets, default_params(**PARAMS), threads=cores)
+            orc.close()
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -322,7 +329,8 @@ def main():
         roof = None
         if stats:
             q_per_read = (stats["n_O"] + stats["n_Oalpha"]) / n_s
-            k_ms = float(np.mean(kernel_ms))
+            k4_only = float(np.mean(kernel_ms))
+            k_ms = k4_only + float(np.mean(k3_ms))      # the reference's Q spans calculate_d (K3) and inexact_match (K4)
             achieved = w["batch"] * q_per_read * 128 / (k_ms / 1e3) / 1e9
             traffic, traffic_src = None, None
             try:
@@ -334,8 +342,9 @@ def main():
             roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                     "traffic": traffic, "traffic_unit": "GB of DRAM read+write per launch", "traffic_source": traffic_src,
                     "algorithmic_gb_per_launch": w["batch"] * q_per_read * 128 / 1e9, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
-                    "kernel": "k_search_l (K4: inexact search, one read per lane)", "kernel_ms_per_launch": k_ms,
-                    "k3_ms_per_launch": float(np.mean(k3_ms)), "kernel_share_of_step": k_ms / (dev_ms / args.steps),
+                    "kernel": "k_calc_d_g + k_search_l (K3 lower bounds + K4 search; K4 is the dominant launch)",
+                    "kernel_ms_per_launch": k_ms, "k4_ms_per_launch": k4_only, "k3_ms_per_launch": float(np.mean(k3_ms)),
+                    "kernel_share_of_step": k_ms / (dev_ms / args.steps),
                     "rank_queries_per_read_reference": q_per_read,
                     "bytes_per_query": 128,
                     "physical_block_loads_per_read": ctr_sum.get("rank_queries", 0) / (w["batch"] * args.steps)}

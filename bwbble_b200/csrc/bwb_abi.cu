@@ -39,7 +39,7 @@ struct Device {
     // index
     uint4 *blocks = nullptr;
     // search scratch (sized for n_warps)
-    int n_warps = 0, grid = 0, wpb = 0;
+    int n_warps = 0, grid = 0, wpb = 0, grid3 = 0;
     size_t smem_bytes = 0;
     DevBuf glists, chunks, chunk_link, stage;
     uint32_t chunks_per_warp = 0, n_chunks = 0;
@@ -259,8 +259,21 @@ int prepare_search_lane(bwb_ctx *ctx, Device &d, int nb, bool wide) {
     }
     d.grid = grid; d.wpb = tpb / 32; d.smem_bytes = smem;
     int rc;
-    // K3 still runs 8-lane groups: its list scratch is sized for its own grid of 256-thread blocks
-    const int n_groups3 = (grid / 2 + 1) * (256 / GL);
+    // K3 runs 8-lane groups in 256-thread blocks on its own persistent grid (occupancy query)
+    {
+        int bps3 = 0;
+        const size_t smem3 = (size_t)(256 / GL) * (G_LIST_SMEM + 256);
+        if (wide) {
+            CU(cudaFuncSetAttribute(k_calc_d_g<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
+            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps3, k_calc_d_g<true>, 256, smem3));
+        } else {
+            CU(cudaFuncSetAttribute(k_calc_d_g<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
+            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps3, k_calc_d_g<false>, 256, smem3));
+        }
+        if (bps3 <= 0) bps3 = 1;
+        d.grid3 = bps3 * d.sm_count;
+    }
+    const int n_groups3 = d.grid3 * (256 / GL);
     if ((rc = ensure(ctx, d.glists, (size_t)n_groups3 * 2 * ctx->list_cap * sizeof(ulonglong2), false))) return rc;
     {
         // arena of 32-byte slots: 3/4 split into private ranges, 1/4 shared in blocks of LBLK slots
@@ -851,7 +864,7 @@ static int launch_shard(bwb_ctx *ctx, Device &d, const bwb_params *p, int nb, co
         c.status = a.status; c.counters = a.counters;
         c.smem_per_group = G_LIST_SMEM + ((max_len + 15) & ~15);
         const size_t smem3 = (size_t)(256 / GL) * c.smem_per_group;
-        const int grid3 = d.grid / 2 + 1;
+        const int grid3 = d.grid3;
         if (wide) {
             CU(cudaFuncSetAttribute(k_calc_d_g<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
             k_calc_d_g<true><<<grid3, 256, smem3, d.stream>>>(c);

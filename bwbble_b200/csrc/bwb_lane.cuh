@@ -64,34 +64,24 @@ struct LaneAlloc {
     uint32_t borrowed_last;
 };
 
-// slow path: borrow a block of LBLK slots from the shared pool (own shard first)
-__device__ __noinline__ uint32_t lane_borrow(LaneAlloc &al, const LaneArgs &a, uint32_t lane_slot) {
+// slow path: take a block of LBLK slots from the shared pool (own shard first); NIL if exhausted.
+// Deliberately free of references to the caller's allocator state so that it stays in registers.
+__device__ __noinline__ uint32_t pool_take_block(PoolState *pool, uint32_t *blk_link, uint32_t lane_slot) {
     for (int t = 0; t < POOL_SHARDS; t++) {
         const uint32_t sh = (lane_slot + (uint32_t)t) % POOL_SHARDS;
-        uint32_t blk = NIL;
-        {   // pop one block
-            unsigned long long *head = &a.pool->head[sh];
-            unsigned long long old = atomicAdd(head, 0ull);
-            for (;;) {
-                const uint32_t id = (uint32_t)old;
-                if (id == NIL) break;
-                const uint32_t nx = *reinterpret_cast<volatile uint32_t *>(a.blk_link + id);
-                const unsigned long long prev = atomicCAS(head, old, (((old >> 32) + 1ull) << 32) | nx);
-                if (prev == old) { blk = id; break; }
-                old = prev;
-            }
+        unsigned long long *head = &pool->head[sh];
+        unsigned long long old = atomicAdd(head, 0ull);
+        for (;;) {
+            const uint32_t id = (uint32_t)old;
+            if (id == NIL) break;
+            const uint32_t nx = *reinterpret_cast<volatile uint32_t *>(blk_link + id);
+            const unsigned long long prev = atomicCAS(head, old, (((old >> 32) + 1ull) << 32) | nx);
+            if (prev == old) return id;
+            old = prev;
         }
-        if (blk == NIL && *reinterpret_cast<volatile uint32_t *>(&a.pool->bump[sh]) < a.pool->limit[sh]) {
-            const uint32_t o = atomicAdd(&a.pool->bump[sh], 1u);
-            if (o < a.pool->limit[sh]) blk = o;
-        }
-        if (blk != NIL) {
-            a.blk_link[blk] = al.borrowed;
-            if (al.borrowed == NIL) al.borrowed_last = blk;
-            al.borrowed = blk;
-            al.ov_cur = blk * LBLK;
-            al.ov_end = al.ov_cur + LBLK;
-            return al.ov_cur++;
+        if (*reinterpret_cast<volatile uint32_t *>(&pool->bump[sh]) < pool->limit[sh]) {
+            const uint32_t o = atomicAdd(&pool->bump[sh], 1u);
+            if (o < pool->limit[sh]) return o;
         }
     }
     return NIL;
@@ -100,7 +90,14 @@ __device__ __noinline__ uint32_t lane_borrow(LaneAlloc &al, const LaneArgs &a, u
 __device__ __forceinline__ uint32_t lane_alloc(LaneAlloc &al, const LaneArgs &a, uint32_t lane_slot) {
     if (al.bump < al.priv_hi) return al.bump++;
     if (al.ov_cur < al.ov_end) return al.ov_cur++;
-    return lane_borrow(al, a, lane_slot);
+    const uint32_t blk = pool_take_block(a.pool, a.blk_link, lane_slot);
+    if (blk == NIL) return NIL;
+    a.blk_link[blk] = al.borrowed;
+    if (al.borrowed == NIL) al.borrowed_last = blk;
+    al.borrowed = blk;
+    al.ov_cur = blk * LBLK;
+    al.ov_end = al.ov_cur + LBLK;
+    return al.ov_cur++;
 }
 // end of a read: every slot is dead; hand borrowed blocks back with one CAS
 __device__ __forceinline__ void lane_alloc_reset(LaneAlloc &al, const LaneArgs &a, uint32_t lane_slot) {
@@ -330,10 +327,15 @@ __global__ void __launch_bounds__(128, BWB_LANE_MIN_BLOCKS) k_search_l(const __g
                 const int dl = max_diff - used;
                 const int dls = a.max_diff_seed - used;
                 const int si = ei - (len - a.seed_len);
+                // everything this entry may need from the read's arrays, fetched in one go (one latency)
+                const uint32_t dA = D[ei > 0 ? ei - 1 : 0];                 // D[i-1]
+                const uint32_t dB = D[ei > 1 ? ei - 2 : 0];                 // D[i-2]
+                const uint32_t sA = Ds[si > 0 ? si - 1 : 0];                // D_seed[si-1]
+                const uint32_t sB = Ds[si > 1 ? si - 2 : 0];                // D_seed[si-2]
+                const uint32_t base_i1 = rseq[ei > 0 ? len - ei : 0];       // seq[len-1-(i-1)]
                 if ((eb & 0xff) > best_score + a.mm_score) {
                     mode = FLUSH;                                       // inexact_match.c:309
-                } else if (dl < 0 || (ei > 0 && dl < (int)(D[ei - 1] & 0x1ff)) ||
-                           (si > 0 && dls < (int)(Ds[si - 1] & 0x1ff))) {
+                } else if (dl < 0 || (ei > 0 && dl < (int)(dA & 0x1ff)) || (si > 0 && dls < (int)(sA & 0x1ff))) {
                     // pruned
                 } else if (ei == 0) {                                   // a hit (inexact_match.c:331-344)
                     bool add = true;
@@ -378,12 +380,12 @@ __global__ void __launch_bounds__(128, BWB_LANE_MIN_BLOCKS) k_search_l(const __g
                     bool allow_diff = true, allow_mm = true;
                     const int i1 = ei - 1;
                     if (i1 > 0) {
-                        const uint32_t d1 = D[i1], d0 = D[i1 - 1];
+                        const uint32_t d1 = dA, d0 = dB;
                         if (dl - 1 < (int)(d0 & 0x1ff)) allow_diff = false;
                         else if ((int)(d1 & 0x1ff) == dl - 1 && (int)(d0 & 0x1ff) == dl - 1 && (d1 & 0x8000u)) allow_mm = false;
                     }
                     if (si - 1 > 0) {
-                        const uint32_t s1 = Ds[si - 1], s0 = Ds[si - 2];
+                        const uint32_t s1 = sA, s0 = sB;
                         if (dls - 1 < (int)(s0 & 0x1ff)) allow_diff = false;
                         else if ((int)(s1 & 0x1ff) == dls - 1 && (int)(s0 & 0x1ff) == dls - 1 && (s1 & 0x8000u)) allow_mm = false;
                     }
@@ -395,7 +397,7 @@ __global__ void __launch_bounds__(128, BWB_LANE_MIN_BLOCKS) k_search_l(const __g
                     // bit0 full (mismatch children allowed), bit1 deletions allowed, bit2 insertion allowed
                     t_flags = ((allow_diff && allow_mm) ? 1u : 0u) | ((gap_allowed && state != 1u) ? 2u : 0u) |
                               ((gap_allowed && state != 2u) ? 4u : 0u);
-                    cbase = nt4_compl(rseq[len - 1 - i1]);              // rc[i-1]
+                    cbase = nt4_compl(base_i1);                         // rc[i-1]
                     have_task = true;
                     task_tail = false;
                 }
