@@ -41,7 +41,7 @@ WORKLOADS = {
     # name: genome kwargs, reads kwargs, reads per step (per GPU)
     "chr21": dict(genome=dict(seed=21, n_bases=48_100_000, n_records=1, snp_rate=0.012, tri_frac=0.03,
                               n_bubbles=40_000, n_frac=0.27),
-                  reads=dict(read_len=100, max_sub=2), batch=1 << 21, total_reads=10_000_000,
+                  reads=dict(read_len=100, max_sub=2), batch=1 << 22, total_reads=10_000_000,
                   desc="synthetic chr21-scale multi-genome (48.1 Mbp, 27% N, 1.2% SNP, 40k bubbles); 10M x 100bp reads, 0-2 subs"),
     "small": dict(genome=dict(seed=5, n_bases=2_000_000, n_records=2, snp_rate=0.012, tri_frac=0.03,
                               n_bubbles=1000, n_frac=0.05),
@@ -141,10 +141,11 @@ def run_cpu_reference(fa: str, reads, n_sample: int, params: dict, threads: int,
     if want_stats:      # instrumented restatement: rank-query count Q of the reference algorithm
         orc = oracle.Oracle(fa + ".bwt")
         t = time.time()
-        _, stats = orc.align(sub.seq, sub.offsets, p, threads=threads)
+        aln_bytes, stats = orc.align(sub.seq, sub.offsets, p, threads=threads)
         port_s = time.time() - t
         orc.close()
         out["port_reads_per_s"] = n_sample / port_s
+        out["port_aln_bytes"] = aln_bytes
     ref_bin = os.path.join(ROOT, "oracle", "_ref", "bwbble")
     if os.path.exists(ref_bin):
         with tempfile.TemporaryDirectory() as d:
@@ -320,6 +321,20 @@ def main():
             orc = oracle.Oracle(fa + ".bwt")
             _, stats = orc.align(sub.seq, sub.offsets, default_params(**PARAMS), threads=cores)
             orc.close()
+        parity = None
+        if cpu is not None and "port_aln_bytes" in cpu:
+            # spot check at bench scale: the sample's .aln stream from the device == the oracle's
+            sub = batches[args.warmup].slice(0, n_s)
+            got = al.align(sub.seq, sub.offsets, p).aln_bytes()
+            parity = {"reads": n_s, "identical_to_oracle": got == cpu.pop("port_aln_bytes"), "aln_bytes": len(got)}
+        occ = {}
+        try:
+            nq = 1 << 26
+            for mode, name in ((0, "O(c,i): 1 thread/query"), (1, "O_alphabet(i): 16 lanes/query")):
+                ms, _ = al.occ_bench(nq, seed=7, mode=mode, iters=5)
+                occ[name] = {"queries_per_s": nq / (ms / 1e3), "GBps_at_128B_per_query": nq * 128 / (ms / 1e3) / 1e9}
+        except Exception as ex:          # never let the micro-benchmark break the headline line
+            occ = {"error": str(ex)}
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -363,6 +378,7 @@ def main():
                 "roofline": roof, "cpu_baseline": None if cpu is None else
                 {"value": cpu["value"], "unit": "reads/s", "cores": cpu["cores"], "kind": cpu["kind"], "sample": cpu["sample"],
                  "port_reads_per_s": cpu.get("port_reads_per_s")},
+                "parity_check": parity, "occ_gather": occ,
                 "counters_per_read": {k: (v if k.startswith("max") else v / (w["batch"] * args.steps)) for k, v in ctr_sum.items()},
                 "hits_per_read": hits_total / (w["batch"] * args.steps)}
         print(json.dumps(line), flush=True)
