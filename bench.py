@@ -43,6 +43,11 @@ WORKLOADS = {
                               n_bubbles=40_000, n_frac=0.27),
                   reads=dict(read_len=100, max_sub=2), batch=1 << 22, total_reads=10_000_000,
                   desc="synthetic chr21-scale multi-genome (48.1 Mbp, 27% N, 1.2% SNP, 40k bubbles); 10M x 100bp reads, 0-2 subs"),
+    # 600 M-row index (HBM-resident, ~5x L2): the regime of BASELINE configs[3] at 1/11 of its size
+    "g300": dict(genome=dict(seed=37, n_bases=300_000_000, n_records=8, snp_rate=0.012, tri_frac=0.03,
+                             n_bubbles=130_000, n_frac=0.05),
+                 reads=dict(read_len=100, max_sub=2), batch=1 << 20, total_reads=100_000_000,
+                 desc="synthetic 300 Mbp multi-genome (600 M BWT rows, 5% N, 1.2% SNP, 130k bubbles); 100bp reads, 0-2 subs"),
     "small": dict(genome=dict(seed=5, n_bases=2_000_000, n_records=2, snp_rate=0.012, tri_frac=0.03,
                               n_bubbles=1000, n_frac=0.05),
                   reads=dict(read_len=100, max_sub=2), batch=1 << 15, total_reads=1_000_000,

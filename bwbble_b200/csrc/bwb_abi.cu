@@ -699,7 +699,7 @@ int bwb_lower_bounds(bwb_ctx *ctx, const uint8_t *seq, const uint64_t *offsets, 
     CalcArgs c;
     memset(&c, 0, sizeof c);
     c.ix = make_view(ctx, d); c.seq = dseq; c.offsets = doff; c.n_reads = (uint32_t)n_reads;
-    c.seed_len = seed_len; c.max_len = max_len; c.queue = (uint32_t *)(sm + 4);
+    c.seed_len = seed_len; c.max_len = max_len; c.is_multiref = 1; c.queue = (uint32_t *)(sm + 4);
     c.glists = gl; c.list_cap = ctx->list_cap; c.d_main = dm; c.d_seed = ds;
     c.status = (uint32_t *)(sm + 8); c.counters = (unsigned long long *)(sm + 32);
     c.smem_per_group = G_LIST_SMEM + ((max_len + 15) & ~15);
@@ -763,7 +763,8 @@ void bwb_reads_free(bwb_reads *r) {
 
 static int check_params(bwb_ctx *ctx, const bwb_params *p, int max_len, int &nb) {
     if (p->use_precalc) return fail(ctx, BWB_ERR_UNSUPPORTED, "-P (pre-calculated intervals) is not built on the device path");
-    if (!p->is_multiref) return fail(ctx, BWB_ERR_UNSUPPORTED, "-S (single-genome mode) is not built on the device path");
+    if (!p->is_multiref && ctx->engine != 0)
+        return fail(ctx, BWB_ERR_UNSUPPORTED, "-S (single-genome mode) is only built in the lane engine");
     if (p->max_diff < 0 || p->max_gapo < 0 || p->max_gape < 0 || p->mm_score < 0 || p->gapo_score < 0 || p->gape_score < 0 ||
         p->seed_length < 0 || p->max_diff > 200)
         return fail(ctx, BWB_ERR_ARG, "negative or out-of-range alignment parameter");
@@ -857,7 +858,7 @@ static int launch_shard(bwb_ctx *ctx, Device &d, const bwb_params *p, int nb, co
         CalcArgs c;
         memset(&c, 0, sizeof c);
         c.ix = a.ix; c.seq = a.seq; c.offsets = a.offsets; c.n_reads = a.n_reads;
-        c.seed_len = p->seed_length; c.max_len = max_len;
+        c.seed_len = p->seed_length; c.max_len = max_len; c.is_multiref = p->is_multiref;
         c.queue = (uint32_t *)(sm + 4);
         c.glists = d.glists.p; c.list_cap = ctx->list_cap;
         c.pk_main = (uint16_t *)d.pk_main.p; c.pk_seed = (uint16_t *)d.pk_seed.p; c.n_count = (uint16_t *)d.n_count.p;
@@ -881,7 +882,7 @@ static int launch_shard(bwb_ctx *ctx, Device &d, const bwb_params *p, int nb, co
         g.max_diff = a.max_diff; g.max_gapo = a.max_gapo; g.max_gape = a.max_gape; g.max_entries = a.max_entries;
         g.mm_score = a.mm_score; g.gapo_score = a.gapo_score; g.gape_score = a.gape_score;
         g.seed_len = a.seed_len; g.max_diff_seed = a.max_diff_seed; g.max_best = a.max_best; g.no_indel_len = a.no_indel_len;
-        g.nb = a.nb; g.queue = a.queue;
+        g.nb = a.nb; g.queue = a.queue; g.is_multiref = p->is_multiref;
         g.pk_main = c.pk_main; g.pk_seed = c.pk_seed; g.n_count = c.n_count;
         g.slots = (uint4 *)d.chunks.p;
         g.slots_per_lane = d.slots_per_lane; g.priv_total = d.priv_total;
@@ -898,7 +899,7 @@ static int launch_shard(bwb_ctx *ctx, Device &d, const bwb_params *p, int nb, co
         CalcArgs c;
         memset(&c, 0, sizeof c);
         c.ix = a.ix; c.seq = a.seq; c.offsets = a.offsets; c.n_reads = a.n_reads;
-        c.seed_len = p->seed_length; c.max_len = max_len;
+        c.seed_len = p->seed_length; c.max_len = max_len; c.is_multiref = 1;
         c.queue = (uint32_t *)(sm + 4);
         c.glists = d.glists.p; c.list_cap = ctx->list_cap;
         c.d_main = (int2 *)d.d_main.p; c.d_seed = (int2 *)d.d_seed.p;

@@ -75,10 +75,12 @@ struct StepState {
 // `on` is uniform per group.  Returns false (for the group) if the list overflows ls.cap.
 template <class T>
 __device__ __forceinline__ bool list_pass(bool on, const IndexView &ix, const T *sC, const GList<T> &ls,
-                                          StepState<T> &st, uint32_t c, uint32_t &nloads) {
+                                          StepState<T> &st, uint32_t c, uint32_t &nloads, bool multiref = true) {
     const uint32_t gl = g_lane();
-    const bool active = on && gl < 7u && st.s < st.n_cur;
-    const uint32_t code = (compat_codes(c & 3u) >> (4u * (gl < 7u ? gl : 0u))) & 15u;
+    // multi-genome: the 7 codes containing base c on lanes 0..6; single-genome (-S): nt4_gray[c] on lane 0
+    const bool active = on && (multiref ? gl < 7u : gl == 0u) && st.s < st.n_cur;
+    const uint32_t code = multiref ? ((compat_codes(c & 3u) >> (4u * (gl < 7u ? gl : 0u))) & 15u)
+                                   : ((0x173Fu >> (4u * (c & 3u))) & 15u);
     typename Pair<T>::type iv;
     iv.x = 1; iv.y = 0;
     if (active) iv = glget<T>(ls, st.cur, st.s);
@@ -150,6 +152,7 @@ struct CalcArgs {
     uint32_t n_reads;
     int seed_len;            // 0: no seed array
     int max_len;
+    int is_multiref;         // 0 = -S: one code per base (inexact_match.c:176-206)
     uint32_t *queue;
     void *glists;            // [n_groups][2][list_cap] pairs (allocated 16 B each)
     int list_cap;
@@ -229,7 +232,7 @@ __global__ void __launch_bounds__(256) k_calc_d_g(const __grid_constant__ CalcAr
         }
         const bool pass_on = run && in_step && st.s < st.n_cur;
         if (__any_sync(FULL, pass_on)) {
-            if (!list_pass<T>(pass_on, a.ix, sC, ls, st, c, nloads)) {
+            if (!list_pass<T>(pass_on, a.ix, sC, ls, st, c, nloads, a.is_multiref != 0)) {
                 if (gl == 0) atomicExch(a.status, (uint32_t)(-BWB_ERR_CAPACITY));
                 st.n_next = 0;
             }

@@ -39,6 +39,7 @@ struct LaneArgs {
     int max_diff, max_gapo, max_gape, max_entries, mm_score, gapo_score, gape_score;
     int seed_len, max_diff_seed, max_best, no_indel_len;
     int nb;
+    int is_multiref;                         // 0 = -S single-genome mode (codes A,G,C,T only)
     uint32_t *queue;
     const uint16_t *pk_main, *pk_seed;       // packed lower bounds from K3
     const uint16_t *n_count;                 // N bases per read, from K3
@@ -230,6 +231,7 @@ __global__ void __launch_bounds__(128, BWB_LANE_MIN_BLOCKS) k_search_l(const __g
 
     const uint32_t lane_slot = blockIdx.x * blockDim.x + threadIdx.x;
     const T lastrow = (T)(a.ix.length - 1);
+    const bool multiref = a.is_multiref != 0;
     LaneAlloc al;
     al.priv_lo = lane_slot * a.slots_per_lane;
     al.priv_hi = al.priv_lo + a.slots_per_lane;
@@ -569,8 +571,8 @@ __global__ void __launch_bounds__(128, BWB_LANE_MIN_BLOCKS) k_search_l(const __g
                 const T Cj = sC[j], Cj1 = sC[j + 1];
                 T Lj, Uj;
                 if (quirk) {
-                    const T qL = task_tail ? (T)vL : (T)0 - (T)(l0 & 1u);
-                    const T qU = task_tail ? (T)vU : (T)0 - (T)(u0 & 1u);
+                    const T qL = (task_tail || !multiref) ? (T)vL : (T)0 - (T)(l0 & 1u);
+                    const T qU = (task_tail || !multiref) ? (T)vU : (T)0 - (T)(u0 & 1u);
                     Lj = (T)(Cj + (negL ? (T)0 : qL) + 1);
                     Uj = topU ? Cj1 : (T)(Cj + qU);
                 } else {
@@ -581,14 +583,21 @@ __global__ void __launch_bounds__(128, BWB_LANE_MIN_BLOCKS) k_search_l(const __g
                 sUj[j][threadIdx.x] = Uj;
                 okmask |= (Lj <= Uj) ? (1u << j) : 0u;
             }
-            // codes whose base set contains the read base, N excluded = nucl_bases_table[c] (io.h:102-106)
-            const uint32_t compat_set = cbase == 0 ? 0xFB00u : (cbase == 1 ? 0x383Cu : (cbase == 2 ? 0x0BF0u : (cbase == 3 ? 0x6266u : 0u)));
+            // Child index space t: multi-genome t = code (1..15, the reference's loop order);
+            // single-genome (-S) t = 0..3 = A,G,C,T = codes 15,3,7,1 (O_actg_alphabet's order, bwt.c:440-463).
+            // compat_set = indices that MATCH the read base: nucl_bases_table[c] (io.h:102-106, N excluded)
+            // resp. the base itself (inexact_match.c:476).
+            if (!multiref)
+                okmask = ((okmask >> 15) & 1u) | (((okmask >> 3) & 1u) << 1) | (((okmask >> 7) & 1u) << 2) | (((okmask >> 1) & 1u) << 3);
+            const uint32_t compat_set = !multiref ? (cbase < 4u ? (1u << cbase) : 0u)
+                : (cbase == 0 ? 0xFB00u : (cbase == 1 ? 0x383Cu : (cbase == 2 ? 0x0BF0u : (cbase == 3 ? 0x6266u : 0u))));
+#define BWB_CODE_OF(t) (multiref ? (int)(t) : (int)((0x173Fu >> (4 * (t))) & 15u))
             bool ok_all = true;
             if (task_tail) {
                 // ---- (2a) exact tail: ordered append with adjacent merge (align.c:93-110)
                 uint32_t m = okmask & compat_set;
                 while (m) {
-                    const int j = __ffs(m) - 1;
+                    const int j = BWB_CODE_OF(__ffs(m) - 1);
                     m &= m - 1;
                     const T Lj = sLj[j][threadIdx.x], Uj = sUj[j][threadIdx.x];
                     nx_w += (uint32_t)(Uj - Lj + 1);
@@ -616,7 +625,7 @@ __global__ void __launch_bounds__(128, BWB_LANE_MIN_BLOCKS) k_search_l(const __g
                     const int jk = 31 - __clz(cand);
                     mmk &= ~(1u << jk);
                     have_next = true;
-                    nx.L = sLj[jk][threadIdx.x]; nx.U = sUj[jk][threadIdx.x];
+                    nx.L = sLj[BWB_CODE_OF(jk)][threadIdx.x]; nx.U = sUj[BWB_CODE_OF(jk)][threadIdx.x];
                     nx.z = zm + (((compat_set >> jk) & 1u) ? 0u : 0x100u);
                     nx.w = e.w; nx.r1 = e.r1; nx.r2 = e.r2; nx.r3 = e.r3;
                     nx_bucket = b0;
@@ -629,16 +638,18 @@ __global__ void __launch_bounds__(128, BWB_LANE_MIN_BLOCKS) k_search_l(const __g
                 while (md | mmk) {
                     const bool isdel = md != 0u;
                     const uint32_t cm = isdel ? md : mmk;
-                    const int j = __ffs(cm) - 1;
+                    const int t = __ffs(cm) - 1;
+                    const int j = BWB_CODE_OF(t);
                     if (isdel) md &= md - 1; else mmk &= mmk - 1;
                     const T Lj = sLj[j][threadIdx.x], Uj = sUj[j][threadIdx.x];
-                    const bool is_mm = !((compat_set >> j) & 1u);
+                    const bool is_mm = !((compat_set >> t) & 1u);
                     const int sc = isdel ? b2 : (is_mm ? b1 : b0);
                     const uint32_t cz = isdel ? (zg | (2u << 28)) : (zm + (is_mm ? 0x100u : 0u));
                     ok_all &= h.push(al, a, lane_slot, sc, Lj, Uj, cz, isdel ? wD : e.w, isdel ? r1D : e.r1,
                                      isdel ? r2D : e.r2, isdel ? r3D : e.r3);
                 }
             }
+#undef BWB_CODE_OF
             if (!ok_all) { err = BWB_ERR_CAPACITY; mode = FLUSH; }
         }
 

@@ -32,7 +32,7 @@ typedef enum {
     BWB_ERR_IO = -3,           /* file could not be read / written */
     BWB_ERR_NO_INDEX = -4,     /* bwb_align before bwb_index_upload */
     BWB_ERR_CAPACITY = -5,     /* a device pool (heap chunks, interval lists, hits) overflowed */
-    BWB_ERR_UNSUPPORTED = -6   /* feature of the reference not built yet (-P, -S on device) */
+    BWB_ERR_UNSUPPORTED = -6   /* feature of the reference not built yet (-P; max_gapo > 4; > 128 score buckets) */
 } bwb_status;
 
 /* Mirror of aln_params_t (mg-aligner/align.h:48-79): the same 15 ints in the same order, so a
@@ -51,7 +51,7 @@ typedef struct {
     int32_t no_indel_length;
     int32_t matched_Ncontig;  /* unused by the reference's hot path */
     int32_t use_precalc;      /* -P: BWB_ERR_UNSUPPORTED */
-    int32_t is_multiref;      /* 0 = -S: BWB_ERR_UNSUPPORTED on device */
+    int32_t is_multiref;      /* 0 = -S single-genome mode */
     int32_t n_threads;        /* -t: ignored by the device path */
 } bwb_params;
 

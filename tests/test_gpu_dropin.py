@@ -33,3 +33,14 @@ def test_dropin_cli_writes_the_reference_aln_and_sam(tmp_path, tag):
         n = flags[flags.index("-n") + 1]
         subprocess.run([REF_BIN, "aln2sam", "-n", n, fa, fq, aln, sam], check=True, stdout=subprocess.DEVNULL, timeout=600)
         assert open(sam, "rb").read() == G.golden_bytes("sam_%s.sam" % tag)
+
+
+def test_dropin_single_genome_mode_equals_reference_binary(tmp_path):
+    """-S through the drop-in CLI against the reference binary run on the same files."""
+    fa = G.materialise_index(tmp_path)
+    fq = os.path.join(G.GOLDEN, "r.fq")
+    a, b = str(tmp_path / "gpu.aln"), str(tmp_path / "ref.aln")
+    for binary, out in ((GPU_BIN, a), (REF_BIN, b)):
+        r = subprocess.run([binary, "align", "-S", "-n", "3", fa, fq, out], capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stdout[-1500:]
+    assert open(a, "rb").read() == open(b, "rb").read()

@@ -258,9 +258,9 @@ def test_resident_path_equals_host_path(gpu_case):
 def test_unsupported_params_fail_loudly(gpu_case):
     from bwbble_b200 import BwbError
     al, reads = gpu_case["al"], gpu_case["reads"]
-    for kw in (dict(use_precalc=1), dict(is_multiref=0), dict(o=9)):
+    for kw in (dict(n=2, use_precalc=1), dict(n=2, o=9), dict(n=140, M=9)):
         with pytest.raises(BwbError):
-            al.align(reads.seq, reads.offsets, default_params(n=2, **kw))
+            al.align(reads.seq, reads.offsets, default_params(**kw))
 
 
 def test_gpu_reproduces_the_reference_golden_files(tmp_path):
@@ -278,3 +278,25 @@ def test_gpu_reproduces_the_reference_golden_files(tmp_path):
             got = al.align(reads.seq, reads.offsets, default_params(**kw)).aln_bytes()
             exp = G.golden_bytes("aln_%s.aln" % tag)
             assert got == exp, "%s: %s" % (tag, first_difference(got, exp))
+
+
+@pytest.mark.parametrize("kw", [dict(n=0), dict(n=2), dict(n=4), dict(n=3, o=2, e=3, l=20, k=3), dict(n=4, M=0, m=3000)],
+                         ids=lambda k: "-".join("%s%d" % kv for kv in k.items()))
+def test_single_genome_mode_S(small_case, kw):
+    """-S (is_multiref = 0): 4-code fan-out A,G,C,T (O_actg_alphabet bwt.c:440-463, exact_match_1to1_bounded
+    exact_match.c:196-222, the !is_multiref branches of inexact_match.c) -- SURVEY 8f row 3."""
+    reads = small_case["reads"]
+    p = default_params(is_multiref=0, **kw)
+    orc = oracle.Oracle(small_case["bwt"])
+    exp, st = orc.align(reads.seq, reads.offsets, p)
+    orc.close()
+    for wide in (0, 1):
+        with Aligner(heap_pool_mb=512) as al:
+            if wide:
+                al.set_option("force_wide", 1)
+            al.load_index(small_case["bwt"])
+            res = al.align(reads.seq, reads.offsets, p)
+            got = res.aln_bytes()
+            assert got == exp, first_difference(got, exp)
+            ctr = res.counters()
+            assert ctr["pops"] == st["pops"] and ctr["pushes"] == st["pushes"] and ctr["exact_tails"] == st["exact_tail_calls"]
