@@ -102,6 +102,28 @@ class AlignResult:
         finally:
             _lib.lib().bwb_free(buf)
 
+    def locations(self) -> np.ndarray:
+        """K6 output per read: ref_pos (SA of hit 0's L; 2^64-1 if unmapped), top1, top2."""
+        dt = np.dtype([("ref_pos", "<u8"), ("top1", "<i4"), ("top2", "<i4")])
+        p = _lib.lib().bwb_results_locations(self._h)
+        n = self.num_reads
+        if not p:
+            raise _lib.BwbError(-4, "no sampled SA uploaded (Aligner.load_index(..., with_sa=True))")
+        return np.frombuffer(C.string_at(p, n * dt.itemsize), dtype=dt).copy()
+
+    def write_sam(self, sam_path: str, ann_path: str, names, seq, offsets, quals=None, max_mm: int = 6,
+                  header: bool = True, append: bool = False):
+        """`bwbble aln2sam -n max_mm` for these reads (align.c:494-652)."""
+        seq, offsets = _u8(seq), _u64(offsets)
+        n = len(offsets) - 1
+        nm = (C.c_char_p * n)(*[x.encode() for x in names])
+        ql = None
+        if quals is not None:
+            ql = (C.c_char_p * n)(*[x.encode() for x in quals])
+        _lib.check(_lib.lib().bwb_results_write_sam(self._h, os.fsencode(ann_path), nm, seq.ctypes.data, offsets.ctypes.data,
+                                                    ql, self._a.index.length, int(max_mm), os.fsencode(sam_path),
+                                                    int(header), int(append)), self._a._ctx)
+
     def write_aln(self, path: str, append: bool = False):
         _lib.check(_lib.lib().bwb_results_write_aln(self._h, os.fsencode(path), int(append)), self._a._ctx)
 
@@ -169,8 +191,13 @@ class Aligner:
                                                len(bwt), O.ctypes.data, len(O) // 16), self._ctx)
         self.index = ix
 
-    def load_index(self, bwt_path: str):
-        self.upload_index(load_bwt(bwt_path))
+    def load_index(self, bwt_path: str, with_sa: bool = False):
+        """load_bwt(path, loadSA) (bwt.c:90-125); with_sa also uploads the sampled SA, enabling K6."""
+        ix = load_bwt(bwt_path, load_sa=with_sa)
+        self.upload_index(ix)
+        if with_sa:
+            sa = _u64(ix.SA)
+            _lib.check(_lib.lib().bwb_sa_upload(self._ctx, sa.ctypes.data, len(sa)), self._ctx)
 
     def download_blocks(self) -> np.ndarray:
         n = int(_lib.lib().bwb_index_num_blocks(self._ctx))
@@ -290,4 +317,19 @@ def align_reads(fasta_path: str, fastq_path: str, aln_path: str, params: Optiona
             res = al.align(sub.seq, sub.offsets, params)
             res.write_aln(aln_path, append=True)
             res.close()
+    return reads.n
+
+
+def alns2sam(fasta_path: str, fastq_path: str, sam_path: str, params: Optional[Params] = None, max_mm: int = 6,
+             devices: Optional[Sequence[int]] = None) -> int:
+    """`bwbble align` + `bwbble aln2sam -n max_mm` in one go, SAM straight from the device results
+    (alns2sam, align.c:494-556, without the .aln round trip)."""
+    from .fastx import read_fastq
+    params = params or default_params()
+    reads = read_fastq(fastq_path, with_quals=True)
+    with Aligner(devices) as al:
+        al.load_index(fasta_path + ".bwt", with_sa=True)
+        res = al.align(reads.seq, reads.offsets, params)
+        res.write_sam(sam_path, fasta_path + ".ann", reads.names, reads.seq, reads.offsets, reads.meta["quals"], max_mm)
+        res.close()
     return reads.n

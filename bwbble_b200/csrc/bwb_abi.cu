@@ -38,6 +38,7 @@ struct Device {
     int sm_count = 0;
     // index
     uint4 *blocks = nullptr;
+    uint64_t *sa = nullptr;   // sampled suffix array (optional: enables K6)
     // search scratch (sized for n_warps)
     int n_warps = 0, grid = 0, wpb = 0, grid3 = 0;
     size_t smem_bytes = 0;
@@ -46,6 +47,7 @@ struct Device {
     // per-call buffers
     DevBuf seq, offsets, read_off, read_cnt, ordered_off, unordered, ordered, cub_tmp, small, d_main, d_seed, pool;
     DevBuf pk_main, pk_seed, n_count, nxt, blk_link, heads;      // lane engine
+    DevBuf loc;                                                  // K6 output
     uint32_t slots_per_lane = 0, total_slots = 0, priv_total = 0;
     uint64_t auto_pool_bytes = 0;
     int engine = -1;          // engine the scratch was sized for
@@ -61,6 +63,8 @@ struct bwb_ctx {
     std::string err;
     // index meta
     bool have_index = false;
+    bool have_sa = false;
+    uint64_t num_sa = 0;
     uint64_t length = 0, num_blocks = 0, sa0 = 0;
     uint64_t C[17] = {0};
     // options
@@ -88,6 +92,8 @@ struct bwb_results {
     uint64_t n_reads = 0;
     std::vector<uint32_t> counts;
     std::vector<bwb_hit> hits;
+    std::vector<bwb_loc> loc;
+    bool have_loc = false;
     uint64_t counters[8] = {0};
     float kernel_ms = 0.f;    // K4 duration (max over devices), CUDA events on the launch stream
     float k3_ms = 0.f;        // K3 duration (engines with a separate lower-bound kernel)
@@ -398,8 +404,9 @@ void bwb_destroy(bwb_ctx *ctx) {
         cudaSetDevice(d.id);
         cudaDeviceSynchronize();
         if (d.blocks) cudaFree(d.blocks);
+        if (d.sa) cudaFree(d.sa);
         DevBuf *bufs[] = {&d.glists, &d.chunks, &d.chunk_link, &d.stage, &d.seq, &d.offsets, &d.read_off, &d.read_cnt,
-                          &d.ordered_off, &d.unordered, &d.ordered, &d.cub_tmp, &d.small, &d.d_main, &d.d_seed, &d.pool, &d.pk_main, &d.pk_seed, &d.n_count, &d.nxt, &d.blk_link, &d.heads};
+                          &d.ordered_off, &d.unordered, &d.ordered, &d.cub_tmp, &d.small, &d.d_main, &d.d_seed, &d.pool, &d.loc, &d.pk_main, &d.pk_seed, &d.n_count, &d.nxt, &d.blk_link, &d.heads};
         for (DevBuf *b : bufs) release(*b);
         if (d.h_small) cudaFreeHost(d.h_small);
         if (d.ev0) cudaEventDestroy(d.ev0);
@@ -449,6 +456,7 @@ int bwb_index_upload(bwb_ctx *ctx, uint64_t length, uint64_t sa0_index, const ui
         return fail(ctx, BWB_ERR_ARG, "bwb_index_upload: arrays shorter than length implies");
     if (length >= (1ull << 40)) return fail(ctx, BWB_ERR_ARG, "index longer than 2^40 rows");
     ctx->length = length;
+    ctx->have_sa = false;
     ctx->sa0 = sa0_index;
     ctx->num_blocks = (length + 127) / 128;
     memcpy(ctx->C, C, sizeof ctx->C);
@@ -484,6 +492,31 @@ int bwb_index_load_file(bwb_ctx *ctx, const char *bwt_path) {
     bwb_host::HostIndex ix;
     if (bwb_host::read_bwt_file(bwt_path, ix, false)) return fail(ctx, BWB_ERR_IO, "cannot read %s", bwt_path);
     return bwb_index_upload(ctx, ix.length, ix.sa0_index, ix.C, ix.bwt.data(), ix.num_words, ix.O.data(), ix.num_occ);
+}
+
+int bwb_sa_upload(bwb_ctx *ctx, const uint64_t *SA, uint64_t num_sa) {
+    if (!ctx || !SA) return BWB_ERR_ARG;
+    if (!ctx->have_index) return fail(ctx, BWB_ERR_NO_INDEX, "bwb_sa_upload before bwb_index_upload");
+    if (num_sa < (ctx->length + 31) / 32) return fail(ctx, BWB_ERR_ARG, "sampled SA shorter than ceil(length/32)");
+    for (auto &d : ctx->dev) {
+        CU(cudaSetDevice(d.id));
+        if (d.sa) { CU(cudaFree(d.sa)); d.sa = nullptr; }
+        CU(cudaMalloc(&d.sa, num_sa * 8));
+        CU(cudaMemcpyAsync(d.sa, SA, num_sa * 8, cudaMemcpyHostToDevice, d.stream));
+        CU(cudaStreamSynchronize(d.stream));
+    }
+    ctx->num_sa = num_sa;
+    ctx->have_sa = true;
+    return BWB_OK;
+}
+
+int bwb_index_load_file_sa(bwb_ctx *ctx, const char *bwt_path) {
+    if (!ctx || !bwt_path) return BWB_ERR_ARG;
+    bwb_host::HostIndex ix;
+    if (bwb_host::read_bwt_file(bwt_path, ix, true)) return fail(ctx, BWB_ERR_IO, "cannot read %s (with SA)", bwt_path);
+    int rc = bwb_index_upload(ctx, ix.length, ix.sa0_index, ix.C, ix.bwt.data(), ix.num_words, ix.O.data(), ix.num_occ);
+    if (rc) return rc;
+    return bwb_sa_upload(ctx, ix.SA.data(), ix.num_sa);
 }
 
 uint64_t bwb_index_num_blocks(const bwb_ctx *ctx) { return ctx && ctx->have_index ? ctx->num_blocks : 0; }
@@ -944,6 +977,12 @@ static int launch_shard(bwb_ctx *ctx, Device &d, const bwb_params *p, int nb, co
         k_emit<<<(unsigned)((n + 127) / 128), 128, 0, d.stream>>>((const bwb_hit *)d.unordered.p, a.read_off, cnt, ooff,
                                                               (uint32_t)n, (bwb_hit *)d.ordered.p);
         CU(cudaGetLastError());
+        if (ctx->have_sa) {                          // K6: locate + top1/top2 (aln2sam's eval_aln)
+            if ((rc = ensure(ctx, d.loc, n * sizeof(bwb_loc)))) return rc;
+            k_locate<<<(unsigned)((n + 127) / 128), 128, 0, d.stream>>>(a.ix, ctx->sa0, d.sa, (const bwb_hit *)d.ordered.p, ooff,
+                                                                    cnt, (uint32_t)n, (bwb_loc *)d.loc.p);
+            CU(cudaGetLastError());
+        }
     }
     return BWB_OK;
 }
@@ -960,6 +999,7 @@ static int align_impl(bwb_ctx *ctx, const bwb_params *p, const bwb_reads *R, bwb
     bwb_results *res = new bwb_results();
     res->ctx = ctx; res->n_reads = R->n_reads; res->shard_lo = R->shard_lo; res->shard_total.assign(G, 0);
     res->counts.assign(R->n_reads, 0);
+    res->have_loc = ctx->have_sa;
 
     std::vector<unsigned long long> cap(G);
     for (int g = 0; g < G; g++) {
@@ -1025,6 +1065,7 @@ int bwb_results_fetch(bwb_results *r) {
     uint64_t total = 0;
     for (int g = 0; g < G; g++) total += r->shard_total[g];
     r->hits.resize(total);
+    if (r->have_loc) r->loc.resize(r->n_reads);
     uint64_t w = 0;
     for (int g = 0; g < G; g++) {
         Device &d = ctx->dev[g];
@@ -1033,6 +1074,7 @@ int bwb_results_fetch(bwb_results *r) {
         if (n) CU(cudaMemcpyAsync(r->counts.data() + lo, d.read_cnt.p, n * 4, cudaMemcpyDeviceToHost, d.stream));
         if (r->shard_total[g])
             CU(cudaMemcpyAsync(r->hits.data() + w, d.ordered.p, r->shard_total[g] * sizeof(bwb_hit), cudaMemcpyDeviceToHost, d.stream));
+        if (r->have_loc && n) CU(cudaMemcpyAsync(r->loc.data() + lo, d.loc.p, n * sizeof(bwb_loc), cudaMemcpyDeviceToHost, d.stream));
         w += r->shard_total[g];
     }
     for (int g = 0; g < G; g++) {
@@ -1075,6 +1117,7 @@ uint64_t bwb_results_num_hits(const bwb_results *r) {
 }
 const uint32_t *bwb_results_counts(const bwb_results *r) { return r && r->fetched ? r->counts.data() : nullptr; }
 const bwb_hit *bwb_results_hits(const bwb_results *r) { return r && r->fetched ? r->hits.data() : nullptr; }
+const bwb_loc *bwb_results_locations(const bwb_results *r) { return r && r->fetched && r->have_loc ? r->loc.data() : nullptr; }
 int bwb_results_counters(const bwb_results *r, uint64_t out[8]) {
     if (!r || !out) return BWB_ERR_ARG;
     memcpy(out, r->counters, sizeof r->counters);
@@ -1092,4 +1135,5 @@ namespace bwb_host {
 const std::vector<uint32_t> &results_counts(const bwb_results *r) { return r->counts; }
 const std::vector<bwb_hit> &results_hits(const bwb_results *r) { return r->hits; }
 bool results_fetched(const bwb_results *r) { return r->fetched; }
+const std::vector<bwb_loc> *results_loc(const bwb_results *r) { return r->have_loc ? &r->loc : nullptr; }
 }  // namespace bwb_host

@@ -884,4 +884,52 @@ __global__ void k_emit(const bwb_hit *__restrict__ unordered, const unsigned lon
     for (uint32_t k = 0; k < n * 3; k++) dst[k] = src[k];
 }
 
+// ---------------------------------------------------------------------------------------------
+// K6: SA locate of every read's first hit + the top1/top2 sums of eval_aln (align.c:760-812)
+// ---------------------------------------------------------------------------------------------
+// invPsi(i) = C[B(i)] + O(B(i), i), 0 for the sentinel row (bwt.c:311-317); O(0, i) does not count
+// the sentinel row although it stores nibble 0 (bwt.c:362-370).
+__device__ __forceinline__ uint64_t inv_psi(const IndexView &ix, uint64_t sa0, uint64_t i) {
+    if (i == sa0) return 0;
+    const uint4 *blk = ix.blocks + (i >> 7) * 8;
+    const uint32_t p = (uint32_t)(i & 127u);
+    const uint32_t *pw = reinterpret_cast<const uint32_t *>(blk) + 16 + (p >> 5);
+    uint32_t c = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) c |= ((__ldg(pw + 4 * k) >> (p & 31u)) & 1u) << k;
+    uint64_t o;
+    if (i == ix.length - 1) {
+        o = ix.C[c + 1] - ix.C[c];
+    } else {
+        const BlockBits b = load_block(blk, c);
+        o = rank_in_block(b, p);
+        if (c == 0 && (sa0 >> 7) == (i >> 7) && (sa0 & 127u) <= p) o -= 1;
+    }
+    return ix.C[c] + o;
+}
+
+__global__ void k_locate(IndexView ix, uint64_t sa0, const uint64_t *__restrict__ SA, const bwb_hit *__restrict__ hits,
+                         const unsigned long long *__restrict__ off, const uint32_t *__restrict__ cnt, uint32_t n_reads,
+                         bwb_loc *__restrict__ out) {
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_reads) return;
+    bwb_loc loc;
+    loc.ref_pos = ~0ull; loc.top1 = 0; loc.top2 = 0;
+    const uint32_t n = cnt[r];
+    if (n) {
+        const bwb_hit *h = hits + off[r];
+        const int best = h[0].score;
+        uint32_t t1 = 0, t2 = 0;
+        for (uint32_t k = 0; k < n; k++) {
+            const uint32_t w = (uint32_t)(h[k].U - h[k].L + 1);
+            if (h[k].score > best) t2 += w; else t1 += w;
+        }
+        uint64_t i = h[0].L, j = 0;
+        while (i & 31u) { i = inv_psi(ix, sa0, i); j++; }          // SA(), bwt.c:320-329
+        loc.ref_pos = (SA[i >> 5] + j) % ix.length;
+        loc.top1 = (int32_t)t1; loc.top2 = (int32_t)t2;
+    }
+    out[r] = loc;
+}
+
 }  // namespace bwb

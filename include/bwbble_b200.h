@@ -109,8 +109,10 @@ int bwb_set_stream(bwb_ctx *ctx, int dev_slot, void *cuda_stream);
  * Re-laid-out on the device into 128-byte blocks (K0).  Host arrays are not referenced afterwards. */
 int bwb_index_upload(bwb_ctx *ctx, uint64_t length, uint64_t sa0_index, const uint64_t C[17],
                      const uint32_t *bwt, uint64_t num_words, const uint64_t *O, uint64_t num_occ);
-/* Read "<path>" in store_bwt's layout (bwt.c:66-82) and upload it. */
+/* Read "<path>" in store_bwt's layout (bwt.c:66-82) and upload it (without the sampled SA). */
 int bwb_index_load_file(bwb_ctx *ctx, const char *bwt_path);
+/* Same, and upload the sampled SA stored at the end of the file as well (load_bwt(path, 1)). */
+int bwb_index_load_file_sa(bwb_ctx *ctx, const char *bwt_path);
 /* Download the device blocks of device slot 0 (tests): out must hold bwb_index_num_blocks()*128 bytes. */
 uint64_t bwb_index_num_blocks(const bwb_ctx *ctx);
 int bwb_index_download_blocks(bwb_ctx *ctx, void *out);
@@ -180,6 +182,25 @@ int bwb_results_aln_bytes(const bwb_results *r, uint8_t **buf, uint64_t *len);  
 int bwb_results_write_aln(const bwb_results *r, const char *path, int append);
 void bwb_results_free(bwb_results *r);
 void bwb_free(void *p);
+
+/* ---- SA locate + SAM (the step right after the path; bwbble aln2sam) ------------ */
+/* Sampled suffix array of the index (every 32nd value, bwt.h:16,34; the tail of the .bwt file).  Once
+ * uploaded, every bwb_align call also runs K6: per read the text position of its first hit,
+ * SA(L) = (SA[i/32] + j) mod length after j applications of invPsi (bwt.c:311-329), and the
+ * aln_top1_count / aln_top2_count sums of eval_aln (align.c:760-812). */
+int bwb_sa_upload(bwb_ctx *ctx, const uint64_t *SA, uint64_t num_sa);
+typedef struct {
+    uint64_t ref_pos;          /* SA(L of hit 0); ~0 for a read without hits */
+    int32_t top1, top2;        /* wrapped int sums of interval widths: score <= best / score > best */
+} bwb_loc;
+const bwb_loc *bwb_results_locations(const bwb_results *r);     /* NULL if no SA was uploaded */
+/* Write what `bwbble aln2sam -n max_mm` writes for these reads (alns2sam, align.c:494-652): @SQ/@PG
+ * header (if write_header), one line per read; strand/POS from the located position, MAPQ by mapq()
+ * (align.c:738-746), CIGAR from the edit path.  ann_path = <fasta>.ann; names/quals = n_reads C strings
+ * (quals may be NULL), seq/offsets as given to bwb_align. */
+int bwb_results_write_sam(const bwb_results *r, const char *ann_path, const char *const *names, const uint8_t *seq,
+                          const uint64_t *offsets, const char *const *quals, uint64_t index_length, int max_mm,
+                          const char *sam_path, int write_header, int append);
 
 /* ---- host-side index construction (bwbble index, bwt.c:29-63; SURVEY 8f "next") ----------- */
 /* Builds <fasta>.bwt and <fasta>.ann byte-identical to the reference's `bwbble index <fasta>`

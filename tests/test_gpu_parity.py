@@ -300,3 +300,31 @@ def test_single_genome_mode_S(small_case, kw):
             assert got == exp, first_difference(got, exp)
             ctr = res.counters()
             assert ctr["pops"] == st["pops"] and ctr["pushes"] == st["pushes"] and ctr["exact_tails"] == st["exact_tail_calls"]
+
+
+@pytest.mark.parametrize("tag", ["n0", "n3", "n4_o2_e3_k3_l20"])
+def test_device_locate_and_sam_equal_reference_aln2sam(tmp_path, tag):
+    """K6 (SA locate + top1/top2) + the host SAM writer reproduce, byte for byte, the SAM file
+    the reference's `aln2sam -n <n>` wrote for the same reads (tests/golden/sam_*.sam)."""
+    import golden_util as G
+    from bwbble_b200.fastx import read_fastq
+    import os
+    fa = G.materialise_index(tmp_path)
+    reads = read_fastq(os.path.join(G.GOLDEN, "r.fq"), with_quals=True)
+    kw = G.flags_to_kwargs(G.grid()[tag])
+    p = default_params(**kw)
+    for wide in (0, 1):
+        with Aligner(heap_pool_mb=512) as al:
+            if wide:
+                al.set_option("force_wide", 1)
+            al.load_index(fa + ".bwt", with_sa=True)
+            res = al.align(reads.seq, reads.offsets, p)
+            sam = str(tmp_path / ("out%d.sam" % wide))
+            res.write_sam(sam, fa + ".ann", reads.names, reads.seq, reads.offsets, reads.meta["quals"], max_mm=kw["max_diff"])
+            got, exp = open(sam, "rb").read(), G.golden_bytes("sam_%s.sam" % tag)
+            if got != exp:
+                gl, el = got.split(b"\n"), exp.split(b"\n")
+                bad = [i for i in range(min(len(gl), len(el))) if gl[i] != el[i]][:3]
+                raise AssertionError("SAM differs at lines %s:\n got %s\n exp %s" % (bad, [gl[i] for i in bad], [el[i] for i in bad]))
+            loc = res.locations()
+            assert ((loc["ref_pos"] == np.uint64(2**64 - 1)) == (res.counts() == 0)).all()
