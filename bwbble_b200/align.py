@@ -301,23 +301,21 @@ class Aligner:
 
 
 def align_reads(fasta_path: str, fastq_path: str, aln_path: str, params: Optional[Params] = None,
-                devices: Optional[Sequence[int]] = None, batch: int = 0x40000 * 4) -> int:
-    """`bwbble align` (align_reads, align.c:40-87): loads <fasta>.bwt, maps every read of the FASTQ
-    and writes the binary .aln file, in batches (READ_BATCH_SIZE x 4 reads by default)."""
-    from .fastx import read_fastq
+                devices: Optional[Sequence[int]] = None, batch: int = 0, sam_path: Optional[str] = None,
+                max_mm: int = 6) -> int:
+    """`bwbble align` (align_reads, align.c:40-87): loads <fasta>.bwt, streams the FASTQ through the native
+    batch reader (fastq_stream.cpp) and writes the binary .aln file -- and, if sam_path is given, the
+    SAM file `bwbble aln2sam -n max_mm` would write -- without holding all reads in memory."""
     params = params or default_params()
-    if os.path.exists(aln_path):
-        os.remove(aln_path)                       # align.c:48
-    reads = read_fastq(fastq_path)
     with Aligner(devices) as al:
-        al.load_index(fasta_path + ".bwt")
-        open(aln_path, "wb").close()
-        for lo in range(0, reads.n, batch):
-            sub = reads.slice(lo, min(reads.n, lo + batch))
-            res = al.align(sub.seq, sub.offsets, params)
-            res.write_aln(aln_path, append=True)
-            res.close()
-    return reads.n
+        al.load_index(fasta_path + ".bwt", with_sa=sam_path is not None)
+        n = _lib.lib().bwb_align_fastq(al._ctx, C.byref(params), os.fsencode(fastq_path), os.fsencode(aln_path),
+                                       os.fsencode(sam_path) if sam_path else None,
+                                       os.fsencode(fasta_path + ".ann") if sam_path else None,
+                                       al.index.length, int(max_mm), int(batch))
+        if n < 0:
+            _lib.check(int(n), al._ctx)
+    return int(n)
 
 
 def alns2sam(fasta_path: str, fastq_path: str, sam_path: str, params: Optional[Params] = None, max_mm: int = 6,

@@ -202,6 +202,15 @@ int bwb_results_write_sam(const bwb_results *r, const char *ann_path, const char
                           const uint64_t *offsets, const char *const *quals, uint64_t index_length, int max_mm,
                           const char *sam_path, int write_header, int append);
 
+/* ---- streaming ingest (replaces the all-resident fastq2reads, io.c:410-515) ------- */
+/* Parse `fastq_path` in batches of `batch_reads` (0 = 4 Mi) reads, align every batch and append its
+ * records to `aln_path` (binary .aln, removed first like align.c:48) and/or `sam_path` (needs the
+ * sampled SA uploaded, `ann_path` = <fasta>.ann, index_length, max_mm as for bwb_results_write_sam).
+ * Returns the number of reads, or a negative bwb_status. */
+long long bwb_align_fastq(bwb_ctx *ctx, const bwb_params *params, const char *fastq_path, const char *aln_path,
+                          const char *sam_path, const char *ann_path, uint64_t index_length, int max_mm,
+                          uint64_t batch_reads);
+
 /* ---- host-side index construction (bwbble index, bwt.c:29-63; SURVEY 8f "next") ----------- */
 /* Builds <fasta>.bwt and <fasta>.ann byte-identical to the reference's `bwbble index <fasta>`
  * (io.c:190-321 fasta2ref, bwt.c:161-218 construct_bwt, is.c:214-243) with an own SA-IS. */

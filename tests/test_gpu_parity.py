@@ -328,3 +328,17 @@ def test_device_locate_and_sam_equal_reference_aln2sam(tmp_path, tag):
                 raise AssertionError("SAM differs at lines %s:\n got %s\n exp %s" % (bad, [gl[i] for i in bad], [el[i] for i in bad]))
             loc = res.locations()
             assert ((loc["ref_pos"] == np.uint64(2**64 - 1)) == (res.counts() == 0)).all()
+
+
+@pytest.mark.parametrize("batch", [0, 37])
+def test_streaming_fastq_ingest_writes_reference_aln_and_sam(tmp_path, batch):
+    """native batched FASTQ reader -> align -> append; any batch size gives the reference's files."""
+    import golden_util as G
+    from bwbble_b200 import align_reads
+    import os
+    fa = G.materialise_index(tmp_path)
+    aln, sam = str(tmp_path / "o.aln"), str(tmp_path / "o.sam")
+    n = align_reads(fa, os.path.join(G.GOLDEN, "r.fq"), aln, default_params(n=3), batch=batch, sam_path=sam, max_mm=3)
+    assert n == 200
+    assert open(aln, "rb").read() == G.golden_bytes("aln_n3.aln")
+    assert open(sam, "rb").read() == G.golden_bytes("sam_n3.sam")
