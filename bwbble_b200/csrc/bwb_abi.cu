@@ -39,6 +39,10 @@ struct Device {
     // index
     uint4 *blocks = nullptr;
     uint64_t *sa = nullptr;   // sampled suffix array (optional: enables K6)
+    // k-mer table of the top of the search tree (K0b)
+    unsigned long long *ktab_w = nullptr;
+    uint32_t *ktab_off = nullptr, *ktab_cnt = nullptr;
+    void *ktab_iv = nullptr;
     // search scratch (sized for n_warps)
     int n_warps = 0, grid = 0, wpb = 0, grid3 = 0;
     size_t smem_bytes = 0;
@@ -75,6 +79,7 @@ struct bwb_ctx {
     int blocks_per_sm = 0;
     int engine = 0;           // 0 = read per lane (k_calc_d_g + k_search_l), 1 = warp per read (k_align),
                               // 2 = 8-lane groups (k_calc_d_g + k_search_g); 1 and 2 are A/B baselines
+    int use_ktab = 1;         // k-mer table for calculate_d's top of tree (0 = off, for A/B and tests)
     int force_wide = 0;       // tests: run the 64-bit / 32-byte-entry kernels on a small index
 };
 
@@ -345,6 +350,62 @@ int prepare_search(bwb_ctx *ctx, Device &d, const SmemLayout &L, bool wide) {
     return BWB_OK;
 }
 
+// K0b: build the k-mer table on one device (after its blocks exist)
+int build_ktab(bwb_ctx *ctx, Device &d) {
+    CU(cudaSetDevice(d.id));
+    if (d.ktab_w) { cudaFree(d.ktab_w); cudaFree(d.ktab_off); cudaFree(d.ktab_cnt); cudaFree(d.ktab_iv); }
+    d.ktab_w = nullptr; d.ktab_off = d.ktab_cnt = nullptr; d.ktab_iv = nullptr;
+    const bool wide = index_is_wide(ctx);
+    const uint32_t nk = 1u << (2 * KTAB);
+    const size_t nw_entries = ktab_level_off(KTAB + 1);
+    const int wpb = 8, grid = d.sm_count * 2, n_warps = grid * wpb;
+    void *gl = nullptr;
+    unsigned char *sm = nullptr;
+    CU(cudaMalloc(&d.ktab_w, nw_entries * 8));
+    CU(cudaMalloc(&d.ktab_off, (size_t)nk * 4));
+    CU(cudaMalloc(&d.ktab_cnt, (size_t)nk * 4));
+    CU(cudaMalloc(&gl, (size_t)n_warps * 2 * ctx->list_cap * sizeof(ulonglong2)));
+    CU(cudaMalloc(&sm, 64));
+    unsigned long long cap = 8ull << 20;
+    const size_t pair = wide ? 16 : 8;
+    for (int attempt = 0; attempt < 6; attempt++) {
+        CU(cudaMalloc(&d.ktab_iv, cap * pair));
+        CU(cudaMemsetAsync(d.ktab_w, 0, nw_entries * 8, d.stream));
+        CU(cudaMemsetAsync(sm, 0, 64, d.stream));
+        KtabArgs a;
+        memset(&a, 0, sizeof a);
+        a.ix = make_view(ctx, d); a.glists = gl; a.list_cap = ctx->list_cap;
+        a.w = d.ktab_w; a.koff = d.ktab_off; a.kcnt = d.ktab_cnt; a.iv = d.ktab_iv; a.iv_cap = cap;
+        a.cursor = (unsigned long long *)sm; a.status = (uint32_t *)(sm + 8);
+        const size_t smem = (size_t)wpb * LIST_SMEM_BYTES;
+        if (wide) k_kmer_table<uint64_t><<<grid, wpb * 32, smem, d.stream>>>(a);
+        else k_kmer_table<uint32_t><<<grid, wpb * 32, smem, d.stream>>>(a);
+        CU(cudaGetLastError());
+        unsigned long long used = 0;
+        uint32_t st = 0;
+        CU(cudaMemcpyAsync(&used, sm, 8, cudaMemcpyDeviceToHost, d.stream));
+        CU(cudaMemcpyAsync(&st, sm + 8, 4, cudaMemcpyDeviceToHost, d.stream));
+        CU(cudaStreamSynchronize(d.stream));
+        if (st) {       // a top-of-tree list longer than list_cap: run without the table rather than fail
+            cudaFree(d.ktab_iv); cudaFree(d.ktab_w); cudaFree(d.ktab_off); cudaFree(d.ktab_cnt);
+            d.ktab_w = nullptr; d.ktab_off = d.ktab_cnt = nullptr; d.ktab_iv = nullptr;
+            break;
+        }
+        if (used <= cap) break;
+        CU(cudaFree(d.ktab_iv));
+        d.ktab_iv = nullptr;
+        cap = used + 1024;
+    }
+    cudaFree(gl); cudaFree(sm);
+    return BWB_OK;
+}
+
+void set_ktab(const bwb_ctx *ctx, const Device &d, CalcArgs &c) {
+    const bool on = ctx->use_ktab && d.ktab_w && d.ktab_iv;
+    c.ktab_w = on ? d.ktab_w : nullptr;
+    c.ktab_off = d.ktab_off; c.ktab_cnt = d.ktab_cnt; c.ktab_iv = d.ktab_iv;
+}
+
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------
@@ -405,6 +466,10 @@ void bwb_destroy(bwb_ctx *ctx) {
         cudaDeviceSynchronize();
         if (d.blocks) cudaFree(d.blocks);
         if (d.sa) cudaFree(d.sa);
+        if (d.ktab_w) cudaFree(d.ktab_w);
+        if (d.ktab_off) cudaFree(d.ktab_off);
+        if (d.ktab_cnt) cudaFree(d.ktab_cnt);
+        if (d.ktab_iv) cudaFree(d.ktab_iv);
         DevBuf *bufs[] = {&d.glists, &d.chunks, &d.chunk_link, &d.stage, &d.seq, &d.offsets, &d.read_off, &d.read_cnt,
                           &d.ordered_off, &d.unordered, &d.ordered, &d.cub_tmp, &d.small, &d.d_main, &d.d_seed, &d.pool, &d.loc, &d.pk_main, &d.pk_seed, &d.n_count, &d.nxt, &d.blk_link, &d.heads};
         for (DevBuf *b : bufs) release(*b);
@@ -422,7 +487,7 @@ int bwb_device_count(const bwb_ctx *ctx) { return ctx ? (int)ctx->dev.size() : 0
 int bwb_set_option(bwb_ctx *ctx, const char *key, long long value) {
     if (!ctx || !key) return BWB_ERR_ARG;
     std::string k(key);
-    if (value <= 0 && k != "blocks_per_sm" && k != "force_wide" && k != "engine" && k != "heap_pool_mb") return fail(ctx, BWB_ERR_ARG, "option %s needs a positive value", key);
+    if (value <= 0 && k != "blocks_per_sm" && k != "force_wide" && k != "engine" && k != "heap_pool_mb" && k != "kmer_table") return fail(ctx, BWB_ERR_ARG, "option %s needs a positive value", key);
     if (k == "heap_pool_mb") ctx->heap_pool_mb = value;
     else if (k == "list_cap") ctx->list_cap = (int)(value < SL + 4 ? SL + 4 : value);
     else if (k == "hits_per_read") ctx->hits_per_read = (int)value;
@@ -430,7 +495,13 @@ int bwb_set_option(bwb_ctx *ctx, const char *key, long long value) {
         if (value > 8) return fail(ctx, BWB_ERR_ARG, "warps_per_block must be 1..8");
         ctx->warps_per_block = (int)value;
     } else if (k == "blocks_per_sm") ctx->blocks_per_sm = (int)value;
-    else if (k == "force_wide") ctx->force_wide = value > 1 ? 0 : 1;
+    else if (k == "force_wide") {
+        const int nv = value > 1 ? 0 : 1;
+        if (nv != ctx->force_wide && ctx->have_index)
+            return fail(ctx, BWB_ERR_ARG, "force_wide must be set before the index is uploaded");
+        ctx->force_wide = nv;
+    }
+    else if (k == "kmer_table") ctx->use_ktab = value > 1 ? 0 : 1;
     else if (k == "engine") ctx->engine = (value == 1 || value == 2) ? (int)value : 0;
     else return fail(ctx, BWB_ERR_ARG, "unknown option %s", key);
     for (auto &d : ctx->dev) {       // scratch is re-sized lazily
@@ -484,6 +555,10 @@ int bwb_index_upload(bwb_ctx *ctx, uint64_t length, uint64_t sa0_index, const ui
         if (herr) return fail(ctx, BWB_ERR_ARG, "a per-code rank counter exceeds 2^32 (index too large for u32 checkpoints)");
     }
     ctx->have_index = true;
+    for (auto &d : ctx->dev) {
+        int rc = build_ktab(ctx, d);
+        if (rc) return rc;
+    }
     return BWB_OK;
 }
 
@@ -736,6 +811,7 @@ int bwb_lower_bounds(bwb_ctx *ctx, const uint8_t *seq, const uint64_t *offsets, 
     c.glists = gl; c.list_cap = ctx->list_cap; c.d_main = dm; c.d_seed = ds;
     c.status = (uint32_t *)(sm + 8); c.counters = (unsigned long long *)(sm + 32);
     c.smem_per_group = G_LIST_SMEM + ((max_len + 15) & ~15);
+    set_ktab(ctx, d, c);
     const size_t smem3 = (size_t)(256 / GL) * c.smem_per_group;
     if (wide) {
         CU(cudaFuncSetAttribute(k_calc_d_g<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
@@ -897,9 +973,12 @@ static int launch_shard(bwb_ctx *ctx, Device &d, const bwb_params *p, int nb, co
         c.pk_main = (uint16_t *)d.pk_main.p; c.pk_seed = (uint16_t *)d.pk_seed.p; c.n_count = (uint16_t *)d.n_count.p;
         c.status = a.status; c.counters = a.counters;
         c.smem_per_group = G_LIST_SMEM + ((max_len + 15) & ~15);
+        set_ktab(ctx, d, c);
         const size_t smem3 = (size_t)(256 / GL) * c.smem_per_group;
         const int grid3 = d.grid3;
-        if (wide) {
+        // K3's coordinate width follows the index alone (the k-mer table is typed by it); `wide` may also
+        // be set by max_gapo > 1, which only concerns K4's entry format
+        if (index_is_wide(ctx)) {
             CU(cudaFuncSetAttribute(k_calc_d_g<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
             k_calc_d_g<true><<<grid3, 256, smem3, d.stream>>>(c);
         } else {
@@ -938,8 +1017,9 @@ static int launch_shard(bwb_ctx *ctx, Device &d, const bwb_params *p, int nb, co
         c.d_main = (int2 *)d.d_main.p; c.d_seed = (int2 *)d.d_seed.p;
         c.status = a.status; c.counters = a.counters;
         c.smem_per_group = G_LIST_SMEM + ((max_len + 15) & ~15);
+        set_ktab(ctx, d, c);
         const size_t smem3 = (size_t)(256 / GL) * c.smem_per_group;
-        if (wide) {
+        if (index_is_wide(ctx)) {
             CU(cudaFuncSetAttribute(k_calc_d_g<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
             k_calc_d_g<true><<<d.grid, 256, smem3, d.stream>>>(c);
         } else {

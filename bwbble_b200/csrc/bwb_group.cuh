@@ -163,6 +163,10 @@ struct CalcArgs {
     uint32_t *status;
     unsigned long long *counters;   // [3] rank queries, [5] max list
     int smem_per_group;
+    // k-mer table of the top of the search tree (k_kmer_table); ktab_w == nullptr disables it
+    const unsigned long long *ktab_w;
+    const uint32_t *ktab_off, *ktab_cnt;
+    const void *ktab_iv;
 };
 
 template <bool WIDE>
@@ -195,6 +199,8 @@ __global__ void __launch_bounds__(256) k_calc_d_g(const __grid_constant__ CalcAr
     step_begin(st);
     uint32_t c = 0;
     bool in_step = false;
+    bool fresh = false;           // the current list is the full range (start of an array / after a restart)
+    const bool use_tab = a.ktab_w != nullptr && a.is_multiref != 0;
     uint32_t nloads = 0, maxlist = 0;
 
     for (;;) {
@@ -214,7 +220,7 @@ __global__ void __launch_bounds__(256) k_calc_d_g(const __grid_constant__ CalcAr
                 if (a.n_count && gl == 0) a.n_count[r] = (uint16_t)nN;
                 phase = 0; dlen = len; D = a.d_main ? a.d_main + off + r : nullptr;
                 PK = a.pk_main ? a.pk_main + off + r : nullptr;
-                i = dlen - 1; z = 0; st.cur = 0; st.n_cur = 1; in_step = false;
+                i = dlen - 1; z = 0; st.cur = 0; st.n_cur = 1; in_step = false; fresh = true; prev_w = 0;
                 if (gl == 0) glset<T>(ls, 0, 0, (T)0, fullU);
                 mode = RUN;
             }
@@ -222,8 +228,76 @@ __global__ void __launch_bounds__(256) k_calc_d_g(const __grid_constant__ CalcAr
         }
         if (__all_sync(FULL, mode == DONE)) break;
 
-        // begin a step: read base i of the forward read; an N (or a finished array) needs no pass
+        // ---- table step: from the full range, the next KTAB steps are a function of the next KTAB bases
         bool run = (mode == RUN);
+        {
+            const bool cand = use_tab && run && !in_step && fresh && i >= KTAB - 1;
+            if (__any_sync(FULL, cand)) {
+                // lane l serves steps s = l+1 and l+9 (<= KTAB); base of step s is seq[i-s+1]
+                const int s1 = (int)gl + 1, s2 = (int)gl + 9;
+                const uint32_t b1 = cand ? sseq[i - s1 + 1] : 0u;
+                const uint32_t b2 = (cand && s2 <= KTAB) ? sseq[i - s2 + 1] : 0u;
+                const bool hasN = gballot(b1 > 3u || b2 > 3u) != 0u;
+                const bool go = cand && !hasN;
+                const uint32_t X = gsum(((b1 & 3u) << (2 * (s1 - 1))) | (s2 <= KTAB ? ((b2 & 3u) << (2 * (s2 - 1))) : 0u));
+                unsigned long long e1 = 0, e2 = 0, p1 = 0, p2 = 0;     // entries of steps s1, s2 and of the steps before them
+                if (go) {
+                    e1 = a.ktab_w[ktab_level_off(s1) + (X & ((1u << (2 * s1)) - 1u))];
+                    if (s1 > 1) p1 = a.ktab_w[ktab_level_off(s1 - 1) + (X & ((1u << (2 * (s1 - 1))) - 1u))];
+                    if (s2 <= KTAB) {
+                        e2 = a.ktab_w[ktab_level_off(s2) + (X & ((1u << (2 * s2)) - 1u))];
+                        p2 = a.ktab_w[ktab_level_off(s2 - 1) + (X & ((1u << (2 * (s2 - 1))) - 1u))];
+                    }
+                }
+                // first step whose list is empty (KTAB+1 if none)
+                const uint32_t em1 = gballot(go && !((e1 >> 32) & 1ull));
+                const uint32_t em2 = gballot(go && s2 <= KTAB && !((e2 >> 32) & 1ull));
+                const int first_empty = em1 ? __ffs(em1) : (em2 ? 8 + __ffs(em2) : KTAB + 1);
+                const uint32_t wlast = (uint32_t)gshfl((uint32_t)e2, 1);                 // width after step KTAB (= s2 of lane 1)
+                const uint32_t lenw = (uint32_t)a.ix.length;
+                uint32_t ml = 0;
+                if (go) {
+                    const int k0 = dlen - 1 - i;                       // D index of step 1
+#pragma unroll
+                    for (int h = 0; h < 2; h++) {
+                        const int sx = h ? s2 : s1;
+                        const unsigned long long ee = h ? e2 : e1, pp = h ? p2 : p1;
+                        if (sx <= KTAB && sx <= first_empty) {
+                            const bool emptying = (sx == first_empty);
+                            const uint32_t num = emptying ? lenw : (uint32_t)ee;
+                            const uint32_t before = (sx == 1) ? prev_w : (uint32_t)pp;
+                            const int zz = emptying ? z + 1 : z;
+                            const int k = k0 + sx - 1;
+                            if (D) D[k] = make_int2(zz, (int)num);
+                            if (PK) PK[k] = (uint16_t)((zz & 0x1ff) | ((k && num == before) ? 0x8000 : 0));
+                            if (!emptying) ml = max(ml, (uint32_t)(ee >> 33));
+                        }
+                    }
+                }
+                ml = max(ml, __shfl_xor_sync(FULL, ml, 1, GL));
+                ml = max(ml, __shfl_xor_sync(FULL, ml, 2, GL));
+                ml = max(ml, __shfl_xor_sync(FULL, ml, 4, GL));
+                if (go) {
+                    if (ml > maxlist) maxlist = ml;
+                    if (first_empty <= KTAB) {                         // restart inside the window: stay fresh
+                        i -= first_empty;
+                        z++;
+                        prev_w = lenw;
+                    } else {                                           // adopt the tabulated list
+                        const uint32_t n = a.ktab_cnt[X], o = a.ktab_off[X];
+                        const P *src = reinterpret_cast<const P *>(a.ktab_iv) + o;
+                        for (uint32_t k = gl; k < n; k += GL) { const P v = src[k]; glset<T>(ls, 0, (int)k, v.x, v.y); }
+                        st.cur = 0; st.n_cur = (int)n;
+                        i -= KTAB;
+                        prev_w = wlast;
+                        fresh = false;
+                    }
+                }
+                __syncwarp();
+            }
+        }
+
+        // begin a step: read base i of the forward read; an N (or a finished array) needs no pass
         if (run && !in_step && i >= 0) {
             c = sseq[i];
             step_begin(st);
@@ -246,11 +320,13 @@ __global__ void __launch_bounds__(256) k_calc_d_g(const __grid_constant__ CalcAr
             int nn = (c <= 3u) ? st.n_next : 0;
             if (c <= 3u) st.cur ^= 1;
             if ((uint32_t)nn > maxlist) maxlist = (uint32_t)nn;
+            fresh = false;
             if (nn == 0) {                           // restart from the full range, one more difference
                 if (gl == 0) glset<T>(ls, st.cur, 0, (T)0, fullU);
                 nn = 1;
                 z++;
                 num = (uint32_t)a.ix.length;
+                fresh = true;
             }
             st.n_cur = nn;
             if (gl == 0) {
@@ -272,7 +348,7 @@ __global__ void __launch_bounds__(256) k_calc_d_g(const __grid_constant__ CalcAr
                 uint16_t *PKs = a.pk_seed ? a.pk_seed + (size_t)r * (a.seed_len + 1) : nullptr;
                 if (len > a.seed_len) {
                     phase = 1; dlen = a.seed_len; D = Ds; PK = PKs;
-                    i = dlen - 1; z = 0; st.cur = 0; st.n_cur = 1;
+                    i = dlen - 1; z = 0; st.cur = 0; st.n_cur = 1; fresh = true; prev_w = 0;
                     if (gl == 0) glset<T>(ls, 0, 0, (T)0, fullU);
                 } else {
                     // Q6: the reference consults a stale per-thread D_seed for such reads; the defined

@@ -885,6 +885,68 @@ __global__ void k_emit(const bwb_hit *__restrict__ unordered, const unsigned lon
 }
 
 // ---------------------------------------------------------------------------------------------
+// K0b: k-mer table for the top of the backward-search tree ("design levers").
+// After every (re)start from the full range the next k steps of calculate_d depend only on the next
+// k read bases.  For every k-mer X (k = KTAB, first applied base in the low digits) this kernel runs
+// the ordinary multi-interval extension (same extend_step as everywhere else) and records
+//   w[level s][X mod 4^s] = n_s << 33 | (n_s != 0) << 32 | (wrapped sum of widths after s steps)
+// for every prefix (all k-mers sharing a prefix write the same value), and the interval list after
+// k steps.  K3 then replaces up to k list steps by k look-ups -- same D arrays, bit for bit.
+// ---------------------------------------------------------------------------------------------
+constexpr int KTAB = 10;
+__host__ __device__ __forceinline__ uint32_t ktab_level_off(int s) { return ((1u << (2 * s)) - 4u) / 3u; }   // sum_{t<s} 4^t
+
+struct KtabArgs {
+    IndexView ix;
+    void *glists;                 // warp scratch [n_warps][2][list_cap]
+    int list_cap;
+    unsigned long long *w;        // all levels, level s at ktab_level_off(s)
+    uint32_t *koff, *kcnt;        // list of every k-mer in `iv`
+    void *iv;                     // Pair<T> pool
+    unsigned long long iv_cap;
+    unsigned long long *cursor;
+    uint32_t *status;
+};
+
+template <class T>
+__global__ void k_kmer_table(KtabArgs a) {
+    typedef typename Pair<T>::type P;
+    extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ T sC[17];
+    stage_C<T>(a.ix, sC);
+    const int wpb = blockDim.x >> 5;
+    const uint32_t gw = blockIdx.x * wpb + (threadIdx.x >> 5);
+    const uint32_t nw = gridDim.x * wpb;
+    unsigned char *wbase = smem + (size_t)(threadIdx.x >> 5) * LIST_SMEM_BYTES;
+    ListStore<T> ls;
+    warp_lists<T>(wbase, a.glists, gw, a.list_cap, ls);
+    const uint32_t lane = lane_id();
+    for (uint32_t X = gw; X < (1u << (2 * KTAB)); X += nw) {
+        if (lane == 0) lset<T>(ls, 0, 0, (T)0, (T)(a.ix.length - 1));
+        __syncwarp();
+        int cur = 0, n = 1;
+        for (int s = 1; s <= KTAB; s++) {
+            const uint32_t c = (X >> (2 * (s - 1))) & 3u;
+            uint32_t sumw = 0, nl = 0;
+            n = extend_step<T>(a.ix, sC, ls, cur, n, c, sumw, nl);
+            if (n < 0) { if (lane == 0) atomicExch(a.status, (uint32_t)(-BWB_ERR_CAPACITY)); n = 0; }
+            cur ^= 1;
+            if (lane == 0)
+                a.w[ktab_level_off(s) + (X & ((1u << (2 * s)) - 1u))] =
+                    n ? (((unsigned long long)n << 33) | (1ull << 32) | sumw) : 0ull;
+            if (n == 0) break;
+        }
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(a.cursor, (unsigned long long)n);
+        base = shfl64(base, 0);
+        if (base + n <= a.iv_cap)
+            for (int k = lane; k < n; k += 32) reinterpret_cast<P *>(a.iv)[base + k] = lget<T>(ls, cur, k);
+        if (lane == 0) { a.koff[X] = (uint32_t)base; a.kcnt[X] = (uint32_t)n; }
+        __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // K6: SA locate of every read's first hit + the top1/top2 sums of eval_aln (align.c:760-812)
 // ---------------------------------------------------------------------------------------------
 // invPsi(i) = C[B(i)] + O(B(i), i), 0 for the sentinel row (bwt.c:311-317); O(0, i) does not count

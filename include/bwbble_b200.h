@@ -99,6 +99,7 @@ int bwb_device_count(const bwb_ctx *ctx);
  *   "warps_per_block"  search kernel block shape (default 8)
  *   "blocks_per_sm"    persistent blocks per SM (default: occupancy query)
  *   "engine"           1 = warp-per-read kernel k_align (A/B only; 2 = back to the default 8-lane groups)
+ *   "kmer_table"       2 = do not use the 10-mer table of calculate_d's top of tree (A/B, tests; default on)
  *   "force_wide"       1 = 64-bit coordinates / 32-byte heap entries even on a small index (tests)  */
 int bwb_set_option(bwb_ctx *ctx, const char *key, long long value);
 /* Launch on a caller-owned cudaStream_t (e.g. torch's current stream) instead of the context's own. */

@@ -172,6 +172,11 @@ def test_calculate_d(gpu_case, use_len):
 def test_lower_bounds_k3(gpu_case, seed_len):
     al, orc, reads = gpu_case["al"], gpu_case["orc"], gpu_case["reads"]
     main, seed = al.lower_bounds(reads.seq, reads.offsets, seed_len)
+    al.set_option("kmer_table", 2)                     # same arrays without the 10-mer table
+    main2, seed2 = al.lower_bounds(reads.seq, reads.offsets, seed_len)
+    al.set_option("kmer_table", 1)
+    assert all((x == y).all() for x, y in zip(main, main2))
+    assert seed is None or all((x == y).all() for x, y in zip(seed, seed2))
     for r in range(reads.n):
         rd = reads.read(r)
         exp = orc.calculate_d(rd)
@@ -342,3 +347,18 @@ def test_streaming_fastq_ingest_writes_reference_aln_and_sam(tmp_path, batch):
     assert n == 200
     assert open(aln, "rb").read() == G.golden_bytes("aln_n3.aln")
     assert open(sam, "rb").read() == G.golden_bytes("sam_n3.sam")
+
+
+def test_kmer_table_on_dense_genome(dense_case):
+    """10-mer table of calculate_d's top of tree: adoption of tabulated lists (dozens of intervals), restarts inside
+    the window, N inside the window, reads shorter than the window -- D arrays equal the oracle's."""
+    from bwbble_b200 import synth
+    al, orc = dense_case["al"], dense_case["orc"]
+    reads = synth.make_reads(dense_case["genome"], 9, 300, 60, 3, n_base_frac=0.02, ragged=(6, 60))
+    main, seed = al.lower_bounds(reads.seq, reads.offsets, 20)
+    for r in range(reads.n):
+        rd = reads.read(r)
+        exp = orc.calculate_d(rd)
+        assert (main[r] == exp).all(), "D read %d (len %d):\n got %s\n exp %s" % (r, len(rd), main[r].T, exp.T)
+        exps = orc.calculate_d(rd, 20) if len(rd) > 20 else np.zeros((21, 2), dtype=np.int32)
+        assert (seed[r] == exps).all()
