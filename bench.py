@@ -205,7 +205,7 @@ def main():
             return 0
         fa = prepare_index(args.workload, 0, lambda: None)
         reads = make_batch(args.workload, 0, 0, 1)
-        n_s = args.cpu_sample or max(256, cores * 48)
+        n_s = args.cpu_sample or max(2048, cores * 512)
         times = []
         meta = None
         for s in range(args.warmup + args.steps):
@@ -367,7 +367,12 @@ def main():
                     "kernel_share_of_step": k_ms / (dev_ms / args.steps),
                     "rank_queries_per_read_reference": q_per_read,
                     "bytes_per_query": 128,
-                    "physical_block_loads_per_read": ctr_sum.get("rank_queries", 0) / (w["batch"] * args.steps)}
+                    "physical_block_loads_per_read": ctr_sum.get("rank_queries", 0) / (w["batch"] * args.steps),
+                    "physical_gbs": ctr_sum.get("rank_queries", 0) / args.steps * 128 / (k_ms / 1e3) / 1e9,
+                    "note": "achieved counts the REFERENCE algorithm's rank queries (SURVEY 8d); the device path does fewer "
+                            "physical block loads (L-1/U share a block, one block serves all 15 codes, K0b's 10-mer table "
+                            "replaces the top of calculate_d) and most of them hit L2, so frac may exceed 1; physical_gbs is "
+                            "the block-load rate the kernels really sustain"}
         line = {"metric": "reads/sec (100bp, BWA-default diffs)", "value": value, "unit": "reads/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64/u32 integer",

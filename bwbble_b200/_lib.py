@@ -83,6 +83,12 @@ SIGNATURES = {
     "bwb_sa_upload": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64]),
     "bwb_index_load_file_sa": (C.c_int, [C.c_void_p, C.c_char_p]),
     "bwb_results_locations": (C.c_void_p, [C.c_void_p]),
+    "bwb_precalc_build": (C.c_int, [C.c_void_p, C.c_int]),
+    "bwb_precalc_upload": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int]),
+    "bwb_precalc_load_file": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int]),
+    "bwb_precalc_write": (C.c_int, [C.c_void_p, C.c_char_p]),
+    "bwb_precalc_num_intervals": (C.c_uint64, [C.c_void_p]),
+    "bwb_precalc_row": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32)]),
     "bwb_results_write_sam": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_char_p), C.c_void_p, C.c_void_p,
                                         C.POINTER(C.c_char_p), C.c_uint64, C.c_int, C.c_char_p, C.c_int, C.c_int]),
 }

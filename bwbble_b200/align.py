@@ -199,6 +199,38 @@ class Aligner:
             sa = _u64(ix.SA)
             _lib.check(_lib.lib().bwb_sa_upload(self._ctx, sa.ctypes.data, len(sa)), self._ctx)
 
+    # ---- -P seed table (align.c:200-238) ---------------------------------------------------------
+    def build_precalc(self, is_multiref: bool = True):
+        """precalc_sa_intervals on the device (K0c): exact_match() of all 4^12 12-mers."""
+        _lib.check(_lib.lib().bwb_precalc_build(self._ctx, int(bool(is_multiref))), self._ctx)
+
+    def load_precalc(self, pre_path: str, is_multiref: bool = True):
+        """load_precalc_sa_intervals(<fasta>.pre)"""
+        _lib.check(_lib.lib().bwb_precalc_load_file(self._ctx, pre_path.encode(), int(bool(is_multiref))), self._ctx)
+
+    def upload_precalc(self, sizes, intervals_lu, is_multiref: bool = True):
+        sizes = np.ascontiguousarray(sizes, dtype=np.int32)
+        lu = _u64(np.asarray(intervals_lu).reshape(-1))
+        if len(sizes) != 1 << 24:
+            raise ValueError("the seed table has 4^12 rows")
+        _lib.check(_lib.lib().bwb_precalc_upload(self._ctx, sizes.ctypes.data, lu.ctypes.data, len(lu) // 2,
+                                                 int(bool(is_multiref))), self._ctx)
+
+    def write_precalc(self, pre_path: str):
+        """store the table in the reference's .pre layout (align.c:144-152,217-222)"""
+        _lib.check(_lib.lib().bwb_precalc_write(self._ctx, pre_path.encode()), self._ctx)
+
+    def precalc_num_intervals(self) -> int:
+        return int(_lib.lib().bwb_precalc_num_intervals(self._ctx))
+
+    def precalc_row(self, row: int) -> np.ndarray:
+        n = C.c_uint32()
+        _lib.check(_lib.lib().bwb_precalc_row(self._ctx, row, None, 0, C.byref(n)), self._ctx)
+        out = np.zeros((n.value, 2), dtype=np.uint64)
+        if n.value:
+            _lib.check(_lib.lib().bwb_precalc_row(self._ctx, row, out.ctypes.data, n.value, C.byref(n)), self._ctx)
+        return out
+
     def download_blocks(self) -> np.ndarray:
         n = int(_lib.lib().bwb_index_num_blocks(self._ctx))
         out = np.zeros((n, 32), dtype=np.uint32)

@@ -43,6 +43,9 @@ struct Device {
     unsigned long long *ktab_w = nullptr;
     uint32_t *ktab_off = nullptr, *ktab_cnt = nullptr;
     void *ktab_iv = nullptr;
+    // -P seed table (K0c): row offsets / sizes and the (L,U) pool
+    uint32_t *pre_off = nullptr, *pre_cnt = nullptr;
+    ulonglong2 *pre_iv = nullptr;
     // search scratch (sized for n_warps)
     int n_warps = 0, grid = 0, wpb = 0, grid3 = 0;
     size_t smem_bytes = 0;
@@ -81,6 +84,11 @@ struct bwb_ctx {
                               // 2 = 8-lane groups (k_calc_d_g + k_search_g); 1 and 2 are A/B baselines
     int use_ktab = 1;         // k-mer table for calculate_d's top of tree (0 = off, for A/B and tests)
     int force_wide = 0;       // tests: run the 64-bit / 32-byte-entry kernels on a small index
+    // -P seed table, host copy in row order (what a .pre file holds)
+    bool have_pre = false;
+    int pre_multiref = 1;
+    std::vector<uint32_t> pre_cnt_h, pre_off_h;
+    std::vector<uint64_t> pre_lu_h;  // L,U pairs
 };
 
 struct bwb_reads {
@@ -253,12 +261,22 @@ int prepare_search_lane(bwb_ctx *ctx, Device &d, int nb, bool wide) {
     CU(cudaSetDevice(d.id));
     const int tpb = 128;
     const size_t smem = (size_t)nb * tpb * 4;                 // bucket heads [nb][128]
-    if (wide) CU(cudaFuncSetAttribute(k_search_l<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    else CU(cudaFuncSetAttribute(k_search_l<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // the -P instantiations differ only in how a read is seeded: same launch shape as the plain ones
+    CU(cudaFuncSetAttribute(k_search_l<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CU(cudaFuncSetAttribute(k_search_l<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CU(cudaFuncSetAttribute(k_search_l<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CU(cudaFuncSetAttribute(k_search_l<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int bps = ctx->blocks_per_sm;
     if (bps <= 0) {
-        if (wide) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_search_l<true>, tpb, smem));
-        else CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_search_l<false>, tpb, smem));
+        int b0 = 0, b1 = 0;
+        if (wide) {
+            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b0, k_search_l<true, false>, tpb, smem));
+            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b1, k_search_l<true, true>, tpb, smem));
+        } else {
+            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b0, k_search_l<false, false>, tpb, smem));
+            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b1, k_search_l<false, true>, tpb, smem));
+        }
+        bps = b0 < b1 ? b0 : b1;
         if (bps <= 0) return fail(ctx, BWB_ERR_CUDA, "k_search_l does not fit on an SM");
     }
     const int grid = bps * d.sm_count;
@@ -400,6 +418,90 @@ int build_ktab(bwb_ctx *ctx, Device &d) {
     return BWB_OK;
 }
 
+// put a row-ordered seed table (sizes + concatenated L,U pairs) on every device
+int precalc_install(bwb_ctx *ctx, int is_multiref) {
+    const uint64_t total = ctx->pre_lu_h.size() / 2;
+    if (total > 0xfffffff0ull) return fail(ctx, BWB_ERR_UNSUPPORTED, "seed table with %llu intervals", (unsigned long long)total);
+    std::vector<uint32_t> &off = ctx->pre_off_h;
+    off.resize(NUM_PRECALC);
+    uint64_t acc = 0;
+    for (uint32_t x = 0; x < NUM_PRECALC; x++) { off[x] = (uint32_t)acc; acc += ctx->pre_cnt_h[x]; }
+    if (acc != total) return fail(ctx, BWB_ERR_ARG, "seed table: sizes sum to %llu, %llu intervals given", (unsigned long long)acc, (unsigned long long)total);
+    for (auto &d : ctx->dev) {
+        CU(cudaSetDevice(d.id));
+        if (d.pre_off) { cudaFree(d.pre_off); cudaFree(d.pre_cnt); cudaFree(d.pre_iv); d.pre_off = d.pre_cnt = nullptr; d.pre_iv = nullptr; }
+        CU(cudaMalloc(&d.pre_off, (size_t)NUM_PRECALC * 4));
+        CU(cudaMalloc(&d.pre_cnt, (size_t)NUM_PRECALC * 4));
+        CU(cudaMalloc(&d.pre_iv, (total + 1) * sizeof(ulonglong2)));
+        CU(cudaMemcpyAsync(d.pre_off, off.data(), (size_t)NUM_PRECALC * 4, cudaMemcpyHostToDevice, d.stream));
+        CU(cudaMemcpyAsync(d.pre_cnt, ctx->pre_cnt_h.data(), (size_t)NUM_PRECALC * 4, cudaMemcpyHostToDevice, d.stream));
+        if (total) CU(cudaMemcpyAsync(d.pre_iv, ctx->pre_lu_h.data(), total * 16, cudaMemcpyHostToDevice, d.stream));
+        CU(cudaStreamSynchronize(d.stream));
+    }
+    ctx->have_pre = true;
+    ctx->pre_multiref = is_multiref ? 1 : 0;
+    return BWB_OK;
+}
+
+// K0c on device 0 -> row-ordered host copy
+int precalc_compute(bwb_ctx *ctx, int is_multiref) {
+    Device &d = ctx->dev[0];
+    CU(cudaSetDevice(d.id));
+    const bool wide = index_is_wide(ctx);
+    const int wpb = 8, grid = d.sm_count * 2, n_warps = grid * wpb;
+    uint32_t *off = nullptr, *cnt = nullptr;
+    void *gl = nullptr;
+    unsigned char *sm = nullptr;
+    ulonglong2 *iv = nullptr;
+    CU(cudaMalloc(&off, (size_t)NUM_PRECALC * 4));
+    CU(cudaMalloc(&cnt, (size_t)NUM_PRECALC * 4));
+    CU(cudaMalloc(&gl, (size_t)n_warps * 2 * ctx->list_cap * sizeof(ulonglong2)));
+    CU(cudaMalloc(&sm, 64));
+    unsigned long long cap = 32ull << 20, used = 0;
+    uint32_t st = 0;
+    int rc = BWB_OK;
+    for (int attempt = 0; attempt < 3; attempt++) {
+        CU(cudaMalloc(&iv, cap * sizeof(ulonglong2)));
+        CU(cudaMemsetAsync(sm, 0, 64, d.stream));
+        PrecalcArgs a;
+        memset(&a, 0, sizeof a);
+        a.ix = make_view(ctx, d); a.glists = gl; a.list_cap = ctx->list_cap; a.is_multiref = is_multiref;
+        a.off = off; a.cnt = cnt; a.iv = iv; a.iv_cap = cap;
+        a.cursor = (unsigned long long *)sm; a.status = (uint32_t *)(sm + 8);
+        const size_t smem = (size_t)wpb * LIST_SMEM_BYTES;
+        if (wide) k_precalc<uint64_t><<<grid, wpb * 32, smem, d.stream>>>(a);
+        else k_precalc<uint32_t><<<grid, wpb * 32, smem, d.stream>>>(a);
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(&used, sm, 8, cudaMemcpyDeviceToHost, d.stream));
+        CU(cudaMemcpyAsync(&st, sm + 8, 4, cudaMemcpyDeviceToHost, d.stream));
+        CU(cudaStreamSynchronize(d.stream));
+        if (st || used <= cap) break;
+        CU(cudaFree(iv));
+        iv = nullptr;
+        cap = used + 1024;
+    }
+    if (st) rc = fail(ctx, -(int)st, "seed table: interval list exceeded list_cap=%d (raise it with bwb_set_option)", ctx->list_cap);
+    else if (used > 0xfffffff0ull) rc = fail(ctx, BWB_ERR_UNSUPPORTED, "seed table with %llu intervals", used);
+    if (!rc) {
+        std::vector<uint32_t> hoff(NUM_PRECALC);
+        std::vector<ulonglong2> pool(used);
+        ctx->pre_cnt_h.resize(NUM_PRECALC);
+        CU(cudaMemcpy(hoff.data(), off, (size_t)NUM_PRECALC * 4, cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(ctx->pre_cnt_h.data(), cnt, (size_t)NUM_PRECALC * 4, cudaMemcpyDeviceToHost));
+        if (used) CU(cudaMemcpy(pool.data(), iv, used * sizeof(ulonglong2), cudaMemcpyDeviceToHost));
+        ctx->pre_lu_h.resize(used * 2);
+        uint64_t w = 0;
+        for (uint32_t x = 0; x < NUM_PRECALC; x++)
+            for (uint32_t k = 0; k < ctx->pre_cnt_h[x]; k++, w++) {
+                ctx->pre_lu_h[2 * w] = pool[hoff[x] + k].x;
+                ctx->pre_lu_h[2 * w + 1] = pool[hoff[x] + k].y;
+            }
+    }
+    cudaFree(off); cudaFree(cnt); cudaFree(gl); cudaFree(sm);
+    if (iv) cudaFree(iv);
+    return rc;
+}
+
 void set_ktab(const bwb_ctx *ctx, const Device &d, CalcArgs &c) {
     const bool on = ctx->use_ktab && d.ktab_w && d.ktab_iv;
     c.ktab_w = on ? d.ktab_w : nullptr;
@@ -470,6 +572,9 @@ void bwb_destroy(bwb_ctx *ctx) {
         if (d.ktab_off) cudaFree(d.ktab_off);
         if (d.ktab_cnt) cudaFree(d.ktab_cnt);
         if (d.ktab_iv) cudaFree(d.ktab_iv);
+        if (d.pre_off) cudaFree(d.pre_off);
+        if (d.pre_cnt) cudaFree(d.pre_cnt);
+        if (d.pre_iv) cudaFree(d.pre_iv);
         DevBuf *bufs[] = {&d.glists, &d.chunks, &d.chunk_link, &d.stage, &d.seq, &d.offsets, &d.read_off, &d.read_cnt,
                           &d.ordered_off, &d.unordered, &d.ordered, &d.cub_tmp, &d.small, &d.d_main, &d.d_seed, &d.pool, &d.loc, &d.pk_main, &d.pk_seed, &d.n_count, &d.nxt, &d.blk_link, &d.heads};
         for (DevBuf *b : bufs) release(*b);
@@ -592,6 +697,54 @@ int bwb_index_load_file_sa(bwb_ctx *ctx, const char *bwt_path) {
     int rc = bwb_index_upload(ctx, ix.length, ix.sa0_index, ix.C, ix.bwt.data(), ix.num_words, ix.O.data(), ix.num_occ);
     if (rc) return rc;
     return bwb_sa_upload(ctx, ix.SA.data(), ix.num_sa);
+}
+
+// ---- -P seed table ------------------------------------------------------------------------
+int bwb_precalc_build(bwb_ctx *ctx, int is_multiref) {
+    if (!ctx) return BWB_ERR_ARG;
+    if (!ctx->have_index) return fail(ctx, BWB_ERR_NO_INDEX, "bwb_precalc_build before bwb_index_upload");
+    int rc = precalc_compute(ctx, is_multiref ? 1 : 0);
+    if (rc) return rc;
+    return precalc_install(ctx, is_multiref);
+}
+
+int bwb_precalc_upload(bwb_ctx *ctx, const int32_t *sizes, const uint64_t *intervals_LU, uint64_t n_intervals, int is_multiref) {
+    if (!ctx || !sizes || (n_intervals && !intervals_LU)) return BWB_ERR_ARG;
+    if (!ctx->have_index) return fail(ctx, BWB_ERR_NO_INDEX, "bwb_precalc_upload before bwb_index_upload");
+    ctx->pre_cnt_h.resize(NUM_PRECALC);
+    for (uint32_t x = 0; x < NUM_PRECALC; x++) {
+        if (sizes[x] < 0) return fail(ctx, BWB_ERR_ARG, "seed table row %u has negative size", x);
+        ctx->pre_cnt_h[x] = (uint32_t)sizes[x];
+    }
+    ctx->pre_lu_h.assign(intervals_LU, intervals_LU + 2 * n_intervals);
+    return precalc_install(ctx, is_multiref);
+}
+
+int bwb_precalc_load_file(bwb_ctx *ctx, const char *pre_path, int is_multiref) {
+    if (!ctx || !pre_path) return BWB_ERR_ARG;
+    if (!ctx->have_index) return fail(ctx, BWB_ERR_NO_INDEX, "bwb_precalc_load_file before bwb_index_upload");
+    if (bwb_host::read_pre_file(pre_path, ctx->pre_cnt_h, ctx->pre_lu_h)) return fail(ctx, BWB_ERR_IO, "cannot read %s", pre_path);
+    return precalc_install(ctx, is_multiref);
+}
+
+int bwb_precalc_write(bwb_ctx *ctx, const char *pre_path) {
+    if (!ctx || !pre_path) return BWB_ERR_ARG;
+    if (!ctx->have_pre) return fail(ctx, BWB_ERR_ARG, "no seed table to write");
+    if (bwb_host::write_pre_file(pre_path, ctx->pre_cnt_h, ctx->pre_lu_h)) return fail(ctx, BWB_ERR_IO, "cannot write %s", pre_path);
+    return BWB_OK;
+}
+
+uint64_t bwb_precalc_num_intervals(const bwb_ctx *ctx) { return ctx && ctx->have_pre ? ctx->pre_lu_h.size() / 2 : 0; }
+
+int bwb_precalc_row(const bwb_ctx *ctx, uint32_t row, uint64_t *intervals_LU, uint32_t cap, uint32_t *n) {
+    if (!ctx || !n || row >= NUM_PRECALC || !ctx->have_pre) return BWB_ERR_ARG;
+    *n = ctx->pre_cnt_h[row];
+    const uint64_t base = ctx->pre_off_h[row];
+    for (uint32_t k = 0; k < *n && k < cap && intervals_LU; k++) {
+        intervals_LU[2 * k] = ctx->pre_lu_h[2 * (base + k)];
+        intervals_LU[2 * k + 1] = ctx->pre_lu_h[2 * (base + k) + 1];
+    }
+    return BWB_OK;
 }
 
 uint64_t bwb_index_num_blocks(const bwb_ctx *ctx) { return ctx && ctx->have_index ? ctx->num_blocks : 0; }
@@ -871,7 +1024,12 @@ void bwb_reads_free(bwb_reads *r) {
 }
 
 static int check_params(bwb_ctx *ctx, const bwb_params *p, int max_len, int &nb) {
-    if (p->use_precalc) return fail(ctx, BWB_ERR_UNSUPPORTED, "-P (pre-calculated intervals) is not built on the device path");
+    if (p->use_precalc) {
+        if (ctx->engine != 0) return fail(ctx, BWB_ERR_UNSUPPORTED, "-P (pre-calculated intervals) is only built in the lane engine");
+        if (!ctx->have_pre) return fail(ctx, BWB_ERR_ARG, "use_precalc without a seed table (bwb_precalc_build / _load_file / _upload)");
+        if (ctx->pre_multiref != (p->is_multiref ? 1 : 0))
+            return fail(ctx, BWB_ERR_ARG, "the seed table was made for %s mode", ctx->pre_multiref ? "multi-genome" : "-S");
+    }
     if (!p->is_multiref && ctx->engine != 0)
         return fail(ctx, BWB_ERR_UNSUPPORTED, "-S (single-genome mode) is only built in the lane engine");
     if (p->max_diff < 0 || p->max_gapo < 0 || p->max_gape < 0 || p->mm_score < 0 || p->gapo_score < 0 || p->gape_score < 0 ||
@@ -1001,8 +1159,14 @@ static int launch_shard(bwb_ctx *ctx, Device &d, const bwb_params *p, int nb, co
         g.pool = (PoolState *)d.pool.p; g.blk_link = (uint32_t *)d.blk_link.p;
         g.out_hits = a.out_hits; g.out_cap = a.out_cap; g.out_cursor = a.out_cursor;
         g.read_off = a.read_off; g.read_cnt = a.read_cnt; g.status = a.status; g.counters = a.counters;
-        if (wide) k_search_l<true><<<d.grid, 128, d.smem_bytes, d.stream>>>(g);
-        else k_search_l<false><<<d.grid, 128, d.smem_bytes, d.stream>>>(g);
+        g.pre_off = d.pre_off; g.pre_cnt = d.pre_cnt; g.pre_iv = d.pre_iv;
+        if (p->use_precalc) {
+            if (wide) k_search_l<true, true><<<d.grid, 128, d.smem_bytes, d.stream>>>(g);
+            else k_search_l<false, true><<<d.grid, 128, d.smem_bytes, d.stream>>>(g);
+        } else {
+            if (wide) k_search_l<true, false><<<d.grid, 128, d.smem_bytes, d.stream>>>(g);
+            else k_search_l<false, false><<<d.grid, 128, d.smem_bytes, d.stream>>>(g);
+        }
         CU(cudaGetLastError());
     } else if (n) {
         // K3: lower-bound arrays of every read -> HBM

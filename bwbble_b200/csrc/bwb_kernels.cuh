@@ -947,6 +947,88 @@ __global__ void k_kmer_table(KtabArgs a) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// K0c: the -P seed table (precalc_sa_intervals, align.c:200-224): exact_match() of every 12-mer from
+// the full range.  Row X holds the 12-mer whose base-4 digits are X, most significant digit = first
+// base (next_read, align.c:188-198); the search consumes the LAST base first, i.e. the low digits.
+// Multi-genome: one warp per row (extend_step).  -S: one thread per row, 12 single-code steps
+// (exact_match_1to1_bounded, exact_match.c:196-222).  Lists land in a pool in arrival order;
+// off[X]/cnt[X] find them (the .pre writer walks X in order).
+// ---------------------------------------------------------------------------------------------
+constexpr int PRECALC_LEN = 12;                       // PRECALC_INTERVAL_LENGTH, align.h:31
+constexpr uint32_t NUM_PRECALC = 1u << (2 * PRECALC_LEN);   // align.h:30
+
+struct PrecalcArgs {
+    IndexView ix;
+    void *glists;                 // warp scratch [n_warps][2][list_cap]
+    int list_cap;
+    int is_multiref;
+    uint32_t *off, *cnt;          // per row
+    ulonglong2 *iv;               // (L,U) pool, 64-bit whatever the index width: K4's entry width
+                                  // also depends on max_gapo
+    unsigned long long iv_cap;
+    unsigned long long *cursor;
+    uint32_t *status;
+};
+
+template <class T>
+__global__ void k_precalc(PrecalcArgs a) {
+    typedef typename Pair<T>::type P;
+    extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ T sC[17];
+    stage_C<T>(a.ix, sC);
+    const uint32_t lane = lane_id();
+    if (!a.is_multiref) {
+        const uint32_t nt = gridDim.x * blockDim.x;
+        for (uint32_t X0 = blockIdx.x * blockDim.x; X0 < NUM_PRECALC; X0 += nt) {     // warp-uniform trip count
+            const uint32_t X = X0 + threadIdx.x;
+            T L = 0, U = (T)(a.ix.length - 1);
+            bool ok = true;
+            for (int s = 0; s < PRECALC_LEN && ok; s++) {
+                const uint32_t code = (0x173Fu >> (4u * ((X >> (2 * s)) & 3u))) & 15u;    // nt4_gray, io.h:94-110
+                T oL, oU;
+                occ_pair<T>(a.ix, sC, code, (T)(L - 1), U, oL, oU);
+                L = (T)(sC[code] + oL + 1); U = (T)(sC[code] + oU);
+                ok = L <= U;
+            }
+            const uint32_t V = __ballot_sync(FULL, ok);
+            unsigned long long base = 0;
+            if (lane == 0 && V) base = atomicAdd(a.cursor, (unsigned long long)__popc(V));
+            base = shfl64(base, 0) + __popc(V & ((1u << lane) - 1u));
+            if (ok && base < a.iv_cap) a.iv[base] = make_ulonglong2((unsigned long long)L, (unsigned long long)U);
+            a.off[X] = (uint32_t)base; a.cnt[X] = ok ? 1u : 0u;
+        }
+        return;
+    }
+    const int wpb = blockDim.x >> 5;
+    const uint32_t gw = blockIdx.x * wpb + (threadIdx.x >> 5);
+    const uint32_t nw = gridDim.x * wpb;
+    unsigned char *wbase = smem + (size_t)(threadIdx.x >> 5) * LIST_SMEM_BYTES;
+    ListStore<T> ls;
+    warp_lists<T>(wbase, a.glists, gw, a.list_cap, ls);
+    for (uint32_t X = gw; X < NUM_PRECALC; X += nw) {
+        if (lane == 0) lset<T>(ls, 0, 0, (T)0, (T)(a.ix.length - 1));
+        __syncwarp();
+        int cur = 0, n = 1;
+        for (int s = 0; s < PRECALC_LEN && n; s++) {
+            uint32_t sumw = 0, nl = 0;
+            n = extend_step<T>(a.ix, sC, ls, cur, n, (X >> (2 * s)) & 3u, sumw, nl);
+            if (n < 0) { if (lane == 0) atomicExch(a.status, (uint32_t)(-BWB_ERR_CAPACITY)); n = 0; }
+            cur ^= 1;
+        }
+        unsigned long long base = 0;
+        if (lane == 0 && n) base = atomicAdd(a.cursor, (unsigned long long)n);
+        base = shfl64(base, 0);
+        if (base + n <= a.iv_cap)
+            for (int k = lane; k < n; k += 32) {
+                const P v = lget<T>(ls, cur, k);
+                a.iv[base + k] = make_ulonglong2((unsigned long long)v.x, (unsigned long long)v.y);
+            }
+        if (lane == 0) { a.off[X] = (uint32_t)base; a.cnt[X] = (uint32_t)n; }
+        __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // K6: SA locate of every read's first hit + the top1/top2 sums of eval_aln (align.c:760-812)
 // ---------------------------------------------------------------------------------------------
 // invPsi(i) = C[B(i)] + O(B(i), i), 0 for the sentinel row (bwt.c:311-317); O(0, i) does not count

@@ -43,6 +43,8 @@ struct LaneArgs {
     uint32_t *queue;
     const uint16_t *pk_main, *pk_seed;       // packed lower bounds from K3
     const uint16_t *n_count;                 // N bases per read, from K3
+    const uint32_t *pre_off, *pre_cnt;       // -P seed table (K0c), rows of `pre_iv`; only read by k_search_l<.., true>
+    const ulonglong2 *pre_iv;                // 64-bit (L,U) whatever T is
     uint4 *slots;                            // arena: 2 x uint4 per slot
     uint32_t slots_per_lane;                 // private range of lane-slot s: [s*spl, (s+1)*spl)
     uint32_t priv_total;                     // first slot of the shared region (multiple of LBLK)
@@ -221,7 +223,7 @@ struct LaneHeap {
 #define BWB_LANE_MIN_BLOCKS 3
 #endif
 
-template <bool WIDE>
+template <bool WIDE, bool PRE>
 __global__ void __launch_bounds__(128, BWB_LANE_MIN_BLOCKS) k_search_l(const __grid_constant__ LaneArgs a) {
     typedef typename Coord<WIDE>::type T;
     __shared__ T sC[17];
@@ -298,16 +300,43 @@ __global__ void __launch_bounds__(128, BWB_LANE_MIN_BLOCKS) k_search_l(const __g
             best_score = a.nb; max_diff = a.max_diff; num_best = 0;
             have_task = false;
             for (int b = 0; b < a.nb; b++) h.heads[b * 128] = NIL;
-            if (nN <= a.max_diff) {                                   // N pre-check, inexact_match.c:259-266
+            have_next = false;
+            mode = FLUSH;
+            if (PRE) {
+                // -P (inexact_match.c:50-57,269-279): the search starts from the exact-match intervals of
+                // rc's last 12 bases (= the complement of the read's first 12, read2index align.c:174-186),
+                // pushed in list order with 12 matches on their path; the last one pops first.
+                uint32_t idx = 0, bad = len < PRECALC_LEN ? 1u : 0u;
+                for (int j = 0; j < PRECALC_LEN && !bad; j++) {
+                    const uint32_t c = rseq[j];
+                    bad |= c > 3u ? 1u : 0u;
+                    idx |= (3u - (c & 3u)) << (2 * j);
+                }
+                const uint32_t np = (bad || nN > a.max_diff) ? 0u : a.pre_cnt[idx];
+                if (np) {
+                    const ulonglong2 *src = a.pre_iv + a.pre_off[idx];
+                    const uint32_t z0 = (uint32_t)(len - PRECALC_LEN);
+                    bool ok = true;
+                    for (uint32_t k = 0; k + 1 < np && ok; k++) {
+                        const ulonglong2 v = src[k];
+                        ok = h.push(al, a, lane_slot, 0, (T)v.x, (T)v.y, z0, 0u, 0u, 0u, 0u);
+                    }
+                    if (np > 1) h.mark(0);
+                    const ulonglong2 v = src[np - 1];
+                    have_next = true;
+                    nx.L = (T)v.x; nx.U = (T)v.y; nx.z = z0; nx.w = 0; nx.r1 = nx.r2 = nx.r3 = 0;
+                    nx_bucket = 0;
+                    c_push += np;
+                    mode = SEARCH;
+                    if (!ok) { err = BWB_ERR_CAPACITY; mode = FLUSH; }
+                }
+            } else if (nN <= a.max_diff) {                            // N pre-check, inexact_match.c:259-266
                 // root entry (inexact_match.c:281): straight into the next-pop registers
                 have_next = true;
                 nx.L = 0; nx.U = lastrow; nx.z = (uint32_t)len; nx.w = 0; nx.r1 = nx.r2 = nx.r3 = 0;
                 nx_bucket = 0;
                 c_push++;
                 mode = SEARCH;
-            } else {
-                have_next = false;
-                mode = FLUSH;
             }
         }
 

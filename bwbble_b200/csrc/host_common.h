@@ -19,4 +19,9 @@ int build_index_arrays(const uint8_t *text, uint64_t n, HostIndex &ix);
 int write_bwt_file(const HostIndex &ix, const char *path);
 int read_bwt_file(const char *path, HostIndex &ix, bool load_sa);
 
+// .pre file of `bwbble align -P` (store_sa_interval_list / load_sa_interval_list, align.c:144-172,
+// written row by row by precalc_sa_intervals, align.c:200-224): 4^12 records {int32 n; n x (u64 L, u64 U)}
+int read_pre_file(const char *path, std::vector<uint32_t> &sizes, std::vector<uint64_t> &lu);
+int write_pre_file(const char *path, const std::vector<uint32_t> &sizes, const std::vector<uint64_t> &lu);
+
 }  // namespace bwb_host

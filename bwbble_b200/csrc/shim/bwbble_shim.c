@@ -54,6 +54,21 @@ typedef struct {
     shim_read_t *reads;
 } shim_reads_t;
 
+typedef struct shim_sa_intv_ {           /* align.h:34-38 */
+    uint64_t L, U;
+    struct shim_sa_intv_ *next_intv;
+} shim_sa_intv_t;
+
+typedef struct {                         /* align.h:42-46 */
+    int size;
+    shim_sa_intv_t *first_intv;
+    shim_sa_intv_t *last_intv;
+} shim_sa_intv_list_t;
+
+#define SHIM_NUM_PRECALC 16777216        /* align.h:30 */
+
+_Static_assert(sizeof(shim_sa_intv_t) == 24 && sizeof(shim_sa_intv_list_t) == 24 &&
+               offsetof(shim_sa_intv_list_t, first_intv) == 8, "sa_intv_list_t layout");
 _Static_assert(offsetof(shim_bwt_t, bwt) == 16 && offsetof(shim_bwt_t, C) == 24 && offsetof(shim_bwt_t, O) == 160 &&
                offsetof(shim_bwt_t, num_occ) == 168 && offsetof(shim_bwt_t, SA) == 65712 &&
                offsetof(shim_bwt_t, sa0_index) == 65728 && sizeof(shim_bwt_t) == 65736, "bwt_t layout");
@@ -66,7 +81,26 @@ static void die(bwb_ctx *ctx, const char *what) {
     exit(1);
 }
 
-static int run(shim_bwt_t *BWT, shim_reads_t *reads, bwb_params *params, char *alnFname, const char *banner) {
+/* -P: the table load_precalc_sa_intervals built (align.c:226-238), 4^12 linked lists -> sizes + flat (L,U) pairs */
+static void upload_precalc(bwb_ctx *ctx, const shim_sa_intv_list_t *table, const bwb_params *params) {
+    int32_t *sizes = (int32_t *)malloc((size_t)SHIM_NUM_PRECALC * sizeof(int32_t));
+    uint64_t total = 0;
+    if (!sizes) { printf("bwbble_b200: out of host memory\n"); exit(1); }
+    for (size_t x = 0; x < SHIM_NUM_PRECALC; x++) { sizes[x] = table[x].size; total += (uint64_t)(table[x].size > 0 ? table[x].size : 0); }
+    uint64_t *lu = (uint64_t *)malloc((size_t)(total + 1) * 16);
+    if (!lu) { printf("bwbble_b200: out of host memory\n"); exit(1); }
+    uint64_t w = 0;
+    for (size_t x = 0; x < SHIM_NUM_PRECALC; x++) {
+        const shim_sa_intv_t *iv = table[x].size > 0 ? table[x].first_intv : NULL;
+        for (int k = 0; k < table[x].size; k++, iv = iv->next_intv) { lu[2 * w] = iv->L; lu[2 * w + 1] = iv->U; w++; }
+    }
+    if (bwb_precalc_upload(ctx, sizes, lu, total, params->is_multiref)) die(ctx, "seed table upload failed");
+    free(sizes);
+    free(lu);
+}
+
+static int run(shim_bwt_t *BWT, shim_reads_t *reads, const shim_sa_intv_list_t *precalc, bwb_params *params, char *alnFname,
+               const char *banner) {
     printf("%s", banner);
     FILE *alnFile = fopen(alnFname, "a+b");
     if (alnFile == NULL) {
@@ -91,6 +125,10 @@ static int run(shim_bwt_t *BWT, shim_reads_t *reads, bwb_params *params, char *a
     if (!ctx) die(NULL, "cannot create the device context");
     if (bwb_index_upload(ctx, BWT->length, BWT->sa0_index, BWT->C, BWT->bwt, BWT->num_words, BWT->O, BWT->num_occ))
         die(ctx, "index upload failed");
+    if (params->use_precalc) {
+        if (!precalc) { printf("bwbble_b200: -P without a pre-calculated interval table\n"); exit(1); }
+        upload_precalc(ctx, precalc, params);
+    }
 
     uint8_t *seq = NULL;
     uint64_t *off = NULL;
@@ -134,11 +172,11 @@ static int run(shim_bwt_t *BWT, shim_reads_t *reads, bwb_params *params, char *a
 }
 
 int align_reads_inexact(void *BWT, void *reads, void *precalc_sa_intervals_table, void *params, char *alnFname) {
-    (void)precalc_sa_intervals_table;
-    return run((shim_bwt_t *)BWT, (shim_reads_t *)reads, (bwb_params *)params, alnFname, "BWBBLE Inexact Alignment...\n");
+    return run((shim_bwt_t *)BWT, (shim_reads_t *)reads, (const shim_sa_intv_list_t *)precalc_sa_intervals_table,
+               (bwb_params *)params, alnFname, "BWBBLE Inexact Alignment...\n");
 }
 
 int align_reads_inexact_parallel(void *BWT, void *reads, void *precalc_sa_intervals_table, void *params, char *alnFname) {
-    (void)precalc_sa_intervals_table;
-    return run((shim_bwt_t *)BWT, (shim_reads_t *)reads, (bwb_params *)params, alnFname, "BWT-SNP Inexact Alignment...\n");
+    return run((shim_bwt_t *)BWT, (shim_reads_t *)reads, (const shim_sa_intv_list_t *)precalc_sa_intervals_table,
+               (bwb_params *)params, alnFname, "BWT-SNP Inexact Alignment...\n");
 }

@@ -129,6 +129,25 @@ int bwb_occ_alphabet(bwb_ctx *ctx, const uint64_t *pos, uint64_t n, int inc, uin
 int bwb_occ_bench(bwb_ctx *ctx, uint64_t n, uint64_t seed, int mode, int iters, float *ms_per_launch,
                   uint64_t *checksum);
 
+/* ---- -P seed table -------------------------------------------------------- */
+/* `bwbble align -P` starts every search from the exact-match intervals of the read's last 12
+ * (reverse-complement) bases, looked up in a 4^12-row table that precalc_sa_intervals()
+ * (align.c:200-224) computes with exact_match() and stores as <fasta>.pre.  A read with an N among
+ * those bases, or shorter than 12, gets no alignments (inexact_match.c:50-57; the reference reads
+ * out of bounds for the latter).  bwb_params.use_precalc = 1 needs one of these first: */
+/* K0c: compute the table on the device (is_multiref = 0 for the -S flavour) */
+int bwb_precalc_build(bwb_ctx *ctx, int is_multiref);
+/* the table as the reference holds it after load_precalc_sa_intervals (align.c:226-238):
+ * sizes[4^12] and the rows' (L,U) pairs concatenated in row order */
+int bwb_precalc_upload(bwb_ctx *ctx, const int32_t *sizes, const uint64_t *intervals_LU, uint64_t n_intervals,
+                       int is_multiref);
+/* read / write a .pre file, byte-identical to the reference's (align.c:144-172) */
+int bwb_precalc_load_file(bwb_ctx *ctx, const char *pre_path, int is_multiref);
+int bwb_precalc_write(bwb_ctx *ctx, const char *pre_path);
+uint64_t bwb_precalc_num_intervals(const bwb_ctx *ctx);
+/* one row (tests): *n = its size, up to cap (L,U) pairs copied */
+int bwb_precalc_row(const bwb_ctx *ctx, uint32_t row, uint64_t *intervals_LU, uint32_t cap, uint32_t *n);
+
 /* ---- search ---------------------------------------------------------------------------- */
 /* seq: nt4 codes (A0 G1 C2 T3, anything else = N) of the FORWARD reads, concatenated;
  * offsets: n_reads+1 entries.  Reads longer than 255 are rejected (8-bit positions, align.h:104). */

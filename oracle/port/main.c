@@ -59,7 +59,7 @@ int main(int argc, char **argv) {
     }
     orc_params p; orc_default_params(&p);
     int c;
-    while ((c = getopt(argc - 1, argv + 1, "M:O:E:n:k:o:e:l:m:t:S")) >= 0) {
+    while ((c = getopt(argc - 1, argv + 1, "M:O:E:n:k:o:e:l:m:t:SP")) >= 0) {
         switch (c) {
             case 'M': p.mm_score = atoi(optarg); break;
             case 'O': p.gapo_score = atoi(optarg); break;
@@ -72,6 +72,7 @@ int main(int argc, char **argv) {
             case 'm': p.max_entries = atoi(optarg); break;
             case 't': p.n_threads = atoi(optarg); break;
             case 'S': p.is_multiref = 0; break;
+            case 'P': p.use_precalc = 1; break;
             default: return 1;
         }
     }

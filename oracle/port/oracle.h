@@ -26,6 +26,8 @@ extern "C" {
 #define ORC_SA_INTERVAL 32     /* bwt.h:16 */
 #define ORC_READ_BATCH 0x40000 /* align.h:14 */
 #define ORC_PATH_ALLOC 256     /* align.h:21 */
+#define ORC_PRECALC_LEN 12     /* PRECALC_INTERVAL_LENGTH, align.h:31 */
+#define ORC_NUM_PRECALC 16777216u /* NUM_PRECALC = 4^12, align.h:30 */
 
 /* FM-index container; field meaning as bwt_t (bwt.h:19-40), file layout as store_bwt (bwt.c:66-82) */
 typedef struct {
@@ -77,6 +79,9 @@ void orc_list_add(orc_list *l, uint64_t L, uint64_t U);                        /
 int orc_exact_match_bounded(const orc_bwt *b, const uint8_t *read, int i, uint64_t l, uint64_t u,
                             const orc_params *p, orc_list *out);
 /* inexact_match.c:171-254.  D has len+1 entries. */
+/* -P: row index of a read (align.c:174-186) and one row of the .pre table (align.c:200-224) */
+long orc_read2index(const uint8_t *read, int len);
+int orc_precalc_entry(const orc_bwt *b, const orc_params *p, uint32_t index, orc_list *out);
 void orc_calculate_d(const orc_bwt *b, const uint8_t *read, int len, orc_dbound *D, const orc_params *p);
 
 /* Whole-batch driver, inexact_match.c:25-168.  seq = nt4 codes of the FORWARD reads, concatenated;

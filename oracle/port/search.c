@@ -256,14 +256,22 @@ static void free_hits(hits_t *hs) {
 }
 
 /* ---- inexact_match, inexact_match.c:256-506 ---------------------------------------- */
-static void inexact_match(const orc_bwt *b, const uint8_t *rc, int len, heap_t *heap, const orc_params *p,
-                          const orc_dbound *D, const orc_dbound *Ds, hits_t *hits) {
+static void inexact_match(const orc_bwt *b, const uint8_t *rc, int len, heap_t *heap, const orc_list *pre,
+                          const orc_params *p, const orc_dbound *D, const orc_dbound *Ds, hits_t *hits) {
     int nN = 0;
     for (int i = 0; i < len; i++) nN += rc[i] > 3;
     if (nN > p->max_diff) return;
 
     heap_clear(heap);
-    heap_push(heap, len, 0, b->length - 1, 0, 0, 0, 0, 0, NULL, p);
+    if (pre) {                                      /* -P seeds, inexact_match.c:269-279 */
+        if (pre->n == 0) return;
+        entry_t seed; memset(&seed, 0, sizeof seed);
+        seed.alen = ORC_PRECALC_LEN - 1;            /* 11 matches; the push appends the 12th */
+        for (int k = 0; k < pre->n; k++)
+            heap_push(heap, len - ORC_PRECALC_LEN, pre->v[k].L, pre->v[k].U, 0, 0, 0, 0, 0, &seed, p);
+    } else {
+        heap_push(heap, len, 0, b->length - 1, 0, 0, 0, 0, 0, NULL, p);
+    }
 
     int best_score = score_of(p->max_diff + 1, p->max_gapo + 1, p->max_gape + 1, p);
     int max_diff = p->max_diff;
@@ -381,21 +389,47 @@ static void inexact_match(const orc_bwt *b, const uint8_t *rc, int len, heap_t *
 }
 
 /* ---- batch drivers, inexact_match.c:25-168 ------------------------------------------ */
-typedef struct { orc_dbound *D, *Ds; heap_t *heap; uint8_t *rc; } work_t;
+typedef struct { orc_dbound *D, *Ds; heap_t *heap; uint8_t *rc; orc_list pre; } work_t;
 
 static void work_init(work_t *w, int max_len, const orc_params *p) {
     w->D = calloc((size_t)max_len + 1, sizeof *w->D);
     w->Ds = calloc((size_t)p->seed_length + 1, sizeof *w->Ds);
     w->heap = heap_new(p);
     w->rc = malloc((size_t)max_len + 1);
+    memset(&w->pre, 0, sizeof w->pre);
 }
-static void work_free(work_t *w) { free(w->D); free(w->Ds); heap_del(w->heap); free(w->rc); }
+static void work_free(work_t *w) { free(w->D); free(w->Ds); heap_del(w->heap); free(w->rc); free(w->pre.v); }
+
+/* read2index, align.c:174-186: the last 12 bases as a base-4 number, <0 if any of them is N */
+long orc_read2index(const uint8_t *read, int len) {
+    long idx = 0;
+    for (int i = len - ORC_PRECALC_LEN; i < len; i++) {
+        if (read[i] > 3) return -1;
+        idx = idx * 4 + read[i];
+    }
+    return idx;
+}
+
+/* entry `index` of the .pre table: exact_match() of the 12-mer whose base-4 digits are `index`
+ * (most significant first; precalc_sa_intervals + next_read, align.c:188-224) */
+int orc_precalc_entry(const orc_bwt *b, const orc_params *p, uint32_t index, orc_list *out) {
+    uint8_t kmer[ORC_PRECALC_LEN];
+    for (int k = 0; k < ORC_PRECALC_LEN; k++) kmer[k] = (uint8_t)((index >> (2 * (ORC_PRECALC_LEN - 1 - k))) & 3u);
+    return orc_exact_match_bounded(b, kmer, ORC_PRECALC_LEN - 1, 0, b->length - 1, p, out);
+}
 
 static void align_one(const orc_bwt *b, const orc_params *p, const uint8_t *seq, int len, work_t *w, hits_t *hits) {
     for (int i = 0; i < len; i++) w->rc[len - 1 - i] = NT4_COMPL[seq[i] > 4 ? 4 : seq[i]];
+    const orc_list *pre = NULL;
+    if (p->use_precalc) {                           /* inexact_match.c:50-57: the table row of rc's last 12 bases */
+        long idx = len >= ORC_PRECALC_LEN ? orc_read2index(w->rc, len) : -1;
+        if (idx < 0) return;                        /* N among them: the read is skipped altogether */
+        orc_precalc_entry(b, p, (uint32_t)idx, &w->pre);   /* same list the table holds for this row */
+        pre = &w->pre;
+    }
     orc_calculate_d(b, seq, len, w->D, p);
     if (p->seed_length && len > p->seed_length) orc_calculate_d(b, seq, p->seed_length, w->Ds, p);
-    inexact_match(b, w->rc, len, w->heap, p, w->D, w->Ds, hits);
+    inexact_match(b, w->rc, len, w->heap, pre, p, w->D, w->Ds, hits);
 }
 
 static void stats_add(orc_stats *a, const orc_stats *t) {
@@ -408,7 +442,6 @@ static void stats_add(orc_stats *a, const orc_stats *t) {
 
 int orc_align(const orc_bwt *b, const orc_params *p, const uint8_t *seq, const uint64_t *offsets,
               uint64_t n_reads, uint8_t **aln, uint64_t *aln_len, orc_stats *stats) {
-    if (p->use_precalc) return -1;                  /* -P not restated */
     int nb = score_of(p->max_diff + 1, p->max_gapo + 1, p->max_gape + 1, p);
     if (nb <= 0) return -2;
     int max_len = 0;

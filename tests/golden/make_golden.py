@@ -8,7 +8,10 @@ seeded multi-genome + reads, and records what the real reference produces:
     g.fa.bwt.gz, g.fa.ann           `bwbble index g.fa`
     aln_<tag>.aln                   `bwbble align <flags> g.fa r.fq out.aln`   for every entry of GRID
     sam_<tag>.sam                   `bwbble aln2sam -n <n> g.fa r.fq out.aln out.sam` (SAM = "next" row)
+    aln_<tag>.aln for PGRID         the same with -P (12-mer seed table); the 68 MB g.fa.pre the
+                                    reference computes on the way is pinned by its md5 and its interval count
     manifest.json                   tag -> flags, md5 of every file
+`python tests/golden/make_golden.py --precalc-only` adds the PGRID files to an existing golden set.
 The reference repository ships no golden vectors of its own, so these ARE the pin.
 """
 import gzip
@@ -40,12 +43,51 @@ GRID = {
     "n4_m200": ["-n", "4", "-m", "200"],
 }
 
+# -P cases; multi-genome and -S tables differ, so each mode gets its own directory / .pre file
+PGRID = {
+    "P_n0": ["-P", "-n", "0"],
+    "P_n3": ["-P", "-n", "3"],
+    "P_n5": ["-P", "-n", "5"],
+    "P_n4_o2_e3_k3_l20": ["-P", "-n", "4", "-o", "2", "-e", "3", "-k", "3", "-l", "20"],
+    "SP_n3": ["-S", "-P", "-n", "3"],
+}
+
 
 def md5(path):
     return hashlib.md5(open(path, "rb").read()).hexdigest()
 
 
+def add_precalc(ref, manifest):
+    import numpy as np
+    import golden_util
+    run = lambda *a: subprocess.run([ref, *a], check=True, stdout=subprocess.DEVNULL)
+    manifest["pgrid"] = PGRID
+    manifest["pre"] = {}
+    for mode in ("multi", "single"):
+        with tempfile.TemporaryDirectory() as d:
+            fa = golden_util.materialise_index(d)
+            fq = os.path.join(HERE, "r.fq")
+            for tag, flags in PGRID.items():
+                if ("-S" in flags) != (mode == "single"):
+                    continue
+                aln = os.path.join(d, "out.aln")
+                run("align", *flags, fa, fq, aln)          # the first run of a mode writes g.fa.pre (minutes)
+                shutil.copy(aln, os.path.join(HERE, "aln_%s.aln" % tag))
+                manifest["md5"]["aln_%s.aln" % tag] = md5(aln)
+            raw = np.fromfile(fa + ".pre", dtype=np.uint8)
+            manifest["pre"][mode] = {"md5": md5(fa + ".pre"), "bytes": int(raw.size),
+                                     "intervals": int((raw.size - 4 * (1 << 24)) // 16)}
+
+
 def main():
+    if "--precalc-only" in sys.argv:
+        import oracle
+        ref = oracle.ensure_ref_binary()
+        assert ref, "/root/reference is required to (re)generate the golden files"
+        manifest = json.load(open(os.path.join(HERE, "manifest.json")))
+        add_precalc(ref, manifest)
+        json.dump(manifest, open(os.path.join(HERE, "manifest.json"), "w"), indent=1, sort_keys=True)
+        return
     import oracle
     from bwbble_b200 import synth
     ref = oracle.ensure_ref_binary()
@@ -85,6 +127,8 @@ def main():
                 manifest["md5"]["sam_%s.sam" % tag] = md5(sam)
         for f in ("g.fa", "r.fq", "g.fa.ann"):
             manifest["md5"][f] = md5(os.path.join(HERE, f))
+    json.dump(manifest, open(os.path.join(HERE, "manifest.json"), "w"), indent=1, sort_keys=True)
+    add_precalc(ref, manifest)
     json.dump(manifest, open(os.path.join(HERE, "manifest.json"), "w"), indent=1, sort_keys=True)
     print("golden files written to", HERE)
 

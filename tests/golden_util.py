@@ -14,8 +14,24 @@ def grid():
     return MANIFEST["grid"]
 
 
+def pgrid():
+    """-P cases (and -S -P): tag -> flags"""
+    return MANIFEST.get("pgrid", {})
+
+
 def flags_to_kwargs(flags):
-    return {_FLAG2FIELD[flags[i]]: int(flags[i + 1]) for i in range(0, len(flags), 2)}
+    kw, i = {}, 0
+    while i < len(flags):
+        if flags[i] == "-P":
+            kw["use_precalc"] = 1
+            i += 1
+        elif flags[i] == "-S":
+            kw["is_multiref"] = 0
+            i += 1
+        else:
+            kw[_FLAG2FIELD[flags[i]]] = int(flags[i + 1])
+            i += 2
+    return kw
 
 
 def golden_bytes(name):

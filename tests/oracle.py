@@ -58,6 +58,10 @@ def lib():
         L.orc_exact_match_bounded.restype = C.c_int
         L.orc_exact_match_bounded.argtypes = [C.POINTER(OrcBwt), C.c_void_p, C.c_int, C.c_uint64, C.c_uint64,
                                               C.POINTER(OrcParams), C.POINTER(OrcList)]
+        L.orc_precalc_entry.restype = C.c_int
+        L.orc_precalc_entry.argtypes = [C.POINTER(OrcBwt), C.POINTER(OrcParams), C.c_uint32, C.POINTER(OrcList)]
+        L.orc_read2index.restype = C.c_long
+        L.orc_read2index.argtypes = [C.c_void_p, C.c_int]
         L.orc_calculate_d.argtypes = [C.POINTER(OrcBwt), C.c_void_p, C.c_int, C.c_void_p, C.POINTER(OrcParams)]
         L.orc_align.restype = C.c_int
         L.orc_align.argtypes = [C.POINTER(OrcBwt), C.POINTER(OrcParams), C.c_void_p, C.c_void_p, C.c_uint64,
@@ -109,6 +113,17 @@ class Oracle:
             out = np.zeros((0, 2), dtype=np.uint64)
         else:
             out = np.frombuffer(C.string_at(lst.v, lst.n * 16), dtype=np.uint64).reshape(-1, 2).copy()
+        if lst.v:
+            lib().orc_free(lst.v)
+        return out
+
+    def precalc_entry(self, index: int, params=None) -> np.ndarray:
+        """row `index` of the reference's .pre table (align.c:200-224) as an (n, 2) array of (L, U)"""
+        p = to_orc_params(params)
+        lst = OrcList()
+        lib().orc_precalc_entry(self.h, C.byref(p), index, C.byref(lst))
+        out = (np.zeros((0, 2), dtype=np.uint64) if lst.n == 0 else
+               np.frombuffer(C.string_at(lst.v, lst.n * 16), dtype=np.uint64).reshape(-1, 2).copy())
         if lst.v:
             lib().orc_free(lst.v)
         return out

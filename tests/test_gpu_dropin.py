@@ -44,3 +44,22 @@ def test_dropin_single_genome_mode_equals_reference_binary(tmp_path):
         r = subprocess.run([binary, "align", "-S", "-n", "3", fa, fq, out], capture_output=True, text=True, timeout=600)
         assert r.returncode == 0, r.stdout[-1500:]
     assert open(a, "rb").read() == open(b, "rb").read()
+
+
+@pytest.mark.parametrize("tag", ["P_n3", "SP_n3"])
+def test_dropin_precalc_P(tmp_path, tag):
+    """`bwbble_gpu align -P`: the reference host loads <fasta>.pre (written here by K0c, so that the run does not
+    spend minutes in the reference's own precalc_sa_intervals) and hands the table to the shim."""
+    from bwbble_b200 import Aligner
+    fa = G.materialise_index(tmp_path)
+    fq = os.path.join(G.GOLDEN, "r.fq")
+    flags = G.pgrid()[tag]
+    with Aligner(heap_pool_mb=256) as al:
+        al.load_index(fa + ".bwt")
+        al.build_precalc("-S" not in flags)
+        al.write_precalc(fa + ".pre")
+    aln = str(tmp_path / "out.aln")
+    r = subprocess.run([GPU_BIN, "align", *flags, fa, fq, aln], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "Pre-calculating" not in r.stdout          # the table came from the file
+    assert open(aln, "rb").read() == G.golden_bytes("aln_%s.aln" % tag)

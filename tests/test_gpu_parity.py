@@ -362,3 +362,123 @@ def test_kmer_table_on_dense_genome(dense_case):
         assert (main[r] == exp).all(), "D read %d (len %d):\n got %s\n exp %s" % (r, len(rd), main[r].T, exp.T)
         exps = orc.calculate_d(rd, 20) if len(rd) > 20 else np.zeros((21, 2), dtype=np.int32)
         assert (seed[r] == exps).all()
+
+
+# ---- -P: 12-mer seed table ---------------------------------------------------------
+@pytest.fixture(scope="module")
+def precalc_case(tmp_path_factory):
+    """golden index + the seed tables K0c builds for it, written in the reference's .pre layout"""
+    import golden_util as G
+    from bwbble_b200.fastx import read_fastq
+    import os
+    d = tmp_path_factory.mktemp("pre")
+    fa = G.materialise_index(d)
+    reads = read_fastq(os.path.join(G.GOLDEN, "r.fq"))
+    pre = {}
+    with Aligner(heap_pool_mb=512) as al:
+        al.load_index(fa + ".bwt")
+        for mode, multi in (("multi", True), ("single", False)):
+            al.build_precalc(multi)
+            pre[mode] = str(d / ("g.%s.pre" % mode))
+            al.write_precalc(pre[mode])
+            assert al.precalc_num_intervals() == G.MANIFEST["pre"][mode]["intervals"]
+    return {"fa": fa, "reads": reads, "pre": pre}
+
+
+@pytest.mark.parametrize("mode", ["multi", "single"])
+def test_precalc_table_is_the_reference_pre_file(precalc_case, mode):
+    """K0c + the .pre writer against the file precalc_sa_intervals() wrote (md5 pinned in the manifest: 68 MB)"""
+    import golden_util as G
+    import hashlib
+    raw = open(precalc_case["pre"][mode], "rb").read()
+    assert len(raw) == G.MANIFEST["pre"][mode]["bytes"]
+    assert hashlib.md5(raw).hexdigest() == G.MANIFEST["pre"][mode]["md5"]
+
+
+@pytest.mark.parametrize("wide", [0, 1])
+def test_precalc_rows_equal_oracle(precalc_case, wide):
+    """rows of the device table against the restated exact_match(), incl. the rows the reads use"""
+    reads = precalc_case["reads"]
+    orc = oracle.Oracle(precalc_case["fa"] + ".bwt")
+    rng = np.random.default_rng(5)
+    rows = set(int(x) for x in rng.integers(0, 1 << 24, 300))
+    for r in range(reads.n):
+        s = reads.seq[int(reads.offsets[r]):int(reads.offsets[r + 1])]
+        if len(s) >= 12 and (s[:12] < 4).all():
+            rows.add(int(sum((3 - int(s[j])) << (2 * j) for j in range(12))))
+    try:
+        for multi in (True, False):
+            p = default_params(is_multiref=int(multi))
+            with Aligner(heap_pool_mb=256) as al:
+                if wide:
+                    al.set_option("force_wide", 1)
+                al.load_index(precalc_case["fa"] + ".bwt")
+                al.build_precalc(multi)
+                nonempty = 0
+                for x in sorted(rows):
+                    got, exp = al.precalc_row(x), orc.precalc_entry(x, p)
+                    assert got.shape == exp.shape and (got == exp).all(), (multi, x, got, exp)
+                    nonempty += len(exp) > 0
+                assert nonempty > 50
+    finally:
+        orc.close()
+
+
+def test_precalc_golden_files(precalc_case):
+    """`bwbble align -P ...` of the unmodified reference (tests/golden/aln_P_*.aln, aln_SP_n3.aln): table loaded
+    from the .pre file, 32- and 64-bit kernels"""
+    import golden_util as G
+    reads = precalc_case["reads"]
+    for wide in (0, 1):
+        for mode, multi in (("multi", 1), ("single", 0)):
+            with Aligner(heap_pool_mb=512) as al:
+                if wide:
+                    al.set_option("force_wide", 1)
+                al.load_index(precalc_case["fa"] + ".bwt")
+                al.load_precalc(precalc_case["pre"][mode], bool(multi))
+                for tag, flags in sorted(G.pgrid().items()):
+                    kw = G.flags_to_kwargs(flags)
+                    if kw.get("is_multiref", 1) != multi:
+                        continue
+                    got = al.align(reads.seq, reads.offsets, default_params(**kw)).aln_bytes()
+                    exp = G.golden_bytes("aln_%s.aln" % tag)
+                    assert got == exp, "%s wide=%d: %s" % (tag, wide, first_difference(got, exp))
+
+
+@pytest.mark.parametrize("kw", [dict(n=2), dict(n=5), dict(n=4, o=2, e=4, l=24, k=3), dict(n=3, is_multiref=0)],
+                         ids=lambda k: "-".join("%s%d" % kv for kv in k.items()))
+def test_precalc_align_equals_oracle_with_counters(small_case, kw):
+    """-P on the seeded synthetic case: .aln bytes and the pop/push counts of the restated search"""
+    reads = small_case["reads"]
+    p = default_params(use_precalc=1, **kw)
+    orc = oracle.Oracle(small_case["bwt"])
+    exp, st = orc.align(reads.seq, reads.offsets, p)
+    orc.close()
+    with Aligner(heap_pool_mb=512) as al:
+        al.load_index(small_case["bwt"])
+        al.build_precalc(bool(p.is_multiref))
+        res = al.align(reads.seq, reads.offsets, p)
+        got = res.aln_bytes()
+        assert got == exp, first_difference(got, exp)
+        ctr = res.counters()
+        assert ctr["pops"] == st["pops"] and ctr["pushes"] == st["pushes"]
+        dr = al.upload_reads(reads.seq, reads.offsets)
+        assert al.align_resident(dr, p, fetch=True).aln_bytes() == exp
+
+
+def test_precalc_misuse_fails_loudly(small_case):
+    from bwbble_b200 import BwbError
+    reads = small_case["reads"]
+    with Aligner(heap_pool_mb=256) as al:
+        al.load_index(small_case["bwt"])
+        with pytest.raises(BwbError):                    # no table yet
+            al.align(reads.seq, reads.offsets, default_params(n=2, use_precalc=1))
+        al.build_precalc(True)
+        with pytest.raises(BwbError):                    # table of the other mode
+            al.align(reads.seq, reads.offsets, default_params(n=2, use_precalc=1, is_multiref=0))
+    with Aligner(heap_pool_mb=256) as al:
+        al.set_option("engine", 1)
+        al.load_index(small_case["bwt"])
+        al.build_precalc(True)
+        with pytest.raises(BwbError):                    # only the production engine seeds from the table
+            al.align(reads.seq, reads.offsets, default_params(n=2, use_precalc=1))

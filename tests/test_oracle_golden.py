@@ -31,6 +31,17 @@ def test_oracle_reproduces_reference_aln(case, tag):
     assert stats["pops"] > 0
 
 
+@pytest.mark.parametrize("tag", sorted(G.pgrid()))
+def test_oracle_reproduces_reference_aln_with_precalc(case, tag):
+    """-P (SURVEY 8f #4): searches seeded from the 12-mer table, multi-genome and -S flavours"""
+    fa, reads, orc = case
+    kw = G.flags_to_kwargs(G.pgrid()[tag])
+    got, stats = orc.align(reads.seq, reads.offsets, default_params(**kw))
+    exp = G.golden_bytes("aln_%s.aln" % tag)
+    assert got == exp, "first difference (read, oracle, reference): %s" % (first_difference(got, exp),)
+    assert got != G.golden_bytes("aln_n3.aln")
+
+
 def test_golden_fixture_exercises_the_hard_cases():
     """gapped hits (I and D), multiple hits per read, unmapped reads, reads with N, 36..150 bp."""
     hits = parse_aln(G.golden_bytes("aln_n4_o2_e3_k3_l20.aln"))
