@@ -15,6 +15,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import weakref
 from typing import List, Optional, Sequence
 
 import numpy as np
@@ -164,6 +165,12 @@ class Aligner:
 
     def close(self):
         if getattr(self, "_ctx", None) and _lib is not None and _lib.lib is not None:
+            # device-resident read sets point into the context: release them first
+            for ref in list(getattr(self, "_children", ())):
+                obj = ref()
+                if obj is not None:
+                    obj.close()
+            self._children = []
             _lib.lib().bwb_destroy(self._ctx)
             self._ctx = None
 
@@ -323,7 +330,11 @@ class Aligner:
         h = C.c_void_p()
         _lib.check(_lib.lib().bwb_reads_upload(self._ctx, seq.ctypes.data, offsets.ctypes.data, len(offsets) - 1,
                                                C.byref(h)), self._ctx)
-        return DeviceReads(self, h.value, len(offsets) - 1)
+        dr = DeviceReads(self, h.value, len(offsets) - 1)
+        if not hasattr(self, "_children"):
+            self._children = []
+        self._children = [r for r in self._children if r() is not None] + [weakref.ref(dr)]
+        return dr
 
     def align_resident(self, reads: DeviceReads, params: Optional[Params] = None, fetch: bool = False) -> AlignResult:
         params = params or default_params()

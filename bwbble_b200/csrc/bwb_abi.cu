@@ -53,7 +53,7 @@ struct Device {
     uint32_t chunks_per_warp = 0, n_chunks = 0;
     // per-call buffers
     DevBuf seq, offsets, read_off, read_cnt, ordered_off, unordered, ordered, cub_tmp, small, d_main, d_seed, pool;
-    DevBuf pk_main, pk_seed, n_count, nxt, blk_link, heads;      // lane engine
+    DevBuf pk_main, pk_seed, n_count, nxt, blk_link, heads, order;      // lane engine
     DevBuf loc;                                                  // K6 output
     uint32_t slots_per_lane = 0, total_slots = 0, priv_total = 0;
     uint64_t auto_pool_bytes = 0;
@@ -84,6 +84,7 @@ struct bwb_ctx {
                               // 2 = 8-lane groups (k_calc_d_g + k_search_g); 1 and 2 are A/B baselines
     int use_ktab = 1;         // k-mer table for calculate_d's top of tree (0 = off, for A/B and tests)
     int force_wide = 0;       // tests: run the 64-bit / 32-byte-entry kernels on a small index
+    int heavy_first = 1;      // K3b: K4 takes reads in descending order of K3's whole-read bound (0 = input order)
     // -P seed table, host copy in row order (what a .pre file holds)
     bool have_pre = false;
     int pre_multiref = 1;
@@ -576,7 +577,7 @@ void bwb_destroy(bwb_ctx *ctx) {
         if (d.pre_cnt) cudaFree(d.pre_cnt);
         if (d.pre_iv) cudaFree(d.pre_iv);
         DevBuf *bufs[] = {&d.glists, &d.chunks, &d.chunk_link, &d.stage, &d.seq, &d.offsets, &d.read_off, &d.read_cnt,
-                          &d.ordered_off, &d.unordered, &d.ordered, &d.cub_tmp, &d.small, &d.d_main, &d.d_seed, &d.pool, &d.loc, &d.pk_main, &d.pk_seed, &d.n_count, &d.nxt, &d.blk_link, &d.heads};
+                          &d.ordered_off, &d.unordered, &d.ordered, &d.cub_tmp, &d.small, &d.d_main, &d.d_seed, &d.pool, &d.loc, &d.pk_main, &d.pk_seed, &d.n_count, &d.nxt, &d.blk_link, &d.heads, &d.order};
         for (DevBuf *b : bufs) release(*b);
         if (d.h_small) cudaFreeHost(d.h_small);
         if (d.ev0) cudaEventDestroy(d.ev0);
@@ -592,7 +593,7 @@ int bwb_device_count(const bwb_ctx *ctx) { return ctx ? (int)ctx->dev.size() : 0
 int bwb_set_option(bwb_ctx *ctx, const char *key, long long value) {
     if (!ctx || !key) return BWB_ERR_ARG;
     std::string k(key);
-    if (value <= 0 && k != "blocks_per_sm" && k != "force_wide" && k != "engine" && k != "heap_pool_mb" && k != "kmer_table") return fail(ctx, BWB_ERR_ARG, "option %s needs a positive value", key);
+    if (value <= 0 && k != "blocks_per_sm" && k != "force_wide" && k != "engine" && k != "heap_pool_mb" && k != "kmer_table" && k != "heavy_first") return fail(ctx, BWB_ERR_ARG, "option %s needs a positive value", key);
     if (k == "heap_pool_mb") ctx->heap_pool_mb = value;
     else if (k == "list_cap") ctx->list_cap = (int)(value < SL + 4 ? SL + 4 : value);
     else if (k == "hits_per_read") ctx->hits_per_read = (int)value;
@@ -607,6 +608,7 @@ int bwb_set_option(bwb_ctx *ctx, const char *key, long long value) {
         ctx->force_wide = nv;
     }
     else if (k == "kmer_table") ctx->use_ktab = value > 1 ? 0 : 1;
+    else if (k == "heavy_first") ctx->heavy_first = value > 1 ? 0 : 1;
     else if (k == "engine") ctx->engine = (value == 1 || value == 2) ? (int)value : 0;
     else return fail(ctx, BWB_ERR_ARG, "unknown option %s", key);
     for (auto &d : ctx->dev) {       // scratch is re-sized lazily
@@ -1055,11 +1057,11 @@ static int launch_shard(bwb_ctx *ctx, Device &d, const bwb_params *p, int nb, co
     if ((rc = ensure(ctx, d.ordered_off, (n + 1) * 8))) return rc;
     if ((rc = ensure(ctx, d.unordered, out_cap * sizeof(bwb_hit)))) return rc;
     if ((rc = ensure(ctx, d.ordered, out_cap * sizeof(bwb_hit)))) return rc;
-    if ((rc = ensure(ctx, d.small, 256))) return rc;
+    if ((rc = ensure(ctx, d.small, 512))) return rc;
     // small block: [0] K4 queue u32 | [4] K3 queue u32 | [8] status 2xu32 | [16] out_cursor u64 |
     // [24] shared-pool bump cursor u32 | [32..96) counters 8xu64 | [96] shared-pool free-list head u64
     unsigned char *sm = (unsigned char *)d.small.p;
-    CU(cudaMemsetAsync(sm, 0, 256, d.stream));
+    CU(cudaMemsetAsync(sm, 0, 512, d.stream));
     const uint32_t ovf0 = (uint32_t)d.n_warps * d.chunks_per_warp;
     CU(cudaMemcpyAsync(sm + 24, &ovf0, 4, cudaMemcpyHostToDevice, d.stream));
     if (ctx->engine == 0) {        // lane engine: shared blocks of LBLK slots above the private ranges
@@ -1144,10 +1146,23 @@ static int launch_shard(bwb_ctx *ctx, Device &d, const bwb_params *p, int nb, co
             k_calc_d_g<false><<<grid3, 256, smem3, d.stream>>>(c);
         }
         CU(cudaGetLastError());
+        // K3b: heavy reads first (counting sort on K3's whole-read bound); part of the K3 interval of the timing
+        uint32_t *order = nullptr;
+        if (ctx->heavy_first) {
+            if ((rc = ensure(ctx, d.order, (n + 1) * 4))) return rc;
+            order = (uint32_t *)d.order.p;
+            uint32_t *hist = (uint32_t *)(sm + 256), *cursor = hist + ORDER_CLASSES;
+            const int ogrid = (int)std::min<uint64_t>((n + 255) / 256, (uint64_t)d.sm_count * 8);
+            k_order_hist<<<ogrid, 256, 0, d.stream>>>(c.pk_main, c.n_count, a.offsets, a.n_reads, p->max_diff, hist);
+            CU(cudaGetLastError());
+            k_order_scatter<<<ogrid, 256, 0, d.stream>>>(c.pk_main, c.n_count, a.offsets, a.n_reads, p->max_diff, hist, cursor, order);
+            CU(cudaGetLastError());
+        }
         CU(cudaEventRecord(d.evm, d.stream));
         // K4: one read per lane
         LaneArgs g;
         memset(&g, 0, sizeof g);
+        g.order = order;
         g.ix = a.ix; g.seq = a.seq; g.offsets = a.offsets; g.n_reads = a.n_reads; g.read_id_base = a.read_id_base;
         g.max_diff = a.max_diff; g.max_gapo = a.max_gapo; g.max_gape = a.max_gape; g.max_entries = a.max_entries;
         g.mm_score = a.mm_score; g.gapo_score = a.gapo_score; g.gape_score = a.gape_score;

@@ -43,6 +43,7 @@ struct LaneArgs {
     uint32_t *queue;
     const uint16_t *pk_main, *pk_seed;       // packed lower bounds from K3
     const uint16_t *n_count;                 // N bases per read, from K3
+    const uint32_t *order;                   // read taken at queue position q (K3b: heavy reads first); null = q
     const uint32_t *pre_off, *pre_cnt;       // -P seed table (K0c), rows of `pre_iv`; only read by k_search_l<.., true>
     const ulonglong2 *pre_iv;                // 64-bit (L,U) whatever T is
     uint4 *slots;                            // arena: 2 x uint4 per slot
@@ -208,6 +209,66 @@ struct LaneHeap {
     }
 };
 
+// ---------------------------------------------------------------------------------------------
+// K3b: queue order for K4.  The cost of a read grows steeply with the whole-read lower bound
+// D[len-1] that K3 just computed (every entry scoring up to best+mm_score is expanded, and the best
+// score is at least D[len-1] mismatches away); reads whose bound already exceeds max_diff die at the
+// root.  Handing the expensive reads out FIRST (longest-processing-time-first) lets the cheap ones
+// fill the end of the launch, instead of a few lanes finishing a late heavy read while the rest of
+// the GPU idles.  Class = bound (0 = trivial), counting sort by descending class; the order inside a
+// class is arbitrary -- results are per read and K5 restores input order.
+// ---------------------------------------------------------------------------------------------
+constexpr int ORDER_CLASSES = 32;
+
+__device__ __forceinline__ uint32_t order_class(const uint16_t *pk_main, const uint16_t *n_count, const uint64_t *offsets,
+                                                uint32_t r, int max_diff) {
+    const uint64_t off = offsets[r];
+    const int len = (int)(offsets[r + 1] - off);
+    if (len <= 0 || (int)n_count[r] > max_diff) return 0u;
+    const int z = (int)(pk_main[off + r + (uint64_t)(len - 1)] & 0x1ffu);
+    if (z > max_diff) return 0u;
+    return (uint32_t)(1 + (z < ORDER_CLASSES - 2 ? z : ORDER_CLASSES - 2));
+}
+
+__global__ void k_order_hist(const uint16_t *__restrict__ pk_main, const uint16_t *__restrict__ n_count,
+                             const uint64_t *__restrict__ offsets, uint32_t n_reads, int max_diff, uint32_t *hist) {
+    __shared__ uint32_t sh[ORDER_CLASSES];
+    if (threadIdx.x < ORDER_CLASSES) sh[threadIdx.x] = 0;
+    __syncthreads();
+    for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < n_reads; r += gridDim.x * blockDim.x)
+        atomicAdd(&sh[order_class(pk_main, n_count, offsets, r, max_diff)], 1u);
+    __syncthreads();
+    if (threadIdx.x < ORDER_CLASSES && sh[threadIdx.x]) atomicAdd(&hist[threadIdx.x], sh[threadIdx.x]);
+}
+
+// same grid as k_order_hist; cursor[] zeroed
+__global__ void k_order_scatter(const uint16_t *__restrict__ pk_main, const uint16_t *__restrict__ n_count,
+                                const uint64_t *__restrict__ offsets, uint32_t n_reads, int max_diff,
+                                const uint32_t *__restrict__ hist, uint32_t *cursor, uint32_t *__restrict__ order) {
+    __shared__ uint32_t start[ORDER_CLASSES], cnt[ORDER_CLASSES], base[ORDER_CLASSES];
+    if (threadIdx.x < ORDER_CLASSES) {
+        uint32_t s = 0;
+        for (int c = ORDER_CLASSES - 1; c > (int)threadIdx.x; c--) s += hist[c];      // heavier classes come first
+        start[threadIdx.x] = s;
+    }
+    for (uint32_t r0 = blockIdx.x * blockDim.x; r0 < n_reads; r0 += gridDim.x * blockDim.x) {     // block-uniform trip count
+        if (threadIdx.x < ORDER_CLASSES) cnt[threadIdx.x] = 0;
+        __syncthreads();
+        const uint32_t r = r0 + threadIdx.x;
+        uint32_t cls = 0, rank = 0;
+        if (r < n_reads) {
+            cls = order_class(pk_main, n_count, offsets, r, max_diff);
+            rank = atomicAdd(&cnt[cls], 1u);
+        }
+        __syncthreads();
+        if (threadIdx.x < ORDER_CLASSES && cnt[threadIdx.x])
+            base[threadIdx.x] = start[threadIdx.x] + atomicAdd(&cursor[threadIdx.x], cnt[threadIdx.x]);
+        __syncthreads();
+        if (r < n_reads) order[base[cls] + rank] = r;
+        __syncthreads();
+    }
+}
+
 // A/B on B200 (chr21-scale, -n 5): 3 blocks of 128 lanes per SM (168 registers, no spills) with the
 // checkpoint counters fetched as 128-bit loads beat 4 blocks (128 registers, spills) by 1.4x.
 #ifndef BWB_LANE_CNT32
@@ -288,6 +349,7 @@ __global__ void __launch_bounds__(128, BWB_LANE_MIN_BLOCKS) k_search_l(const __g
             if (r >= a.n_reads) mode = DONE;
         }
         if (mode == NEED) {
+            if (a.order) r = a.order[r];
             off = a.offsets[r];
             len = (int)(a.offsets[r + 1] - off);
             read_id = a.read_id_base + r;

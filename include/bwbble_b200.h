@@ -177,7 +177,7 @@ int bwb_align(bwb_ctx *ctx, const bwb_params *params, const uint8_t *seq, const 
 /* Device-resident variant: upload once, align many times (bench `value`; no PCIe in the loop). */
 int bwb_reads_upload(bwb_ctx *ctx, const uint8_t *seq, const uint64_t *offsets, uint64_t n_reads,
                      bwb_reads **out);
-void bwb_reads_free(bwb_reads *r);
+void bwb_reads_free(bwb_reads *r);   /* before bwb_destroy() of the context the reads were uploaded to */
 /* Runs the kernels on the context's stream(s); results stay on the device until
  * bwb_results_fetch() (fetch==0: no bulk D2H, only the 256-byte status block is read back). */
 int bwb_align_resident(bwb_ctx *ctx, const bwb_params *params, const bwb_reads *reads, int fetch,

@@ -21,6 +21,10 @@ if eng:
     al.set_option('engine', eng)
 if bps:
     al.set_option('blocks_per_sm', bps)
+opts = os.environ.get('ENG_OPTS', '')
+for kv in filter(None, opts.split(',')):
+    k, v = kv.split('=')
+    al.set_option(k, int(v))
 al.load_index(fa + '.bwt')
 dr = al.upload_reads(b.seq, b.offsets)
 p = default_params(n=5, use_precalc=int(use_p))
@@ -33,6 +37,6 @@ for it in range(2):
     r = al.align_resident(dr, p, fetch=False)
     ms, k3, c = r.kernel_ms, r.k3_ms, r.counters()
     r.close()
-print("RESULT " + json.dumps({'lib': os.environ.get('BWBBLE_B200_LIB', 'default').split('/')[-1], 'engine': eng,
+print("RESULT " + json.dumps({'lib': os.environ.get('BWBBLE_B200_LIB', 'default').split('/')[-1], 'engine': eng, 'opts': opts,
                               'batch': batch, 'bps': bps, 'k4_ms': ms, 'k3_ms': k3, 'precalc_build_s': pre_s, 'pre_intervals': al.precalc_num_intervals() if use_p else 0,
                               'reads_per_s': batch / (ms + k3) * 1e3, 'pops': c['pops']}))

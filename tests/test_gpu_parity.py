@@ -482,3 +482,21 @@ def test_precalc_misuse_fails_loudly(small_case):
         al.build_precalc(True)
         with pytest.raises(BwbError):                    # only the production engine seeds from the table
             al.align(reads.seq, reads.offsets, default_params(n=2, use_precalc=1))
+
+
+def test_heavy_first_queue_order_is_result_neutral(small_case):
+    """K3b only changes the order in which K4 takes the reads: bytes and the pop/push totals stay the oracle's"""
+    reads = small_case["reads"]
+    p = default_params(n=4)
+    orc = oracle.Oracle(small_case["bwt"])
+    exp, st = orc.align(reads.seq, reads.offsets, p)
+    orc.close()
+    for opt in (1, 2):                                   # 1 = on (default), 2 = input order
+        with Aligner(heap_pool_mb=512) as al:
+            al.set_option("heavy_first", opt)
+            al.load_index(small_case["bwt"])
+            res = al.align(reads.seq, reads.offsets, p)
+            got = res.aln_bytes()
+            assert got == exp, (opt, first_difference(got, exp))
+            ctr = res.counters()
+            assert ctr["pops"] == st["pops"] and ctr["pushes"] == st["pushes"]
