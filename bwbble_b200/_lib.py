@@ -78,6 +78,7 @@ SIGNATURES = {
     "bwb_results_free": (None, [C.c_void_p]),
     "bwb_free": (None, [C.c_void_p]),
     "bwb_index_build": (C.c_int, [C.c_char_p, C.c_int]),
+    "bwb_index_build_device": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int, C.POINTER(C.c_int)]),
     "bwb_align_fastq": (C.c_longlong, [C.c_void_p, C.POINTER(Params), C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p,
                                        C.c_uint64, C.c_int, C.c_uint64]),
     "bwb_sa_upload": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64]),

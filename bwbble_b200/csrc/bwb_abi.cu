@@ -385,7 +385,7 @@ int build_ktab(bwb_ctx *ctx, Device &d) {
     CU(cudaMalloc(&d.ktab_cnt, (size_t)nk * 4));
     CU(cudaMalloc(&gl, (size_t)n_warps * 2 * ctx->list_cap * sizeof(ulonglong2)));
     CU(cudaMalloc(&sm, 64));
-    unsigned long long cap = 8ull << 20;
+    unsigned long long cap = std::max<unsigned long long>(8ull << 20, ctx->length / 8);
     const size_t pair = wide ? 16 : 8;
     for (int attempt = 0; attempt < 6; attempt++) {
         CU(cudaMalloc(&d.ktab_iv, cap * pair));
@@ -1391,6 +1391,13 @@ void bwb_free(void *p) { free(p); }
 
 // serialisation lives in aln_io.cpp; it needs the private layout of bwb_results
 namespace bwb_host {
+int ctx_device(const bwb_ctx *ctx, int *device_id, void **stream) {
+    if (!ctx || ctx->dev.empty()) return BWB_ERR_ARG;
+    *device_id = ctx->dev[0].id;
+    *stream = (void *)ctx->dev[0].stream;
+    return BWB_OK;
+}
+int ctx_fail(bwb_ctx *ctx, int code, const char *msg) { return fail(ctx, code, "%s", msg); }
 const std::vector<uint32_t> &results_counts(const bwb_results *r) { return r->counts; }
 const std::vector<bwb_hit> &results_hits(const bwb_results *r) { return r->hits; }
 bool results_fetched(const bwb_results *r) { return r->fetched; }

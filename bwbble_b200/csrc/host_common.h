@@ -3,6 +3,8 @@
 #include <cstdint>
 #include <vector>
 
+struct bwb_ctx;
+
 namespace bwb_host {
 
 // In-memory image of a .bwt file (store_bwt layout, mg-aligner/bwt.c:66-82; fields of bwt_t,
@@ -18,6 +20,11 @@ struct HostIndex {
 int build_index_arrays(const uint8_t *text, uint64_t n, HostIndex &ix);
 int write_bwt_file(const HostIndex &ix, const char *path);
 int read_bwt_file(const char *path, HostIndex &ix, bool load_sa);
+int prepare_index_text(const char *fasta_path, int write_ref_file, std::vector<uint8_t> &text);
+
+// device 0 of a context and its launch stream (cudaStream_t as void*), for host modules outside bwb_abi.cu
+int ctx_device(const struct ::bwb_ctx *ctx, int *device_id, void **stream);
+int ctx_fail(struct ::bwb_ctx *ctx, int code, const char *msg);
 
 // .pre file of `bwbble align -P` (store_sa_interval_list / load_sa_interval_list, align.c:144-172,
 // written row by row by precalc_sa_intervals, align.c:200-224): 4^12 records {int32 n; n x (u64 L, u64 U)}

@@ -274,7 +274,11 @@ int read_bwt_file(const char *path, HostIndex &ix, bool load_sa) {
 
 }  // namespace bwb_host
 
-extern "C" int bwb_index_build(const char *fasta_path, int write_ref_file) {
+namespace bwb_host {
+
+// Everything of `bwbble index` before the suffix sort (fasta2ref, io.c; bwt.c:29-63): parse the FASTA, write
+// <fasta>.ann (and .ref), return the text = forward codes + '$' per record, followed by its reverse complement.
+int prepare_index_text(const char *fasta_path, int write_ref_file, std::vector<uint8_t> &text) {
     if (!fasta_path) return BWB_ERR_ARG;
     FILE *f = fopen(fasta_path, "rb");
     if (!f) return BWB_ERR_IO;
@@ -285,7 +289,6 @@ extern "C" int bwb_index_build(const char *fasta_path, int write_ref_file) {
     if (sz > 0 && fread(file.data(), 1, (size_t)sz, f) != (size_t)sz) { fclose(f); return BWB_ERR_IO; }
     fclose(f);
 
-    std::vector<uint8_t> text;
     std::vector<AnnRecord> ann;
     int rc = parse_fasta(file, text, ann);
     if (rc) return rc;
@@ -309,6 +312,16 @@ extern "C" int bwb_index_build(const char *fasta_path, int write_ref_file) {
         fwrite(text.data(), 1, text.size(), r);
         fclose(r);
     }
+    return BWB_OK;
+}
+
+}  // namespace bwb_host
+
+extern "C" int bwb_index_build(const char *fasta_path, int write_ref_file) {
+    std::vector<uint8_t> text;
+    int rc = bwb_host::prepare_index_text(fasta_path, write_ref_file, text);
+    if (rc) return rc;
+    std::string base(fasta_path);
     bwb_host::HostIndex ix;
     rc = bwb_host::build_index_arrays(text.data(), text.size(), ix);
     if (rc) return rc;

@@ -50,9 +50,17 @@ def load_bwt(path: str, load_sa: bool = False) -> BwtIndex:
     return BwtIndex(length, sa0, C, bwt, O, SA)
 
 
-def build_index(fasta_path: str, write_ref: bool = False) -> str:
+def build_index(fasta_path: str, write_ref: bool = False, aligner=None) -> str:
     """`bwbble index <fasta>` (bwt.c:29-63): writes <fasta>.bwt and <fasta>.ann with the native
-    host builder (bwbble_b200/csrc/index_build.cpp).  Returns the .bwt path."""
+    host builder (bwbble_b200/csrc/index_build.cpp) or, given an Aligner, with the suffix sort and the
+    BWT / checkpoint passes on its first device (K7, index_build_gpu.cu).  Returns the .bwt path."""
+    if aligner is not None:
+        import ctypes as C
+        rounds = C.c_int(0)
+        rc = _lib.lib().bwb_index_build_device(aligner._ctx, os.fsencode(fasta_path), int(write_ref), C.byref(rounds))
+        _lib.check(rc, aligner._ctx)
+        aligner.last_index_sort_rounds = rounds.value
+        return fasta_path + ".bwt"
     rc = _lib.lib().bwb_index_build(os.fsencode(fasta_path), int(write_ref))
     _lib.check(rc)
     return fasta_path + ".bwt"

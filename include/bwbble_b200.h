@@ -235,6 +235,10 @@ long long bwb_align_fastq(bwb_ctx *ctx, const bwb_params *params, const char *fa
 /* Builds <fasta>.bwt and <fasta>.ann byte-identical to the reference's `bwbble index <fasta>`
  * (io.c:190-321 fasta2ref, bwt.c:161-218 construct_bwt, is.c:214-243) with an own SA-IS. */
 int bwb_index_build(const char *fasta_path, int write_ref_file);
+/* K7: the same files with the suffix sort (prefix doubling) and the BWT / checkpoint / SA-sample passes on
+ * device 0 of ctx (bwt.c:161-218 on the GPU); indexes of < 2^31-16 rows.  *sort_rounds (optional) = number of
+ * doubling rounds the suffix sort took. */
+int bwb_index_build_device(bwb_ctx *ctx, const char *fasta_path, int write_ref_file, int *sort_rounds);
 
 #ifdef __cplusplus
 }

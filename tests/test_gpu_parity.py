@@ -500,3 +500,43 @@ def test_heavy_first_queue_order_is_result_neutral(small_case):
             assert got == exp, (opt, first_difference(got, exp))
             ctr = res.counters()
             assert ctr["pops"] == st["pops"] and ctr["pushes"] == st["pushes"]
+
+
+# ---- K7: index construction on the device (SURVEY 8f #4b) --------------------------------------------
+def test_device_index_build_equals_the_reference_files(tmp_path):
+    """`bwbble index g.fa` of the unmodified reference (tests/golden/g.fa.bwt.gz, .ann) rebuilt with the suffix
+    sort on the GPU: byte-identical .bwt (header, C, packed BWT, checkpoints O, SA samples) and .ann"""
+    import golden_util as G
+    import hashlib
+    from bwbble_b200 import index
+    fa = str(tmp_path / "g.fa")
+    open(fa, "wb").write(G.golden_bytes("g.fa"))
+    with Aligner(heap_pool_mb=64) as al:
+        index.build_index(fa, aligner=al)
+        assert al.last_index_sort_rounds >= 2
+    assert hashlib.md5(open(fa + ".bwt", "rb").read()).hexdigest() == G.MANIFEST["md5"]["g.fa.bwt"]
+    assert open(fa + ".ann", "rb").read() == G.golden_bytes("g.fa.ann")
+
+
+def test_device_index_build_equals_host_builder_on_deep_repeats(tmp_path):
+    """long N runs, exact repeats and microsatellites: LCPs of tens of thousands, many doubling rounds"""
+    from bwbble_b200 import index, synth
+    g = synth.make_genome(77, 400_000, n_records=3, snp_rate=0.012, tri_frac=0.05, n_bubbles=60, n_frac=0.3,
+                          n_repeat_copies=6, repeat_len=3000, n_microsats=4, lowercase_frac=0.01)
+    a, b = str(tmp_path / "a.fa"), str(tmp_path / "b.fa")
+    g.write_fasta(a)
+    g.write_fasta(b)
+    index.build_index(a)
+    with Aligner(heap_pool_mb=64) as al:
+        index.build_index(b, aligner=al)
+        assert al.last_index_sort_rounds >= 10
+        # and the device-built index maps reads like the host-built one
+        reads = synth.make_reads(g, 78, 300, 100, 2, indel_frac=0.2)
+        al.load_index(b + ".bwt")
+        got = al.align(reads.seq, reads.offsets, default_params(n=3)).aln_bytes()
+    assert open(a + ".bwt", "rb").read() == open(b + ".bwt", "rb").read()
+    assert open(a + ".ann", "rb").read() == open(b + ".ann", "rb").read()
+    orc = oracle.Oracle(a + ".bwt")
+    exp, _ = orc.align(reads.seq, reads.offsets, default_params(n=3))
+    orc.close()
+    assert got == exp, first_difference(got, exp)
