@@ -22,7 +22,7 @@
 
 #include "bwbble_b200.h"
 
-#define SHIM_READ_BATCH 0x400000         /* 16 x READ_BATCH_SIZE (align.h:14): the device needs millions of
+#define SHIM_READ_BATCH 0x800000         /* 32 x READ_BATCH_SIZE (align.h:14): the device needs millions of
                                            reads per launch to amortise the per-launch tail; the records
                                            and their order in the .aln file do not depend on the batching */
 
