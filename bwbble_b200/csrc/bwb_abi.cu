@@ -53,7 +53,7 @@ struct Device {
     uint32_t chunks_per_warp = 0, n_chunks = 0;
     // per-call buffers
     DevBuf seq, offsets, read_off, read_cnt, ordered_off, unordered, ordered, cub_tmp, small, d_main, d_seed, pool;
-    DevBuf pk_main, pk_seed, n_count, nxt, blk_link, heads, order;      // lane engine
+    DevBuf pk_main, pk_seed, n_count, nxt, blk_link, heads, order, retry;      // lane engine
     DevBuf loc;                                                  // K6 output
     uint32_t slots_per_lane = 0, total_slots = 0, priv_total = 0;
     uint64_t auto_pool_bytes = 0;
@@ -313,8 +313,8 @@ int prepare_search_lane(bwb_ctx *ctx, Device &d, int nb, bool wide) {
             else {
                 size_t fr = 0, tot = 0;
                 CU(cudaMemGetInfo(&fr, &tot));
-                pool_bytes = (uint64_t)fr / 2;
-                if (pool_bytes > (64ull << 30)) pool_bytes = 64ull << 30;
+                pool_bytes = (uint64_t)fr / 5 * 3;
+                if (pool_bytes > (128ull << 30)) pool_bytes = 128ull << 30;
                 d.auto_pool_bytes = pool_bytes;
             }
         }
@@ -577,7 +577,7 @@ void bwb_destroy(bwb_ctx *ctx) {
         if (d.pre_cnt) cudaFree(d.pre_cnt);
         if (d.pre_iv) cudaFree(d.pre_iv);
         DevBuf *bufs[] = {&d.glists, &d.chunks, &d.chunk_link, &d.stage, &d.seq, &d.offsets, &d.read_off, &d.read_cnt,
-                          &d.ordered_off, &d.unordered, &d.ordered, &d.cub_tmp, &d.small, &d.d_main, &d.d_seed, &d.pool, &d.loc, &d.pk_main, &d.pk_seed, &d.n_count, &d.nxt, &d.blk_link, &d.heads, &d.order};
+                          &d.ordered_off, &d.unordered, &d.ordered, &d.cub_tmp, &d.small, &d.d_main, &d.d_seed, &d.pool, &d.loc, &d.pk_main, &d.pk_seed, &d.n_count, &d.nxt, &d.blk_link, &d.heads, &d.order, &d.retry};
         for (DevBuf *b : bufs) release(*b);
         if (d.h_small) cudaFreeHost(d.h_small);
         if (d.ev0) cudaEventDestroy(d.ev0);
@@ -1059,7 +1059,8 @@ static int launch_shard(bwb_ctx *ctx, Device &d, const bwb_params *p, int nb, co
     if ((rc = ensure(ctx, d.ordered, out_cap * sizeof(bwb_hit)))) return rc;
     if ((rc = ensure(ctx, d.small, 512))) return rc;
     // small block: [0] K4 queue u32 | [4] K3 queue u32 | [8] status 2xu32 | [16] out_cursor u64 |
-    // [24] shared-pool bump cursor u32 | [32..96) counters 8xu64 | [96] shared-pool free-list head u64
+    // [24] shared-pool bump cursor u32 | [32..96) counters 8xu64 | [96] shared-pool free-list head u64 |
+    // [112],[116] queues of K4's retry passes | [120],[124] their lengths (deferred-read counts) | [256..512) K3b
     unsigned char *sm = (unsigned char *)d.small.p;
     CU(cudaMemsetAsync(sm, 0, 512, d.stream));
     const uint32_t ovf0 = (uint32_t)d.n_warps * d.chunks_per_warp;
@@ -1175,12 +1176,29 @@ static int launch_shard(bwb_ctx *ctx, Device &d, const bwb_params *p, int nb, co
         g.out_hits = a.out_hits; g.out_cap = a.out_cap; g.out_cursor = a.out_cursor;
         g.read_off = a.read_off; g.read_cnt = a.read_cnt; g.status = a.status; g.counters = a.counters;
         g.pre_off = d.pre_off; g.pre_cnt = d.pre_cnt; g.pre_iv = d.pre_iv;
-        if (p->use_precalc) {
-            if (wide) k_search_l<true, true><<<d.grid, 128, d.smem_bytes, d.stream>>>(g);
-            else k_search_l<false, true><<<d.grid, 128, d.smem_bytes, d.stream>>>(g);
-        } else {
-            if (wide) k_search_l<true, false><<<d.grid, 128, d.smem_bytes, d.stream>>>(g);
-            else k_search_l<false, false><<<d.grid, 128, d.smem_bytes, d.stream>>>(g);
+        // three passes: all reads; the reads pass 0 deferred for lack of arena; what pass 1 deferred (an
+        // overflow there is reported).  Passes 1 and 2 read their queue length on the device: no host sync,
+        // and an empty pass costs a few microseconds.
+        if ((rc = ensure(ctx, d.retry, 2 * (n + 1) * 4))) return rc;
+        uint32_t *rl0 = (uint32_t *)d.retry.p, *rl1 = rl0 + (n + 1);
+        for (int pass = 0; pass < 3; pass++) {
+            g.lane_stride = pass == 0 ? 1u : (pass == 1 ? 8u : 64u);      // 8x, then 64x the arena per read in flight
+            if (pass == 0) { g.retry_list = rl0; g.retry_count = (uint32_t *)(sm + 120); }
+            else if (pass == 1) {
+                g.order = rl0; g.n_queue_ptr = (const uint32_t *)(sm + 120); g.queue = (uint32_t *)(sm + 112);
+                g.retry_list = rl1; g.retry_count = (uint32_t *)(sm + 124);
+            } else {
+                g.order = rl1; g.n_queue_ptr = (const uint32_t *)(sm + 124); g.queue = (uint32_t *)(sm + 116);
+                g.retry_list = nullptr; g.retry_count = nullptr;
+            }
+            if (p->use_precalc) {
+                if (wide) k_search_l<true, true><<<d.grid, 128, d.smem_bytes, d.stream>>>(g);
+                else k_search_l<false, true><<<d.grid, 128, d.smem_bytes, d.stream>>>(g);
+            } else {
+                if (wide) k_search_l<true, false><<<d.grid, 128, d.smem_bytes, d.stream>>>(g);
+                else k_search_l<false, false><<<d.grid, 128, d.smem_bytes, d.stream>>>(g);
+            }
+            CU(cudaGetLastError());
         }
         CU(cudaGetLastError());
     } else if (n) {

@@ -44,6 +44,10 @@ struct LaneArgs {
     const uint16_t *pk_main, *pk_seed;       // packed lower bounds from K3
     const uint16_t *n_count;                 // N bases per read, from K3
     const uint32_t *order;                   // read taken at queue position q (K3b: heavy reads first); null = q
+    const uint32_t *n_queue_ptr;             // retry passes: queue length lives on the device (null: n_reads)
+    uint32_t *retry_list, *retry_count;      // reads that ran out of arena are deferred to the next pass (null: fail)
+    uint32_t lane_stride;                    // retry passes: only every lane_stride-th lane works, and owns the
+                                             // private ranges of the idle lanes after it (power of two, 1 = all)
     const uint32_t *pre_off, *pre_cnt;       // -P seed table (K0c), rows of `pre_iv`; only read by k_search_l<.., true>
     const ulonglong2 *pre_iv;                // 64-bit (L,U) whatever T is
     uint4 *slots;                            // arena: 2 x uint4 per slot
@@ -297,7 +301,11 @@ __global__ void __launch_bounds__(128, BWB_LANE_MIN_BLOCKS) k_search_l(const __g
     const bool multiref = a.is_multiref != 0;
     LaneAlloc al;
     al.priv_lo = lane_slot * a.slots_per_lane;
-    al.priv_hi = al.priv_lo + a.slots_per_lane;
+    al.priv_hi = al.priv_lo + a.slots_per_lane * a.lane_stride;
+    {
+        const uint32_t all = gridDim.x * blockDim.x * a.slots_per_lane;     // end of the private region
+        if (al.priv_hi > all) al.priv_hi = all;
+    }
     al.bump = al.priv_lo;
     al.ov_cur = al.ov_end = 0;
     al.borrowed = NIL;
@@ -307,7 +315,8 @@ __global__ void __launch_bounds__(128, BWB_LANE_MIN_BLOCKS) k_search_l(const __g
     h.clear();
 
     enum { NEED = 0, SEARCH = 1, TAIL = 2, FLUSH = 3, TADD = 4, DONE = 5 };
-    int mode = NEED;
+    int mode = (lane_slot & (a.lane_stride - 1u)) ? DONE : NEED;      // idle lanes of a retry pass never touch the queue
+    const uint32_t n_queue = a.n_queue_ptr ? min(*a.n_queue_ptr, a.n_reads) : a.n_reads;
     uint32_t r = 0, read_id = 0;
     int len = 0, err = 0;
     uint64_t off = 0;
@@ -336,6 +345,10 @@ __global__ void __launch_bounds__(128, BWB_LANE_MIN_BLOCKS) k_search_l(const __g
     uint32_t nx_w = 0, old_tail = NIL;        // wrapped width sum of the level being built
     T nx_tailL = 0, nx_tailU = 0;
 
+    // Entries pushed with a score beyond best_score + mm_score can never be expanded: the search breaks as soon
+    // as one is popped (inexact_match.c:309) and best_score never grows.  They are only COUNTED (num_entries
+    // feeds the max_entries check, :301), not written to the arena.
+    int ghost = 0;
     unsigned long long c_pops = 0, c_push = 0, c_tails = 0, c_rank = 0;
     uint32_t c_maxheap = 0, c_maxlist = 0;
 
@@ -346,7 +359,7 @@ __global__ void __launch_bounds__(128, BWB_LANE_MIN_BLOCKS) k_search_l(const __g
         // ================= take the next read =================
         if (mode == NEED) {
             r = atomicAdd(a.queue, 1u);
-            if (r >= a.n_reads) mode = DONE;
+            if (r >= n_queue) mode = DONE;
         }
         if (mode == NEED) {
             if (a.order) r = a.order[r];
@@ -358,6 +371,7 @@ __global__ void __launch_bounds__(128, BWB_LANE_MIN_BLOCKS) k_search_l(const __g
             Ds = a.pk_seed + (size_t)r * (a.seed_len + 1);
             const int nN = (int)a.n_count[r];                           // counted by K3
             h.clear();
+            ghost = 0;
             n_hits = 0; hit_head = hit_tail = NIL; err = 0;
             best_score = a.nb; max_diff = a.max_diff; num_best = 0;
             have_task = false;
@@ -404,9 +418,12 @@ __global__ void __launch_bounds__(128, BWB_LANE_MIN_BLOCKS) k_search_l(const __g
 
         // ================= pop + prune + classify (inexact_match.c:293-375) =================
         if (mode == SEARCH) {
-            const int nvirt = h.n + (have_next ? 1 : 0);              // heap->num_entries of the reference
+            const int nvirt = h.n + ghost + (have_next ? 1 : 0);      // heap->num_entries of the reference
             if ((uint32_t)nvirt > c_maxheap) c_maxheap = (uint32_t)nvirt;
             if (nvirt == 0 || nvirt > a.max_entries) {
+                mode = FLUSH;
+            } else if (!have_next && h.n == 0) {                      // only dead entries left: pop one, break (:309)
+                c_pops++;
                 mode = FLUSH;
             } else {
                 if (have_next) { e = nx; eb = nx_bucket; have_next = false; }
@@ -721,11 +738,19 @@ __global__ void __launch_bounds__(128, BWB_LANE_MIN_BLOCKS) k_search_l(const __g
                     nx.w = e.w; nx.r1 = e.r1; nx.r2 = e.r2; nx.r3 = e.r3;
                     nx_bucket = b0;
                 }
+                bool ins_live = ins_ok;
+#ifndef BWB_LANE_NO_GHOST
+                {   // dead score classes: count, do not store (b0 = the parent's class is alive by construction)
+                    const int dead_lim = best_score + a.mm_score;
+                    if (b2 > dead_lim) { ghost += __popc(md) + (ins_ok ? 1 : 0); md = 0u; ins_live = false; }
+                    if (b1 > dead_lim) { ghost += __popc(mmk & ~compat_set); mmk &= compat_set; }
+                }
+#endif
                 // occupancy bits once per score class (of what is really pushed) instead of once per child
-                if (ins_ok || md) h.mark(b2);
+                if (ins_live || md) h.mark(b2);
                 if (mmk & ~compat_set) h.mark(b1);
                 if (mmk & compat_set) h.mark(b0);
-                if (ins_ok) ok_all = h.push(al, a, lane_slot, b2, e.L, e.U, (zg | (1u << 28)) - 1u, wI, r1I, r2I, r3I);
+                if (ins_live) ok_all = h.push(al, a, lane_slot, b2, e.L, e.U, (zg | (1u << 28)) - 1u, wI, r1I, r2I, r3I);
                 while (md | mmk) {
                     const bool isdel = md != 0u;
                     const uint32_t cm = isdel ? md : mmk;
@@ -747,7 +772,11 @@ __global__ void __launch_bounds__(128, BWB_LANE_MIN_BLOCKS) k_search_l(const __g
         // ================= flush: hits -> output group (K5 restores input order) =================
         if (mode == FLUSH) {
             if (err) {
-                if (atomicCAS(a.status, 0u, (uint32_t)(-err)) == 0u) a.status[1] = read_id;
+                // out of arena: with every lane busy on a big heap the shared pool can run dry.  The read is
+                // handed to the next pass, which runs only the deferred reads (so each finds far more room);
+                // the last pass reports the overflow.
+                if (a.retry_list) a.retry_list[atomicAdd(a.retry_count, 1u)] = r;
+                else if (atomicCAS(a.status, 0u, (uint32_t)(-err)) == 0u) a.status[1] = read_id;
                 n_hits = 0;
             }
             const unsigned long long base = atomicAdd(a.out_cursor, (unsigned long long)n_hits);

@@ -540,3 +540,25 @@ def test_device_index_build_equals_host_builder_on_deep_repeats(tmp_path):
     exp, _ = orc.align(reads.seq, reads.offsets, default_params(n=3))
     orc.close()
     assert got == exp, first_difference(got, exp)
+
+
+def test_arena_overflow_defers_reads_to_retry_passes(small_case):
+    """thousands of reads in flight on the smallest arena: most of them run out of slots in the first pass, are
+    deferred, and finish in the retry passes (fewer reads in flight, 8x / 64x the arena each) -- same bytes"""
+    reads = small_case["reads"]
+    rep = max(1, 80000 // reads.n)
+    seq = np.tile(reads.seq, rep)
+    total = int(reads.offsets[-1])
+    offsets = np.concatenate([reads.offsets[:-1].astype(np.uint64) + np.uint64(k * total) for k in range(rep)]
+                             + [np.array([rep * total], dtype=np.uint64)])
+    p = default_params(n=5)
+    orc = oracle.Oracle(small_case["bwt"])
+    exp1, st = orc.align(reads.seq, reads.offsets, p)
+    orc.close()
+    with Aligner(heap_pool_mb=1, hits_per_read=64) as al:      # clamps to the minimum: 512 slots per lane
+        al.load_index(small_case["bwt"])
+        res = al.align(seq, offsets, p)
+        got = res.aln_bytes()
+        assert got == exp1 * rep, first_difference(got, exp1 * rep)
+        # deferred reads are searched twice: the pop total exceeds the oracle's iff something was deferred
+        assert res.counters()["pops"] > st["pops"] * rep, "the arena never overflowed: the test does not bite"
