@@ -4,7 +4,8 @@
 // 408 bytes + three mallocs per read) -- ~0.9 kB per read, i.e. ~90 GB for the 100 M-read configs.
 // Here the file is parsed in batches straight into the packed layout bwb_align consumes, every batch
 // is aligned and its records are appended to the .aln (and optionally the SAM) file, so memory is
-// bounded by the batch size.  Parsing follows fastq2reads: records start at the next '@'; the name
+// bounded by the batch size (two batches: a reader thread parses batch k+1 while batch k is on the
+// device and its records are written).  Parsing follows fastq2reads: records start at the next '@'; the name
 // is the rest of that line (first 256 characters kept); the base line is mapped through nt4_table
 // (io.h:113-130: A0 G1 C2 T3, anything else 4); then the '+' line; then the quality line, which
 // must be as long as the base line.
@@ -12,7 +13,12 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <condition_variable>
+#include <deque>
+#include <memory>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "bwbble_b200.h"
@@ -90,19 +96,46 @@ extern "C" long long bwb_align_fastq(bwb_ctx *ctx, const bwb_params *params, con
     if (!f) return BWB_ERR_IO;
     if (aln_path) remove(aln_path);                 // align.c:48
     if (aln_path) { FILE *t = fopen(aln_path, "wb"); if (!t) { fclose(f); return BWB_ERR_IO; } fclose(t); }
-    Reader in(f);
-    Batch b;
-    long long total = 0;
-    bool first = true, eof = false;
-    int rc = BWB_OK;
-    while (!eof && rc == BWB_OK) {
-        b.clear();
-        while (b.off.size() - 1 < batch_reads) {
-            const int st = next_read(in, b, sam_path != nullptr);
-            if (st == 0) { eof = true; break; }
-            if (st < 0) { rc = st; break; }
+    // producer: parses up to batch_reads reads per batch, at most two parsed batches waiting
+    struct Parsed { Batch b; int status = BWB_OK; bool eof = false; };
+    std::mutex mu;
+    std::condition_variable cv;
+    std::deque<std::unique_ptr<Parsed>> ready;
+    bool stop = false;
+    const bool keep_text = sam_path != nullptr;
+    std::thread producer([&] {
+        Reader in(f);
+        for (;;) {
+            std::unique_ptr<Parsed> p(new Parsed());
+            p->b.clear();
+            while (p->b.off.size() - 1 < batch_reads) {
+                const int st = next_read(in, p->b, keep_text);
+                if (st == 0) { p->eof = true; break; }
+                if (st < 0) { p->status = st; break; }
+            }
+            const bool last = p->eof || p->status != BWB_OK;
+            std::unique_lock<std::mutex> lk(mu);
+            cv.wait(lk, [&] { return stop || ready.size() < 2; });
+            if (stop) return;
+            ready.push_back(std::move(p));
+            cv.notify_all();
+            if (last) return;
         }
-        if (rc != BWB_OK) break;
+    });
+    long long total = 0;
+    bool first = true;
+    int rc = BWB_OK;
+    for (;;) {
+        std::unique_ptr<Parsed> p;
+        {
+            std::unique_lock<std::mutex> lk(mu);
+            cv.wait(lk, [&] { return !ready.empty(); });
+            p = std::move(ready.front());
+            ready.pop_front();
+            cv.notify_all();
+        }
+        if (p->status != BWB_OK) { rc = p->status; break; }
+        Batch &b = p->b;
         const uint64_t n = b.off.size() - 1;
         if (n == 0 && !first) break;
         bwb_results *res = nullptr;
@@ -117,9 +150,17 @@ extern "C" long long bwb_align_fastq(bwb_ctx *ctx, const bwb_params *params, con
                                        index_length, max_mm, sam_path, first ? 1 : 0, first ? 0 : 1);
         }
         bwb_results_free(res);
+        if (rc != BWB_OK) break;
         total += (long long)n;
         first = false;
+        if (p->eof) break;
     }
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        stop = true;
+        cv.notify_all();
+    }
+    producer.join();
     fclose(f);
     return rc == BWB_OK ? total : (long long)rc;
 }
