@@ -139,6 +139,25 @@ int fail(bwb_ctx *ctx, int code, const char *fmt, ...) {
                         __FILE__, __LINE__);                                                         \
     } while (0)
 
+// device temporaries of one API call: released on every exit path (the CU() macro returns early)
+struct DevTmp {
+    std::vector<void *> p;
+    template <class T>
+    cudaError_t alloc(T **q, size_t bytes) {
+        cudaError_t e = cudaMalloc((void **)q, bytes ? bytes : 16);
+        if (e == cudaSuccess) p.push_back((void *)*q);
+        return e;
+    }
+    void release(void *q) {
+        for (auto &x : p)
+            if (x == q) { cudaFree(q); x = nullptr; }
+    }
+    ~DevTmp() {
+        for (void *q : p)
+            if (q) cudaFree(q);
+    }
+};
+
 int ensure(bwb_ctx *ctx, DevBuf &b, size_t bytes, bool slack = true) {
     if (b.bytes >= bytes && b.p) return BWB_OK;
     if (b.p) CU(cudaFree(b.p));
@@ -768,7 +787,8 @@ int bwb_occ(bwb_ctx *ctx, const uint8_t *code, const uint64_t *pos, uint64_t n, 
     Device &d = ctx->dev[0];
     CU(cudaSetDevice(d.id));
     uint8_t *dc; uint64_t *dp, *dout;
-    CU(cudaMalloc(&dc, n)); CU(cudaMalloc(&dp, n * 8)); CU(cudaMalloc(&dout, n * 8));
+    DevTmp tmp;
+    CU(tmp.alloc(&dc, n)); CU(tmp.alloc(&dp, n * 8)); CU(tmp.alloc(&dout, n * 8));
     CU(cudaMemcpyAsync(dc, code, n, cudaMemcpyHostToDevice, d.stream));
     CU(cudaMemcpyAsync(dp, pos, n * 8, cudaMemcpyHostToDevice, d.stream));
     if (index_is_wide(ctx)) k_occ<uint64_t><<<(unsigned)((n + 255) / 256), 256, 0, d.stream>>>(make_view(ctx, d), dc, dp, n, dout);
@@ -776,7 +796,6 @@ int bwb_occ(bwb_ctx *ctx, const uint8_t *code, const uint64_t *pos, uint64_t n, 
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(out, dout, n * 8, cudaMemcpyDeviceToHost, d.stream));
     CU(cudaStreamSynchronize(d.stream));
-    cudaFree(dc); cudaFree(dp); cudaFree(dout);
     return BWB_OK;
 }
 
@@ -787,14 +806,14 @@ int bwb_occ_alphabet(bwb_ctx *ctx, const uint64_t *pos, uint64_t n, int inc, uin
     Device &d = ctx->dev[0];
     CU(cudaSetDevice(d.id));
     uint64_t *dp, *dout;
-    CU(cudaMalloc(&dp, n * 8)); CU(cudaMalloc(&dout, n * 16 * 8));
+    DevTmp tmp;
+    CU(tmp.alloc(&dp, n * 8)); CU(tmp.alloc(&dout, n * 16 * 8));
     CU(cudaMemcpyAsync(dp, pos, n * 8, cudaMemcpyHostToDevice, d.stream));
     if (index_is_wide(ctx)) k_occ_alphabet<uint64_t><<<(unsigned)((n * 16 + 255) / 256), 256, 0, d.stream>>>(make_view(ctx, d), dp, n, (uint32_t)inc, dout);
     else k_occ_alphabet<uint32_t><<<(unsigned)((n * 16 + 255) / 256), 256, 0, d.stream>>>(make_view(ctx, d), dp, n, (uint32_t)inc, dout);
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(out, dout, n * 16 * 8, cudaMemcpyDeviceToHost, d.stream));
     CU(cudaStreamSynchronize(d.stream));
-    cudaFree(dp); cudaFree(dout);
     return BWB_OK;
 }
 
@@ -804,7 +823,8 @@ int bwb_occ_bench(bwb_ctx *ctx, uint64_t n, uint64_t seed, int mode, int iters, 
     Device &d = ctx->dev[0];
     CU(cudaSetDevice(d.id));
     unsigned long long *dsink;
-    CU(cudaMalloc(&dsink, 8));
+    DevTmp tmp;
+    CU(tmp.alloc(&dsink, 8));
     CU(cudaMemsetAsync(dsink, 0, 8, d.stream));
     const int chain = mode >= 2 ? 8 : 1;          // modes 2/3 = modes 0/1 with 8 dependent queries per thread
     const int m = mode & 1;
@@ -826,7 +846,7 @@ int bwb_occ_bench(bwb_ctx *ctx, uint64_t n, uint64_t seed, int mode, int iters, 
     unsigned long long h = 0;
     CU(cudaMemcpy(&h, dsink, 8, cudaMemcpyDeviceToHost));
     if (checksum) *checksum = h;
-    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(dsink);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
     return BWB_OK;
 }
 
@@ -853,9 +873,10 @@ static int run_list_kernel(bwb_ctx *ctx, int which, const uint8_t *seq, const ui
     a.use_len = use_len;
     uint8_t *dseq; uint64_t *doff; ulonglong2 *gl; uint32_t *dstatus;
     const bool wide = index_is_wide(ctx);
-    CU(cudaMalloc(&dseq, total + 16)); CU(cudaMalloc(&doff, (n_reads + 1) * 8));
-    CU(cudaMalloc(&gl, (size_t)n_warps * 2 * a.list_cap * sizeof(ulonglong2)));
-    CU(cudaMalloc(&dstatus, 8));
+    DevTmp tmp;
+    CU(tmp.alloc(&dseq, total + 16)); CU(tmp.alloc(&doff, (n_reads + 1) * 8));
+    CU(tmp.alloc(&gl, (size_t)n_warps * 2 * a.list_cap * sizeof(ulonglong2)));
+    CU(tmp.alloc(&dstatus, 8));
     std::vector<uint64_t> rel(n_reads + 1);
     for (uint64_t r = 0; r <= n_reads; r++) rel[r] = offsets[r] - offsets[0];
     CU(cudaMemcpyAsync(dseq, seq + offsets[0], total, cudaMemcpyHostToDevice, d.stream));
@@ -866,9 +887,9 @@ static int run_list_kernel(bwb_ctx *ctx, int which, const uint8_t *seq, const ui
     if (which == 2) {
         unsigned long long *dcur, *droff; uint32_t *drcnt; ulonglong2 *dout;
         unsigned long long cap = n_reads * 8 + 4096;
-        CU(cudaMalloc(&dcur, 8)); CU(cudaMalloc(&droff, n_reads * 8)); CU(cudaMalloc(&drcnt, n_reads * 4));
+        CU(tmp.alloc(&dcur, 8)); CU(tmp.alloc(&droff, n_reads * 8)); CU(tmp.alloc(&drcnt, n_reads * 4));
         for (int attempt = 0;; attempt++) {
-            CU(cudaMalloc(&dout, cap * sizeof(ulonglong2)));
+            CU(tmp.alloc(&dout, cap * sizeof(ulonglong2)));
             CU(cudaMemsetAsync(dcur, 0, 8, d.stream));
             a.out_iv = dout; a.out_cap = cap; a.out_cursor = dcur; a.read_off = droff; a.read_cnt = drcnt;
             const size_t smem = (size_t)wpb * (2 * SL * sizeof(ulonglong2) + ((max_len + 15) & ~15));
@@ -892,17 +913,15 @@ static int run_list_kernel(bwb_ctx *ctx, int which, const uint8_t *seq, const ui
                     for (uint32_t k = 0; k < counts[r]; k++) { res[2 * w] = iv[roff[r] + k].x; res[2 * w + 1] = iv[roff[r] + k].y; w++; }
                 *intervals = res;
                 *n_intervals = w;
-                cudaFree(dout);
                 break;
             }
-            cudaFree(dout);
+            tmp.release(dout);
             cap = used + 4096;
         }
-        cudaFree(dcur); cudaFree(droff); cudaFree(drcnt);
     } else {
         int32_t *dd;
         const size_t nd = 2 * (total + n_reads);
-        CU(cudaMalloc(&dd, nd * 4 + 16));
+        CU(tmp.alloc(&dd, nd * 4 + 16));
         CU(cudaMemsetAsync(dd, 0, nd * 4, d.stream));
         a.out_d = dd;
         const size_t smem = (size_t)wpb * (2 * SL * sizeof(ulonglong2) + (((max_len + 1) * 8 + 15) & ~15) + ((max_len + 15) & ~15));
@@ -917,9 +936,7 @@ static int run_list_kernel(bwb_ctx *ctx, int which, const uint8_t *seq, const ui
         CU(cudaMemcpyAsync(out_d, dd, nd * 4, cudaMemcpyDeviceToHost, d.stream));
         CU(cudaMemcpyAsync(&hstatus, dstatus, 4, cudaMemcpyDeviceToHost, d.stream));
         CU(cudaStreamSynchronize(d.stream));
-        cudaFree(dd);
     }
-    cudaFree(dseq); cudaFree(doff); cudaFree(gl); cudaFree(dstatus);
     if (hstatus) return fail(ctx, -(int)hstatus, "interval list exceeded list_cap=%d (raise it with bwb_set_option)", ctx->list_cap);
     return BWB_OK;
 }
@@ -949,11 +966,12 @@ int bwb_lower_bounds(bwb_ctx *ctx, const uint8_t *seq, const uint64_t *offsets, 
     const int grid = d.sm_count * 2, n_groups = grid * (256 / GL);
     const uint64_t total = offsets[n_reads] - offsets[0];
     uint8_t *dseq; uint64_t *doff; void *gl; unsigned char *sm; int2 *dm, *ds;
-    CU(cudaMalloc(&dseq, total + 16)); CU(cudaMalloc(&doff, (n_reads + 1) * 8));
-    CU(cudaMalloc(&gl, (size_t)n_groups * 2 * ctx->list_cap * sizeof(ulonglong2)));
-    CU(cudaMalloc(&sm, 256));
-    CU(cudaMalloc(&dm, (total + n_reads + 1) * sizeof(int2)));
-    CU(cudaMalloc(&ds, (n_reads * (size_t)(seed_len + 1) + 1) * sizeof(int2)));
+    DevTmp tmp;
+    CU(tmp.alloc(&dseq, total + 16)); CU(tmp.alloc(&doff, (n_reads + 1) * 8));
+    CU(tmp.alloc(&gl, (size_t)n_groups * 2 * ctx->list_cap * sizeof(ulonglong2)));
+    CU(tmp.alloc(&sm, 256));
+    CU(tmp.alloc(&dm, (total + n_reads + 1) * sizeof(int2)));
+    CU(tmp.alloc(&ds, (n_reads * (size_t)(seed_len + 1) + 1) * sizeof(int2)));
     std::vector<uint64_t> rel(n_reads + 1);
     for (uint64_t r = 0; r <= n_reads; r++) rel[r] = offsets[r] - offsets[0];
     CU(cudaMemcpyAsync(dseq, seq + offsets[0], total, cudaMemcpyHostToDevice, d.stream));
@@ -981,7 +999,6 @@ int bwb_lower_bounds(bwb_ctx *ctx, const uint8_t *seq, const uint64_t *offsets, 
     if (seed_len) CU(cudaMemcpyAsync(d_seed, ds, n_reads * (size_t)(seed_len + 1) * sizeof(int2), cudaMemcpyDeviceToHost, d.stream));
     CU(cudaMemcpyAsync(&hstatus, sm + 8, 4, cudaMemcpyDeviceToHost, d.stream));
     CU(cudaStreamSynchronize(d.stream));
-    cudaFree(dseq); cudaFree(doff); cudaFree(gl); cudaFree(sm); cudaFree(dm); cudaFree(ds);
     if (hstatus) return fail(ctx, -(int)hstatus, "interval list exceeded list_cap=%d (raise it with bwb_set_option)", ctx->list_cap);
     return BWB_OK;
 }
