@@ -393,7 +393,7 @@ def main():
                            "parallelism": "reads sharded x%d, index replicated, no collective" % world},
                 "e2e": {"value": e2e, "unit": "reads/s", "h2d_bytes_per_step": h2d * world,
                         "d2h_bytes_per_step": int(np.mean(d2h_bytes)) * world},
-                "gpu_launches": 6 * args.steps,      # K3, K3b hist + scatter, K4, K5 scan + emit
+                "gpu_launches": 8 * args.steps,      # K3, K3b hist + scatter, K4 + its 2 retry passes, K5 scan + emit
                 "clocks": sampler.summary(),
                 "roofline": roof, "cpu_baseline": None if cpu is None else
                 {"value": cpu["value"], "unit": "reads/s", "cores": cpu["cores"], "kind": cpu["kind"], "sample": cpu["sample"],
