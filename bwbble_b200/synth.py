@@ -198,7 +198,11 @@ def make_reads(genome: Genome, seed: int, n_reads: int, read_len: int = 100, max
         take = min(len(good), n_reads - filled)
         pos[filled:filled + take] = good[:take]
         filled += take
-    win = hap[pos[:, None] + np.arange(W)[None, :]]            # (n_reads, W) base idx
+    # (n_reads, W) base idx; gathered in chunks: the int64 index matrix of a whole 8 M-read batch would be 7 GB
+    win = np.empty((n_reads, W), dtype=hap.dtype)
+    arW = np.arange(W)[None, :]
+    for lo in range(0, n_reads, 1 << 19):
+        win[lo:lo + (1 << 19)] = hap[pos[lo:lo + (1 << 19), None] + arW]
 
     # reads drawn from bubble haplotypes (exercise the bubble records)
     if genome.bubbles and bubble_frac > 0:
@@ -213,9 +217,12 @@ def make_reads(genome: Genome, seed: int, n_reads: int, read_len: int = 100, max
                 pos[r] = -1 - b
 
     # single indel per read (fraction indel_frac)
-    idx = np.broadcast_to(np.arange(L)[None, :], (n_reads, L)).copy()
     has_indel = rng.random(n_reads) < indel_frac
-    ins_mask = np.zeros((n_reads, L), dtype=bool)
+    if not has_indel.any():
+        idx = ins_mask = None                                  # identity gather: reads = win[:, :L]
+    else:
+        idx = np.broadcast_to(np.arange(L)[None, :], (n_reads, L)).copy()
+        ins_mask = np.zeros((n_reads, L), dtype=bool)
     if has_indel.any():
         d = rng.integers(1, max_indel + 1, size=n_reads)
         o = rng.integers(8, max(9, L - 8 - max_indel), size=n_reads)
@@ -227,8 +234,8 @@ def make_reads(genome: Genome, seed: int, n_reads: int, read_len: int = 100, max
         shift = np.clip(ar - o[:, None], 0, d[:, None])
         idx = np.where(sel_ins, ar - shift, idx)
         ins_mask = sel_ins & (ar >= o[:, None]) & (ar < (o + d)[:, None])
-    reads = np.take_along_axis(win, idx, axis=1)
-    if ins_mask.any():
+    reads = win[:, :L].copy() if idx is None else np.take_along_axis(win, idx, axis=1)
+    if ins_mask is not None and ins_mask.any():
         reads[ins_mask] = rng.integers(0, 4, size=int(ins_mask.sum()), dtype=np.uint8)
 
     # substitutions: k uniform in [0, max_sub]
