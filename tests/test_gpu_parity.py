@@ -562,3 +562,23 @@ def test_arena_overflow_defers_reads_to_retry_passes(small_case):
         assert got == exp1 * rep, first_difference(got, exp1 * rep)
         # deferred reads are searched twice: the pop total exceeds the oracle's iff something was deferred
         assert res.counters()["pops"] > st["pops"] * rep, "the arena never overflowed: the test does not bite"
+
+
+def test_150bp_gapped_reads_config5_shape(small_case):
+    """BASELINE configs[4] in miniature: 150 bp reads, substitutions + 1-3 bp indels, `-n 4 -o 1 -e 6`; 32- and 64-bit kernels"""
+    from bwbble_b200 import synth
+    reads = synth.make_reads(small_case["genome"], 91, 400, 150, 3, indel_frac=0.5, max_indel=3, n_base_frac=0.002)
+    p = default_params(n=4, o=1, e=6)
+    orc = oracle.Oracle(small_case["bwt"])
+    exp, st = orc.align(reads.seq, reads.offsets, p)
+    orc.close()
+    for wide in (0, 1):
+        with Aligner(heap_pool_mb=512) as al:
+            if wide:
+                al.set_option("force_wide", 1)
+            al.load_index(small_case["bwt"])
+            res = al.align(reads.seq, reads.offsets, p)
+            got = res.aln_bytes()
+            assert got == exp, first_difference(got, exp)
+            ctr = res.counters()
+            assert ctr["pops"] == st["pops"] and ctr["pushes"] == st["pushes"]

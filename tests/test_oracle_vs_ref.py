@@ -54,3 +54,27 @@ def test_oracle_aln_is_byte_identical_to_reference(case, kw, tmp_path):
     got, _ = orc.align(case["reads"].seq, case["reads"].offsets, p, threads=p.n_threads)
     orc.close()
     assert got == exp, first_difference(got, exp)
+
+
+def test_oracle_150bp_gapped_reads_config5_shape(case, tmp_path):
+    """BASELINE configs[4] in miniature: 150 bp reads, up to 4 differences drawn from substitutions and 1-3 bp indels,
+    `-n 4 -o 1 -e 6`, serial and threaded drivers"""
+    g_reads = synth.make_reads(case["genome"] if "genome" in case else _genome(case), 33, 300, 150, 3, indel_frac=0.5,
+                               max_indel=3, n_base_frac=0.002, bubble_frac=0.1)
+    fq = str(tmp_path / "r150.fq")
+    g_reads.write_fastq(fq)
+    for threads in (1, 4):
+        p = default_params(n=4, o=1, e=6, t=threads)
+        out = str(tmp_path / ("ref%d.aln" % threads))
+        subprocess.run([REF, "align", *params_to_cli(p), case["fasta"], fq, out], check=True, stdout=subprocess.DEVNULL)
+        exp = open(out, "rb").read()
+        orc = oracle.Oracle(case["fasta"] + ".bwt")
+        got, st = orc.align(g_reads.seq, g_reads.offsets, p, threads=threads)
+        orc.close()
+        assert got == exp, first_difference(got, exp)
+        assert st["hits"] > 100
+
+
+def _genome(case):
+    return synth.make_genome(31, 120000, n_records=3, snp_rate=0.015, tri_frac=0.06, n_bubbles=40, n_frac=0.04,
+                             n_repeat_copies=30, n_microsats=6, lowercase_frac=0.01)
