@@ -352,6 +352,13 @@ def align_reads(fasta_path: str, fastq_path: str, aln_path: str, params: Optiona
     params = params or default_params()
     with Aligner(devices) as al:
         al.load_index(fasta_path + ".bwt", with_sa=sam_path is not None)
+        if params.use_precalc:                      # -P: <fasta>.pre is loaded, or made first (align.c:59-64)
+            pre = fasta_path + ".pre"
+            if os.path.exists(pre):
+                al.load_precalc(pre, bool(params.is_multiref))
+            else:
+                al.build_precalc(bool(params.is_multiref))
+                al.write_precalc(pre)
         n = _lib.lib().bwb_align_fastq(al._ctx, C.byref(params), os.fsencode(fastq_path), os.fsencode(aln_path),
                                        os.fsencode(sam_path) if sam_path else None,
                                        os.fsencode(fasta_path + ".ann") if sam_path else None,
