@@ -84,12 +84,15 @@ struct bwb_ctx {
                               // 2 = 8-lane groups (k_calc_d_g + k_search_g); 1 and 2 are A/B baselines
     int use_ktab = 1;         // k-mer table for calculate_d's top of tree (0 = off, for A/B and tests)
     int force_wide = 0;       // tests: run the 64-bit / 32-byte-entry kernels on a small index
+    long long hit_cap0 = -1;  // tests: initial capacity of the hit buffers (-1 = 2 per read + 65536), forces the regrow path
     int heavy_first = 1;      // K3b: K4 takes reads in descending order of K3's whole-read bound (0 = input order)
     // -P seed table, host copy in row order (what a .pre file holds)
     bool have_pre = false;
     int pre_multiref = 1;
     std::vector<uint32_t> pre_cnt_h, pre_off_h;
     std::vector<uint64_t> pre_lu_h;  // L,U pairs
+    // every align call overwrites the per-device result buffers: un-fetched results of an older call are stale
+    uint64_t launch_generation = 0;
 };
 
 struct bwb_reads {
@@ -113,6 +116,7 @@ struct bwb_results {
     float k3_ms = 0.f;        // K3 duration (engines with a separate lower-bound kernel)
     // pending (device-resident) state
     bool fetched = false;
+    uint64_t generation = 0;  // ctx->launch_generation of the call that produced the device-resident data
     std::vector<uint64_t> shard_lo;
     std::vector<uint64_t> shard_total;
     int status = 0;
@@ -612,7 +616,7 @@ int bwb_device_count(const bwb_ctx *ctx) { return ctx ? (int)ctx->dev.size() : 0
 int bwb_set_option(bwb_ctx *ctx, const char *key, long long value) {
     if (!ctx || !key) return BWB_ERR_ARG;
     std::string k(key);
-    if (value <= 0 && k != "blocks_per_sm" && k != "force_wide" && k != "engine" && k != "heap_pool_mb" && k != "kmer_table" && k != "heavy_first") return fail(ctx, BWB_ERR_ARG, "option %s needs a positive value", key);
+    if (value <= 0 && k != "blocks_per_sm" && k != "force_wide" && k != "engine" && k != "heap_pool_mb" && k != "kmer_table" && k != "heavy_first" && k != "hit_cap0") return fail(ctx, BWB_ERR_ARG, "option %s needs a positive value", key);
     if (k == "heap_pool_mb") ctx->heap_pool_mb = value;
     else if (k == "list_cap") ctx->list_cap = (int)(value < SL + 4 ? SL + 4 : value);
     else if (k == "hits_per_read") ctx->hits_per_read = (int)value;
@@ -628,6 +632,7 @@ int bwb_set_option(bwb_ctx *ctx, const char *key, long long value) {
     }
     else if (k == "kmer_table") ctx->use_ktab = value > 1 ? 0 : 1;
     else if (k == "heavy_first") ctx->heavy_first = value > 1 ? 0 : 1;
+    else if (k == "hit_cap0") ctx->hit_cap0 = value;
     else if (k == "engine") ctx->engine = (value == 1 || value == 2) ? (int)value : 0;
     else return fail(ctx, BWB_ERR_ARG, "unknown option %s", key);
     for (auto &d : ctx->dev) {       // scratch is re-sized lazily
@@ -654,18 +659,24 @@ int bwb_index_upload(bwb_ctx *ctx, uint64_t length, uint64_t sa0_index, const ui
     if (length >= (1ull << 40)) return fail(ctx, BWB_ERR_ARG, "index longer than 2^40 rows");
     ctx->length = length;
     ctx->have_sa = false;
+    ctx->have_index = false;
+    // a -P seed table belongs to the index it was computed on: drop it with the old index
+    ctx->have_pre = false;
+    ctx->pre_cnt_h.clear(); ctx->pre_off_h.clear(); ctx->pre_lu_h.clear();
     ctx->sa0 = sa0_index;
     ctx->num_blocks = (length + 127) / 128;
     memcpy(ctx->C, C, sizeof ctx->C);
     for (auto &d : ctx->dev) {
         CU(cudaSetDevice(d.id));
+        if (d.pre_off) { cudaFree(d.pre_off); cudaFree(d.pre_cnt); cudaFree(d.pre_iv); d.pre_off = d.pre_cnt = nullptr; d.pre_iv = nullptr; }
         if (d.blocks) { CU(cudaFree(d.blocks)); d.blocks = nullptr; }
+        DevTmp tmp;                                  // freed on every exit path
         uint32_t *d_bwt = nullptr, *d_err = nullptr;
         uint64_t *d_O = nullptr;
         CU(cudaMalloc(&d.blocks, ctx->num_blocks * 128));
-        CU(cudaMalloc(&d_bwt, num_words * 4));
-        CU(cudaMalloc(&d_O, num_occ * 16 * 8));
-        CU(cudaMalloc(&d_err, 4));
+        CU(tmp.alloc(&d_bwt, num_words * 4));
+        CU(tmp.alloc(&d_O, num_occ * 16 * 8));
+        CU(tmp.alloc(&d_err, 4));
         CU(cudaMemcpyAsync(d_bwt, bwt, num_words * 4, cudaMemcpyHostToDevice, d.stream));
         CU(cudaMemcpyAsync(d_O, O, num_occ * 16 * 8, cudaMemcpyHostToDevice, d.stream));
         CU(cudaMemsetAsync(d_err, 0, 4, d.stream));
@@ -677,7 +688,6 @@ int bwb_index_upload(bwb_ctx *ctx, uint64_t length, uint64_t sa0_index, const ui
         uint32_t herr = 0;
         CU(cudaMemcpyAsync(&herr, d_err, 4, cudaMemcpyDeviceToHost, d.stream));
         CU(cudaStreamSynchronize(d.stream));
-        CU(cudaFree(d_bwt)); CU(cudaFree(d_O)); CU(cudaFree(d_err));
         if (herr) return fail(ctx, BWB_ERR_ARG, "a per-code rank counter exceeds 2^32 (index too large for u32 checkpoints)");
     }
     ctx->have_index = true;
@@ -1269,12 +1279,12 @@ static int launch_shard(bwb_ctx *ctx, Device &d, const bwb_params *p, int nb, co
         k_scan_counts<<<1, 1024, 0, d.stream>>>(cnt, (uint32_t)n, ooff);
         CU(cudaGetLastError());
         k_emit<<<(unsigned)((n + 127) / 128), 128, 0, d.stream>>>((const bwb_hit *)d.unordered.p, a.read_off, cnt, ooff,
-                                                              (uint32_t)n, (bwb_hit *)d.ordered.p);
+                                                              (uint32_t)n, (bwb_hit *)d.ordered.p, a.out_cursor, out_cap);
         CU(cudaGetLastError());
         if (ctx->have_sa) {                          // K6: locate + top1/top2 (aln2sam's eval_aln)
             if ((rc = ensure(ctx, d.loc, n * sizeof(bwb_loc)))) return rc;
             k_locate<<<(unsigned)((n + 127) / 128), 128, 0, d.stream>>>(a.ix, ctx->sa0, d.sa, (const bwb_hit *)d.ordered.p, ooff,
-                                                                    cnt, (uint32_t)n, (bwb_loc *)d.loc.p);
+                                                                    cnt, (uint32_t)n, (bwb_loc *)d.loc.p, a.out_cursor, out_cap);
             CU(cudaGetLastError());
         }
     }
@@ -1294,6 +1304,7 @@ static int align_impl(bwb_ctx *ctx, const bwb_params *p, const bwb_reads *R, bwb
     res->ctx = ctx; res->n_reads = R->n_reads; res->shard_lo = R->shard_lo; res->shard_total.assign(G, 0);
     res->counts.assign(R->n_reads, 0);
     res->have_loc = ctx->have_sa;
+    res->generation = ++ctx->launch_generation;
 
     std::vector<unsigned long long> cap(G);
     for (int g = 0; g < G; g++) {
@@ -1301,7 +1312,7 @@ static int align_impl(bwb_ctx *ctx, const bwb_params *p, const bwb_reads *R, bwb
            : ctx->engine == 2 ? prepare_search_group(ctx, ctx->dev[g], L, wide)
                               : prepare_search_lane(ctx, ctx->dev[g], nb, wide);
         if (rc) { delete res; return rc; }
-        cap[g] = (R->shard_lo[g + 1] - R->shard_lo[g]) * 2 + 65536;
+        cap[g] = ctx->hit_cap0 >= 0 ? (unsigned long long)ctx->hit_cap0 : (R->shard_lo[g + 1] - R->shard_lo[g]) * 2 + 65536;
     }
     std::vector<char> done(G, 0);
     for (int attempt = 0; attempt < 6; attempt++) {
@@ -1355,6 +1366,9 @@ int bwb_results_fetch(bwb_results *r) {
     if (!r) return BWB_ERR_ARG;
     if (r->fetched) return BWB_OK;
     bwb_ctx *ctx = r->ctx;
+    if (r->generation != ctx->launch_generation)
+        return fail(ctx, BWB_ERR_ARG, "bwb_results_fetch: a later bwb_align/bwb_align_resident on this context has overwritten "
+                                      "the device buffers of these results (fetch before the next launch)");
     const int G = (int)ctx->dev.size();
     uint64_t total = 0;
     for (int g = 0; g < G; g++) total += r->shard_total[g];

@@ -875,9 +875,13 @@ __global__ void __launch_bounds__(1024) k_scan_counts(const uint32_t *__restrict
 
 __global__ void k_emit(const bwb_hit *__restrict__ unordered, const unsigned long long *__restrict__ read_off,
                        const uint32_t *__restrict__ read_cnt, const unsigned long long *__restrict__ ordered_off,
-                       uint32_t n_reads, bwb_hit *__restrict__ ordered) {
+                       uint32_t n_reads, bwb_hit *__restrict__ ordered, const unsigned long long *__restrict__ out_cursor,
+                       unsigned long long out_cap) {
     const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n_reads) return;
+    // K4 counted more hits than `unordered` / `ordered` hold: nothing was stored for the reads that did not fit,
+    // the host regrows the buffers and runs the shard again -- do not touch memory on this attempt
+    if (*out_cursor > out_cap) return;
     const uint32_t n = read_cnt[r];
     const uint4 *src = reinterpret_cast<const uint4 *>(unordered + read_off[r]);
     uint4 *dst = reinterpret_cast<uint4 *>(ordered + ordered_off[r]);
@@ -1054,9 +1058,11 @@ __device__ __forceinline__ uint64_t inv_psi(const IndexView &ix, uint64_t sa0, u
 
 __global__ void k_locate(IndexView ix, uint64_t sa0, const uint64_t *__restrict__ SA, const bwb_hit *__restrict__ hits,
                          const unsigned long long *__restrict__ off, const uint32_t *__restrict__ cnt, uint32_t n_reads,
-                         bwb_loc *__restrict__ out) {
+                         bwb_loc *__restrict__ out, const unsigned long long *__restrict__ out_cursor,
+                         unsigned long long out_cap) {
     const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n_reads) return;
+    if (*out_cursor > out_cap) return;          // overflowed attempt (see k_emit): the shard is run again
     bwb_loc loc;
     loc.ref_pos = ~0ull; loc.top1 = 0; loc.top2 = 0;
     const uint32_t n = cnt[r];

@@ -179,7 +179,10 @@ int bwb_reads_upload(bwb_ctx *ctx, const uint8_t *seq, const uint64_t *offsets, 
                      bwb_reads **out);
 void bwb_reads_free(bwb_reads *r);   /* before bwb_destroy() of the context the reads were uploaded to */
 /* Runs the kernels on the context's stream(s); results stay on the device until
- * bwb_results_fetch() (fetch==0: no bulk D2H, only the 256-byte status block is read back). */
+ * bwb_results_fetch() (fetch==0: no bulk D2H, only the 256-byte status block is read back).
+ * Lifetime: un-fetched results live in per-context device buffers that the NEXT bwb_align /
+ * bwb_align_resident on the same context overwrites; bwb_results_fetch() on results of an older
+ * launch fails with BWB_ERR_ARG instead of returning another batch's hits. */
 int bwb_align_resident(bwb_ctx *ctx, const bwb_params *params, const bwb_reads *reads, int fetch,
                        bwb_results **out);
 int bwb_results_fetch(bwb_results *r);
