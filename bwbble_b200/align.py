@@ -198,6 +198,10 @@ class Aligner:
                                                len(bwt), O.ctypes.data, len(O) // 16), self._ctx)
         self.index = ix
 
+    def index_length(self) -> int:
+        """BWT rows of the uploaded index (0 before an index is loaded)."""
+        return int(self.index.length) if self.index is not None else 0
+
     def load_index(self, bwt_path: str, with_sa: bool = False):
         """load_bwt(path, loadSA) (bwt.c:90-125); with_sa also uploads the sampled SA, enabling K6."""
         ix = load_bwt(bwt_path, load_sa=with_sa)

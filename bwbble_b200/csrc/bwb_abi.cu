@@ -84,6 +84,8 @@ struct bwb_ctx {
                               // 2 = 8-lane groups (k_calc_d_g + k_search_g); 1 and 2 are A/B baselines
     int use_ktab = 1;         // k-mer table for calculate_d's top of tree (0 = off, for A/B and tests)
     int force_wide = 0;       // tests: run the 64-bit / 32-byte-entry kernels on a small index
+    long long index_chunk = 0;       // K7w: suffixes per sort chunk (0 = 2^29)
+    int index_wide = 0;              // tests: force the chunked 64-bit suffix sorter on a small genome
     long long hit_cap0 = -1;  // tests: initial capacity of the hit buffers (-1 = 2 per read + 65536), forces the regrow path
     int heavy_first = 1;      // K3b: K4 takes reads in descending order of K3's whole-read bound (0 = input order)
     // -P seed table, host copy in row order (what a .pre file holds)
@@ -197,6 +199,9 @@ int check_reads(bwb_ctx *ctx, const uint64_t *offsets, uint64_t n_reads, int &ma
         if (l > 255) return fail(ctx, BWB_ERR_ARG, "read %llu is %llu bases; positions are 8-bit (align.h:104)", (unsigned long long)r, (unsigned long long)l);
         if ((int)l > max_len) max_len = (int)l;
     }
+    // K4 addresses a read's bases and lower bounds with 32-bit offsets
+    if (offsets[n_reads] - offsets[0] + n_reads >= 0xffffffffull)
+        return fail(ctx, BWB_ERR_ARG, "more than 2^32 bases in one call: split the batch");
     return BWB_OK;
 }
 
@@ -238,6 +243,7 @@ SmemLayout g4_layout(int max_len, int seed_len, int nb) {
     return L;
 }
 
+#ifdef BWB_AB_ENGINES
 // size the persistent grid and the per-group scratch for the group engine (K3 + K4)
 int prepare_search_group(bwb_ctx *ctx, Device &d, const SmemLayout &L, bool wide) {
     CU(cudaSetDevice(d.id));
@@ -278,6 +284,8 @@ int prepare_search_group(bwb_ctx *ctx, Device &d, const SmemLayout &L, bool wide
     }
     return BWB_OK;
 }
+
+#endif  // BWB_AB_ENGINES
 
 // size the persistent grid and the per-lane arena for the lane engine (K3 groups + K4 lanes)
 int prepare_search_lane(bwb_ctx *ctx, Device &d, int nb, bool wide) {
@@ -354,6 +362,7 @@ int prepare_search_lane(bwb_ctx *ctx, Device &d, int nb, bool wide) {
     return BWB_OK;
 }
 
+#ifdef BWB_AB_ENGINES
 // size the persistent grid and the per-warp scratch for K4
 int prepare_search(bwb_ctx *ctx, Device &d, const SmemLayout &L, bool wide) {
     CU(cudaSetDevice(d.id));
@@ -391,6 +400,8 @@ int prepare_search(bwb_ctx *ctx, Device &d, const SmemLayout &L, bool wide) {
     }
     return BWB_OK;
 }
+
+#endif  // BWB_AB_ENGINES
 
 // K0b: build the k-mer table on one device (after its blocks exist)
 int build_ktab(bwb_ctx *ctx, Device &d) {
@@ -616,7 +627,7 @@ int bwb_device_count(const bwb_ctx *ctx) { return ctx ? (int)ctx->dev.size() : 0
 int bwb_set_option(bwb_ctx *ctx, const char *key, long long value) {
     if (!ctx || !key) return BWB_ERR_ARG;
     std::string k(key);
-    if (value <= 0 && k != "blocks_per_sm" && k != "force_wide" && k != "engine" && k != "heap_pool_mb" && k != "kmer_table" && k != "heavy_first" && k != "hit_cap0") return fail(ctx, BWB_ERR_ARG, "option %s needs a positive value", key);
+    if (value <= 0 && k != "blocks_per_sm" && k != "force_wide" && k != "engine" && k != "heap_pool_mb" && k != "kmer_table" && k != "heavy_first" && k != "hit_cap0" && k != "index_wide" && k != "index_chunk") return fail(ctx, BWB_ERR_ARG, "option %s needs a positive value", key);
     if (k == "heap_pool_mb") ctx->heap_pool_mb = value;
     else if (k == "list_cap") ctx->list_cap = (int)(value < SL + 4 ? SL + 4 : value);
     else if (k == "hits_per_read") ctx->hits_per_read = (int)value;
@@ -633,7 +644,17 @@ int bwb_set_option(bwb_ctx *ctx, const char *key, long long value) {
     else if (k == "kmer_table") ctx->use_ktab = value > 1 ? 0 : 1;
     else if (k == "heavy_first") ctx->heavy_first = value > 1 ? 0 : 1;
     else if (k == "hit_cap0") ctx->hit_cap0 = value;
-    else if (k == "engine") ctx->engine = (value == 1 || value == 2) ? (int)value : 0;
+    else if (k == "index_wide") { ctx->index_wide = value == 1 ? 1 : 0; return BWB_OK; }
+    else if (k == "index_chunk") { ctx->index_chunk = value > 0 ? value : 0; return BWB_OK; }
+    else if (k == "engine") {
+#ifdef BWB_AB_ENGINES
+        ctx->engine = (value == 1 || value == 2) ? (int)value : 0;
+#else
+        if (value == 1 || value == 2)
+            return fail(ctx, BWB_ERR_UNSUPPORTED, "the round-1 A/B engines (1 = warp per read, 2 = 8 lanes per read) are only built with -DBWB_AB_ENGINES");
+        ctx->engine = 0;
+#endif
+    }
     else return fail(ctx, BWB_ERR_ARG, "unknown option %s", key);
     for (auto &d : ctx->dev) {       // scratch is re-sized lazily
         cudaSetDevice(d.id);
@@ -1143,11 +1164,14 @@ static int launch_shard(bwb_ctx *ctx, Device &d, const bwb_params *p, int nb, co
 
     CU(cudaEventRecord(d.ev0, d.stream));
     CU(cudaEventRecord(d.evm, d.stream));
+#ifdef BWB_AB_ENGINES
     if (n && ctx->engine == 1) {
         if (wide) k_align<true><<<d.grid, d.wpb * 32, d.smem_bytes, d.stream>>>(a);
         else k_align<false><<<d.grid, d.wpb * 32, d.smem_bytes, d.stream>>>(a);
         CU(cudaGetLastError());
-    } else if (n && ctx->engine == 0) {
+    } else
+#endif
+    if (n && ctx->engine == 0) {
         // K3 (8-lane groups): packed lower-bound arrays of every read -> HBM
         if ((rc = ensure(ctx, d.pk_main, (total_bases + n + 1) * 2))) return rc;
         if ((rc = ensure(ctx, d.pk_seed, (n * (size_t)(p->seed_length + 1) + 1) * 2))) return rc;
@@ -1228,7 +1252,9 @@ static int launch_shard(bwb_ctx *ctx, Device &d, const bwb_params *p, int nb, co
             CU(cudaGetLastError());
         }
         CU(cudaGetLastError());
-    } else if (n) {
+    }
+#ifdef BWB_AB_ENGINES
+    else if (n) {
         // K3: lower-bound arrays of every read -> HBM
         if ((rc = ensure(ctx, d.d_main, (total_bases + n + 1) * sizeof(int2)))) return rc;
         if ((rc = ensure(ctx, d.d_seed, (n * (size_t)(p->seed_length + 1) + 1) * sizeof(int2)))) return rc;
@@ -1271,6 +1297,7 @@ static int launch_shard(bwb_ctx *ctx, Device &d, const bwb_params *p, int nb, co
         else k_search_g<false><<<d.grid, 256, d.smem_bytes, d.stream>>>(g);
         CU(cudaGetLastError());
     }
+#endif  // BWB_AB_ENGINES
     CU(cudaEventRecord(d.ev1, d.stream));
     // K5: exclusive scan of the per-read counts, then ordered copy
     const uint32_t *cnt = (const uint32_t *)d.read_cnt.p;
@@ -1308,9 +1335,13 @@ static int align_impl(bwb_ctx *ctx, const bwb_params *p, const bwb_reads *R, bwb
 
     std::vector<unsigned long long> cap(G);
     for (int g = 0; g < G; g++) {
+#ifdef BWB_AB_ENGINES
         rc = ctx->engine == 1 ? prepare_search(ctx, ctx->dev[g], L, wide)
            : ctx->engine == 2 ? prepare_search_group(ctx, ctx->dev[g], L, wide)
                               : prepare_search_lane(ctx, ctx->dev[g], nb, wide);
+#else
+        rc = prepare_search_lane(ctx, ctx->dev[g], nb, wide);
+#endif
         if (rc) { delete res; return rc; }
         cap[g] = ctx->hit_cap0 >= 0 ? (unsigned long long)ctx->hit_cap0 : (R->shard_lo[g + 1] - R->shard_lo[g]) * 2 + 65536;
     }
@@ -1447,6 +1478,10 @@ int ctx_device(const bwb_ctx *ctx, int *device_id, void **stream) {
     return BWB_OK;
 }
 int ctx_fail(bwb_ctx *ctx, int code, const char *msg) { return fail(ctx, code, "%s", msg); }
+bool ctx_index_options(const bwb_ctx *ctx, long long *chunk) {
+    if (chunk) *chunk = ctx ? ctx->index_chunk : 0;
+    return ctx && ctx->index_wide != 0;
+}
 const std::vector<uint32_t> &results_counts(const bwb_results *r) { return r->counts; }
 const std::vector<bwb_hit> &results_hits(const bwb_results *r) { return r->hits; }
 bool results_fetched(const bwb_results *r) { return r->fetched; }

@@ -520,6 +520,7 @@ __device__ __forceinline__ uint32_t g_chunk_alloc(bool need, GHeap &h, uint32_t 
     return id;
 }
 
+#ifdef BWB_AB_ENGINES   // round-1 A/B baseline (8 lanes per read); not in the default build
 template <bool WIDE>
 __global__ void __launch_bounds__(256, BWB_K4_MIN_BLOCKS) k_search_g(const __grid_constant__ SearchArgs a) {
     typedef typename Coord<WIDE>::type T;
@@ -1068,5 +1069,7 @@ __global__ void __launch_bounds__(256, BWB_K4_MIN_BLOCKS) k_search_g(const __gri
         atomicMax(a.counters + 5, (unsigned long long)c_maxlist);
     }
 }
+
+#endif  // BWB_AB_ENGINES
 
 }  // namespace bwb

@@ -552,6 +552,7 @@ __device__ __forceinline__ bool add_hits(HitSink &hs, const PE<T> &e, int score,
 #define BWB_K4_MIN_BLOCKS 3
 #endif
 
+#ifdef BWB_AB_ENGINES   // round-1 A/B baseline (warp per read); not in the default build
 template <bool WIDE>
 __global__ void __launch_bounds__(256, BWB_K4_MIN_BLOCKS) k_align(const __grid_constant__ AlignArgs a) {
     typedef typename Coord<WIDE>::type T;
@@ -831,6 +832,8 @@ __global__ void __launch_bounds__(256, BWB_K4_MIN_BLOCKS) k_align(const __grid_c
         atomicMax(a.counters + 5, (unsigned long long)c_maxlist);
     }
 }
+
+#endif  // BWB_AB_ENGINES
 
 // ---------------------------------------------------------------------------------------------
 // K5: ordered emit.  ordered_off = exclusive scan of read_cnt, then a gather in input order.

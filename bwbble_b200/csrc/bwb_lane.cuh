@@ -107,6 +107,33 @@ __device__ __forceinline__ uint32_t lane_alloc(LaneAlloc &al, const LaneArgs &a,
     al.ov_end = al.ov_cur + LBLK;
     return al.ov_cur++;
 }
+// n consecutive slots (n <= LBLK): the children of one expansion.  A range too short for them is left to the
+// single-slot allocations (private range) or abandoned (borrowed block).
+__device__ __forceinline__ uint32_t lane_alloc_n(LaneAlloc &al, const LaneArgs &a, uint32_t lane_slot, uint32_t n) {
+    if (al.bump + n <= al.priv_hi) { const uint32_t s = al.bump; al.bump += n; return s; }
+    if (al.ov_cur + n <= al.ov_end) { const uint32_t s = al.ov_cur; al.ov_cur += n; return s; }
+    const uint32_t blk = pool_take_block(a.pool, a.blk_link, lane_slot);
+    if (blk == NIL) return NIL;
+    a.blk_link[blk] = al.borrowed;
+    if (al.borrowed == NIL) al.borrowed_last = blk;
+    al.borrowed = blk;
+    al.ov_cur = blk * LBLK + n;
+    al.ov_end = blk * LBLK + LBLK;
+    return blk * LBLK;
+}
+// index of the k-th set bit (k = 0 is the lowest) of a 16-bit mask with more than k bits set
+__device__ __forceinline__ int kth_bit16(uint32_t m, uint32_t k) {
+    int pos = 0;
+    uint32_t c = (uint32_t)__popc(m & 0xffu);
+    if (k >= c) { k -= c; pos = 8; }
+    c = (uint32_t)__popc((m >> pos) & 0xfu);
+    if (k >= c) { k -= c; pos += 4; }
+    c = (uint32_t)__popc((m >> pos) & 0x3u);
+    if (k >= c) { k -= c; pos += 2; }
+    c = (m >> pos) & 1u;
+    if (k >= c) pos += 1;
+    return pos;
+}
 // end of a read: every slot is dead; hand borrowed blocks back with one CAS
 __device__ __forceinline__ void lane_alloc_reset(LaneAlloc &al, const LaneArgs &a, uint32_t lane_slot) {
     if (al.borrowed != NIL) {
@@ -273,30 +300,120 @@ __global__ void k_order_scatter(const uint16_t *__restrict__ pk_main, const uint
     }
 }
 
-// A/B on B200 (chr21-scale, -n 5): 3 blocks of 128 lanes per SM (168 registers, no spills) with the
-// checkpoint counters fetched as 128-bit loads beat 4 blocks (128 registers, spills) by 1.4x.
-#ifndef BWB_LANE_CNT32
-#define BWB_LANE_CNT128 1
-#endif
-#ifdef BWB_LANE_CNT128
-#define BWB_CNT(c, j) (c)[j]
-#else
-#define BWB_CNT(c, j) __ldg((c) + (j))
-#endif
+// ---------------------------------------------------------------------------------------------
+// K4 rank stage: (L, U, quirk mode) -> valid-child mask + (L_j, U_j) for j = 1..15, the straight-line
+// 15-code loop over the two ends of the interval (2 x 15 x (2 LOP3 + 1 POPC) x 4 words).
+//
+// Tried in round 2 and dropped (profiles/r02_k4_exchange.md): re-dealing the rank tasks of a block BY TYPE
+// through shared memory -- narrow same-block intervals (60 % of the expansions) as one cheap work item per
+// row, the rest as full 32-lane batches of this function.  Bit-exact, but 2 block barriers per iteration with
+// 12 warps per SM cost more issue slots (30 % busy instead of 43 %) than the cheaper rank path saved:
+// 0.73-0.77 M reads/s against 1.00 M for every lane ranking its own task.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void low_bits128(int n, uint32_t &k0, uint32_t &k1, uint32_t &k2, uint32_t &k3) {
+    k0 = n >= 32 ? ~0u : ((1u << n) - 1u);
+    k1 = n >= 64 ? ~0u : (n <= 32 ? 0u : ((1u << (n - 32)) - 1u));
+    k2 = n >= 96 ? ~0u : (n <= 64 ? 0u : ((1u << (n - 64)) - 1u));
+    k3 = n >= 128 ? ~0u : (n <= 96 ? 0u : ((1u << (n - 96)) - 1u));
+}
 
-#ifndef BWB_LANE_MIN_BLOCKS
-#define BWB_LANE_MIN_BLOCKS 3
-#endif
+// Task of owner lane o: interval in sLj[0][o], sUj[0][o]; sFlag[o] bit 0 = "true counts for codes 5,9,11,13"
+// (exact tails use O(), bwt.c:348-372, and -S never sees those codes; expansions in multi-genome mode use
+// O_alphabet with quirk Q1, bwt.c:427-435,780).  Results: sLj[j][o], sUj[j][o] for every j, sOk[o] = valid mask.
+template <class T>
+__device__ __forceinline__ void rank_general(const IndexView &ix, const T *sC, T (*sLj)[128], T (*sUj)[128],
+                                             uint32_t *sOk, const uint8_t *sFlag, uint32_t o, T lastrow) {
+    const T L = sLj[0][o], iU = sUj[0][o];
+    const bool trueq = (sFlag[o] & 1u) != 0u;
+    const T iL = (T)(L - 1);
+    const bool negL = (L == 0), topU = (iU == lastrow);
+    const T aL = negL ? (T)0 : iL, aU = topU ? (T)0 : iU;
+    const uint4 *blkU = ix.blocks + (size_t)(aU >> 7) * 8;
+    const uint4 *blkL = ix.blocks + (size_t)(aL >> 7) * 8;
+    // The two ends one after the other: the upper end's 15 counts stay in registers while the lower end's block
+    // (the same cache line for 83 % of the tasks) is loaded and matched -- half the live registers of doing both
+    // ends side by side, which is what lets 4 blocks of 128 lanes share an SM.
+    uint32_t vU[16];
+    uint32_t firstU = 0;                          // bit j: row 0 of the upper block holds code j (Q1)
+    {
+        const Planes pu = load_planes(blkU);
+        const uint4 q0 = __ldg(blkU), q1 = __ldg(blkU + 1), q2 = __ldg(blkU + 2), q3 = __ldg(blkU + 3);
+        const uint32_t cU[16] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, q3.x, q3.y, q3.z, q3.w};
+        uint32_t k0, k1, k2, k3;
+        low_bits128((int)(aU & 127u) + 1, k0, k1, k2, k3);
+#pragma unroll
+        for (int j = 1; j < 16; j++) {
+            const uint32_t x0 = (j & 1) ? 0u : ~0u, x1 = (j & 2) ? 0u : ~0u, x2 = (j & 4) ? 0u : ~0u, x3 = (j & 8) ? 0u : ~0u;
+            const uint32_t u0 = (pu.p0.x ^ x0) & (pu.p1.x ^ x1) & (pu.p2.x ^ x2) & (pu.p3.x ^ x3);
+            const uint32_t u1 = (pu.p0.y ^ x0) & (pu.p1.y ^ x1) & (pu.p2.y ^ x2) & (pu.p3.y ^ x3);
+            const uint32_t u2 = (pu.p0.z ^ x0) & (pu.p1.z ^ x1) & (pu.p2.z ^ x2) & (pu.p3.z ^ x3);
+            const uint32_t u3 = (pu.p0.w ^ x0) & (pu.p1.w ^ x1) & (pu.p2.w ^ x2) & (pu.p3.w ^ x3);
+            vU[j] = cU[j] + __popc(u0 & k0) + __popc(u1 & k1) + __popc(u2 & k2) + __popc(u3 & k3);
+            if (j == 5 || j == 9 || j == 11 || j == 13) firstU |= (u0 & 1u) << j;
+        }
+    }
+    const Planes pl = load_planes(blkL);
+    const uint4 p0 = __ldg(blkL), p1 = __ldg(blkL + 1), p2 = __ldg(blkL + 2), p3 = __ldg(blkL + 3);
+    const uint32_t cL[16] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w, p2.x, p2.y, p2.z, p2.w, p3.x, p3.y, p3.z, p3.w};
+    uint32_t k0, k1, k2, k3;
+    low_bits128((int)(aL & 127u) + 1, k0, k1, k2, k3);
+    uint32_t okmask = 0;
+#pragma unroll
+    for (int j = 1; j < 16; j++) {
+        const uint32_t x0 = (j & 1) ? 0u : ~0u, x1 = (j & 2) ? 0u : ~0u, x2 = (j & 4) ? 0u : ~0u, x3 = (j & 8) ? 0u : ~0u;
+        const uint32_t l0 = (pl.p0.x ^ x0) & (pl.p1.x ^ x1) & (pl.p2.x ^ x2) & (pl.p3.x ^ x3);
+        const uint32_t l1 = (pl.p0.y ^ x0) & (pl.p1.y ^ x1) & (pl.p2.y ^ x2) & (pl.p3.y ^ x3);
+        const uint32_t l2 = (pl.p0.z ^ x0) & (pl.p1.z ^ x1) & (pl.p2.z ^ x2) & (pl.p3.z ^ x3);
+        const uint32_t l3 = (pl.p0.w ^ x0) & (pl.p1.w ^ x1) & (pl.p2.w ^ x2) & (pl.p3.w ^ x3);
+        const uint32_t vL = cL[j] + __popc(l0 & k0) + __popc(l1 & k1) + __popc(l2 & k2) + __popc(l3 & k3);
+        // Q1: O_alphabet skips codes 5,9,11,13 except for the checkpoint-symbol decrement
+        // (bwt.c:427-435,780); the exact search's O() counts them (bwt.c:348-372)
+        const bool quirk = (j == 5 || j == 9 || j == 11 || j == 13);
+        const T Cj = sC[j], Cj1 = sC[j + 1];
+        T Lj, Uj;
+        if (quirk) {
+            const T qL = trueq ? (T)vL : (T)0 - (T)(l0 & 1u);
+            const T qU = trueq ? (T)vU[j] : (T)0 - (T)((firstU >> j) & 1u);
+            Lj = (T)(Cj + (negL ? (T)0 : qL) + 1);
+            Uj = topU ? Cj1 : (T)(Cj + qU);
+        } else {
+            Lj = (T)(Cj + (negL ? (T)0 : (T)vL) + 1);
+            Uj = topU ? Cj1 : (T)(Cj + (T)vU[j]);
+        }
+        sLj[j][o] = Lj;
+        sUj[j][o] = Uj;
+        okmask |= (Lj <= Uj) ? (1u << j) : 0u;
+    }
+    sOk[o] = okmask;
+}
 
+// Per warp iteration (the 32 reads of a warp advance in lock-step, one interval task each):
+//   A  every lane advances its read: [take a read] -> [exact tail: level end / next interval] ->
+//      [pop + prune + classify]; the outcome is at most one interval task;
+//   B  rank stage: the 15-code loop over both ends of the lane's interval;
+//   C  the result is consumed: next level of the exact tail (align.c:93-110), or the children of the
+//      expansion (inexact_match.c:433-504) -- described per lane, then written by the whole warp, one
+//      child per lane and pass; then [flush] of finished reads.
+// Narrow coordinates: 4 blocks of 128 lanes per SM (128 registers, 55 KB shared memory per block at -n 5);
+// wide (64-bit) coordinates: 3 blocks (the shared-memory child arrays are twice the size).
+#ifndef BWB_LANE_BLOCKS_NARROW
+#define BWB_LANE_BLOCKS_NARROW 4
+#endif
+#define BWB_LANE_MIN_BLOCKS(WIDE) ((WIDE) ? 3 : BWB_LANE_BLOCKS_NARROW)
 template <bool WIDE, bool PRE>
-__global__ void __launch_bounds__(128, BWB_LANE_MIN_BLOCKS) k_search_l(const __grid_constant__ LaneArgs a) {
+__global__ void __launch_bounds__(128, BWB_LANE_MIN_BLOCKS(WIDE)) k_search_l(const __grid_constant__ LaneArgs a) {
     typedef typename Coord<WIDE>::type T;
     __shared__ T sC[17];
-    __shared__ T sLj[16][128], sUj[16][128];      // per-lane child intervals of the current task
+    __shared__ T sLj[16][128], sUj[16][128];      // row 0: the lane's interval; rows 1..15: child intervals by code
+    __shared__ uint32_t sOk[128];                 // valid-child mask per lane
+    __shared__ uint8_t sFlag[128];                // quirk mode of the lane's task
+    __shared__ uint32_t sTe[5][128];              // z, w, r1, r2, r3 of the entry whose exact tail is in progress
+                                                  // (touched when a tail starts / ends: kept out of the register file)
     extern __shared__ uint32_t sm_heads[];        // [nb][128] bucket heads
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     stage_C<T>(a.ix, sC);
 
-    const uint32_t lane_slot = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t lane_slot = blockIdx.x * blockDim.x + tid;
     const T lastrow = (T)(a.ix.length - 1);
     const bool multiref = a.is_multiref != 0;
     LaneAlloc al;
@@ -311,7 +428,7 @@ __global__ void __launch_bounds__(128, BWB_LANE_MIN_BLOCKS) k_search_l(const __g
     al.borrowed = NIL;
     al.borrowed_last = NIL;
     LaneHeap<WIDE> h;
-    h.heads = sm_heads + threadIdx.x;
+    h.heads = sm_heads + tid;
     h.clear();
 
     enum { NEED = 0, SEARCH = 1, TAIL = 2, FLUSH = 3, TADD = 4, DONE = 5 };
@@ -319,12 +436,14 @@ __global__ void __launch_bounds__(128, BWB_LANE_MIN_BLOCKS) k_search_l(const __g
     const uint32_t n_queue = a.n_queue_ptr ? min(*a.n_queue_ptr, a.n_reads) : a.n_reads;
     uint32_t r = 0, read_id = 0;
     int len = 0, err = 0;
-    uint64_t off = 0;
-    const uint16_t *D = nullptr, *Ds = nullptr;
-    const uint8_t *rseq = nullptr;
+    uint32_t off = 0;                         // first base of the read (the host checks that a batch has < 2^32 - n bases)
+    // pointers of the read's arrays, re-derived where they are used instead of being held in 6 registers
+#define BWB_RSEQ (a.seq + off)
+#define BWB_D (a.pk_main + ((size_t)off + r))
+#define BWB_DS (a.pk_seed + (size_t)r * (uint32_t)(a.seed_len + 1))
     int best_score = 0, max_diff = 0, num_best = 0, n_hits = 0;
     uint32_t hit_head = NIL, hit_tail = NIL;
-    // the interval task of this iteration
+    // the interval task of this lane
     bool have_task = false, task_tail = false;
     PE<T> e;                                  // expansion: the popped entry; tail: its L,U hold the interval
     e.L = 0; e.U = 0; e.z = 0; e.w = 0; e.r1 = e.r2 = e.r3 = 0;
@@ -337,8 +456,7 @@ __global__ void __launch_bounds__(128, BWB_LANE_MIN_BLOCKS) k_search_l(const __g
     int nx_bucket = 0;
     uint32_t t_flags = 0;                     // expansion flags, see below
     uint32_t cbase = 0;                       // read base of this step (rc[i-1])
-    // exact tail in progress
-    PE<T> te = e;
+    // exact tail in progress (its entry: sTe)
     int t_bucket = 0, t_r = 0;
     uint32_t cur_head = NIL, nx_head = NIL, nx_tail = NIL;
     int nx_n = 0;
@@ -349,32 +467,31 @@ __global__ void __launch_bounds__(128, BWB_LANE_MIN_BLOCKS) k_search_l(const __g
     // as one is popped (inexact_match.c:309) and best_score never grows.  They are only COUNTED (num_entries
     // feeds the max_entries check, :301), not written to the arena.
     int ghost = 0;
-    unsigned long long c_pops = 0, c_push = 0, c_tails = 0, c_rank = 0;
+    uint32_t c_pops = 0, c_push = 0, c_tails = 0, c_rank = 0;         // per read, added to the launch counters at its flush
     uint32_t c_maxheap = 0, c_maxlist = 0;
+    __syncthreads();
 
-    // Lanes are independent, but without forced reconvergence they drift apart for good (the loop
-    // back-edge is not a reconvergence point): the warp-wide vote at the loop head and the
-    // __syncwarp() before the rank loop keep the 32 reads of a warp in lock-step.
-    while (!__all_sync(FULL, mode == DONE)) {
-        // ================= take the next read =================
+#define BWB_CODE_OF(t) (multiref ? (int)(t) : (int)((0x173Fu >> (4 * (t))) & 15u))
+    for (;;) {
+        if (__all_sync(FULL, mode == DONE)) break;
+        if (!have_task) {
+        // ================= A: take the next read =================
         if (mode == NEED) {
             r = atomicAdd(a.queue, 1u);
             if (r >= n_queue) mode = DONE;
         }
         if (mode == NEED) {
             if (a.order) r = a.order[r];
-            off = a.offsets[r];
-            len = (int)(a.offsets[r + 1] - off);
+            const uint64_t off64 = a.offsets[r];
+            off = (uint32_t)off64;
+            len = (int)(a.offsets[r + 1] - off64);
             read_id = a.read_id_base + r;
-            rseq = a.seq + off;
-            D = a.pk_main + off + r;
-            Ds = a.pk_seed + (size_t)r * (a.seed_len + 1);
+            const uint8_t *rseq = BWB_RSEQ;
             const int nN = (int)a.n_count[r];                           // counted by K3
             h.clear();
             ghost = 0;
             n_hits = 0; hit_head = hit_tail = NIL; err = 0;
             best_score = a.nb; max_diff = a.max_diff; num_best = 0;
-            have_task = false;
             for (int b = 0; b < a.nb; b++) h.heads[b * 128] = NIL;
             have_next = false;
             mode = FLUSH;
@@ -416,7 +533,83 @@ __global__ void __launch_bounds__(128, BWB_LANE_MIN_BLOCKS) k_search_l(const __g
             }
         }
 
-        // ================= pop + prune + classify (inexact_match.c:293-375) =================
+        // ================= A: exact tail -- level end, then the next interval of the level =================
+        if (mode == TAIL) {
+            if (cur_head == NIL) {                                      // level finished
+                if (nx_n) slot_write<T>(a.slots, nx_tail, nx_tailL, nx_tailU, 0u, 0u, NIL, 0u, 0u, 0u);
+                if ((uint32_t)nx_n > c_maxlist) c_maxlist = (uint32_t)nx_n;
+                if (nx_n == 0) {
+                    mode = SEARCH;                                      // no match
+                } else if (t_r > 0) {
+                    t_r--;
+                    cur_head = nx_head; nx_head = nx_tail = NIL; nx_n = 0; nx_w = 0;
+                } else {
+                    // tail matched: bookkeeping of a hit (inexact_match.c:347-362); the intervals are
+                    // then added one per iteration (mode TADD)
+                    const uint32_t z = sTe[0][tid];
+                    const int used = (int)((z >> 8) & 0xffu) + (int)((z >> 24) & 15u) + (int)((z >> 16) & 0xffu);
+                    bool stop = false;
+                    if (n_hits == 0) {
+                        best_score = t_bucket;
+                        max_diff = (used + 1 > a.max_diff) ? a.max_diff : used + 1;
+                    }
+                    if (t_bucket == best_score) num_best = (int)((uint32_t)num_best + nx_w);
+                    else if (num_best > a.max_best) stop = true;
+                    old_tail = hit_tail;                                // dedupe only against earlier hits
+                    cur_head = nx_head; nx_head = nx_tail = NIL; nx_n = 0; nx_w = 0;
+                    mode = stop ? FLUSH : TADD;
+                }
+            }
+            if (mode == TAIL) {                                         // next interval of the current level
+                PE<T> nd;
+                cur_head = slot_read<T>(a.slots, cur_head, nd);
+                e.L = nd.L; e.U = nd.U;
+                cbase = nt4_compl(BWB_RSEQ[len - 1 - t_r]);
+                if (cbase > 3u) {                                       // N never matches (exact_match.c:84-87):
+                    cur_head = nx_head = nx_tail = NIL; nx_n = 0;
+                    mode = SEARCH;                                      // empty result
+                } else {
+                    have_task = true;
+                    task_tail = true;
+                }
+            }
+        } else if (mode == TADD) {                                      // add_alignment per interval (:366-370)
+            if (cur_head == NIL) {
+                mode = SEARCH;
+            } else {
+                const uint32_t q = cur_head;
+                PE<T> nd;
+                cur_head = slot_read<T>(a.slots, q, nd);
+                const T L = nd.L, U = nd.U;
+                const uint32_t z = sTe[0][tid], tw = sTe[1][tid];
+                const int ei = (int)(z & 0xffu);
+                const int go = (int)((z >> 24) & 15u);
+                const uint32_t alen2 = ((uint32_t)(len - ei) + (tw & 0xffu) + (uint32_t)ei) & 0xffu;
+                bool add = true;
+                if (go && old_tail != NIL) {
+                    for (uint32_t p = hit_head;;) {
+                        PE<T> hh;
+                        const uint32_t pb = slot_read<T>(a.slots, p, hh);
+                        if (hh.L == L && hh.U == U) { add = false; break; }
+                        if (pb == old_tail) break;
+                        p = slot_next(a.slots, pb);
+                    }
+                }
+                if (add) {                                              // the node becomes slot A of the hit
+                    const uint32_t sb = lane_alloc(al, a, lane_slot);
+                    if (sb == NIL) { err = BWB_ERR_CAPACITY; mode = FLUSH; }
+                    else {
+                        slot_write<T>(a.slots, q, L, U, z, tw, sb, sTe[2][tid], sTe[3][tid], sTe[4][tid]);
+                        slot_write<T>(a.slots, sb, (T)t_bucket, (T)alen2, 0u, 0u, NIL, 0u, 0u, 0u);
+                        if (hit_tail == NIL) hit_head = q; else slot_set_next(a.slots, hit_tail, q);
+                        hit_tail = sb;
+                        n_hits++;
+                    }
+                }
+            }
+        }
+
+        // ================= A: pop + prune + classify (inexact_match.c:293-375) =================
         if (mode == SEARCH) {
             const int nvirt = h.n + ghost + (have_next ? 1 : 0);      // heap->num_entries of the reference
             if ((uint32_t)nvirt > c_maxheap) c_maxheap = (uint32_t)nvirt;
@@ -438,11 +631,12 @@ __global__ void __launch_bounds__(128, BWB_LANE_MIN_BLOCKS) k_search_l(const __g
                 const int dls = a.max_diff_seed - used;
                 const int si = ei - (len - a.seed_len);
                 // everything this entry may need from the read's arrays, fetched in one go (one latency)
+                const uint16_t *D = BWB_D, *Ds = BWB_DS;
                 const uint32_t dA = D[ei > 0 ? ei - 1 : 0];                 // D[i-1]
                 const uint32_t dB = D[ei > 1 ? ei - 2 : 0];                 // D[i-2]
                 const uint32_t sA = Ds[si > 0 ? si - 1 : 0];                // D_seed[si-1]
                 const uint32_t sB = Ds[si > 1 ? si - 2 : 0];                // D_seed[si-2]
-                const uint32_t base_i1 = rseq[ei > 0 ? len - ei : 0];       // seq[len-1-(i-1)]
+                const uint32_t base_i1 = BWB_RSEQ[ei > 0 ? len - ei : 0];   // seq[len-1-(i-1)]
                 if ((eb & 0xff) > best_score + a.mm_score) {
                     mode = FLUSH;                                       // inexact_match.c:309
                 } else if (dl < 0 || (ei > 0 && dl < (int)(dA & 0x1ff)) || (si > 0 && dls < (int)(sA & 0x1ff))) {
@@ -476,13 +670,16 @@ __global__ void __launch_bounds__(128, BWB_LANE_MIN_BLOCKS) k_search_l(const __g
                         }
                     }
                 } else if (dl == 0) {                                   // exact tail (inexact_match.c:345-375)
+                    // its first level is the entry's own interval: the task of this iteration
                     c_tails++;
-                    te = e; t_bucket = eb; t_r = ei - 1;
-                    const uint32_t s = lane_alloc(al, a, lane_slot);
-                    if (s == NIL) { err = BWB_ERR_CAPACITY; mode = FLUSH; }
-                    else {
-                        slot_write<T>(a.slots, s, e.L, e.U, 0u, 0u, NIL, 0u, 0u, 0u);
-                        cur_head = s; nx_head = nx_tail = NIL; nx_n = 0; nx_w = 0;
+                    sTe[0][tid] = e.z; sTe[1][tid] = e.w; sTe[2][tid] = e.r1; sTe[3][tid] = e.r2; sTe[4][tid] = e.r3;
+                    t_bucket = eb; t_r = ei - 1;
+                    cur_head = nx_head = nx_tail = NIL; nx_n = 0; nx_w = 0;
+                    const uint32_t cb = nt4_compl(base_i1);             // rc[i-1]
+                    if (cb <= 3u) {                                     // (N never matches: empty result, exact_match.c:84-87)
+                        cbase = cb;
+                        have_task = true;
+                        task_tail = true;
                         mode = TAIL;
                     }
                 } else {
@@ -513,184 +710,25 @@ __global__ void __launch_bounds__(128, BWB_LANE_MIN_BLOCKS) k_search_l(const __g
                 }
             }
         }
+        }   // !have_task
 
-        // ================= exact tail: next interval of the current level, or level end =================
-        if (mode == TAIL && !have_task) {
-            if (cur_head != NIL) {
-                {
-                    PE<T> nd;
-                    cur_head = slot_read<T>(a.slots, cur_head, nd);
-                    e.L = nd.L; e.U = nd.U;
-                }
-                cbase = nt4_compl(rseq[len - 1 - t_r]);
-                if (cbase > 3u) {                                       // N never matches (exact_match.c:84-87):
-                    cur_head = nx_head = nx_tail = NIL; nx_n = 0;
-                    mode = SEARCH;                                      // empty result
-                } else {
-                    have_task = true;
-                    task_tail = true;
-                }
-            } else {                                                    // level finished
-                if (nx_n) slot_write<T>(a.slots, nx_tail, nx_tailL, nx_tailU, 0u, 0u, NIL, 0u, 0u, 0u);
-                if ((uint32_t)nx_n > c_maxlist) c_maxlist = (uint32_t)nx_n;
-                if (nx_n == 0) {
-                    mode = SEARCH;                                      // no match
-                } else if (t_r > 0) {
-                    t_r--;
-                    cur_head = nx_head; nx_head = nx_tail = NIL; nx_n = 0; nx_w = 0;
-                } else {
-                    // tail matched: bookkeeping of a hit (inexact_match.c:347-362); the intervals are
-                    // then added one per iteration (mode TADD)
-                    const uint32_t z = te.z;
-                    const int used = (int)((z >> 8) & 0xffu) + (int)((z >> 24) & 15u) + (int)((z >> 16) & 0xffu);
-                    bool stop = false;
-                    if (n_hits == 0) {
-                        best_score = t_bucket;
-                        max_diff = (used + 1 > a.max_diff) ? a.max_diff : used + 1;
-                    }
-                    if (t_bucket == best_score) num_best = (int)((uint32_t)num_best + nx_w);
-                    else if (num_best > a.max_best) stop = true;
-                    old_tail = hit_tail;                                // dedupe only against earlier hits
-                    cur_head = nx_head; nx_head = nx_tail = NIL; nx_n = 0; nx_w = 0;
-                    mode = stop ? FLUSH : TADD;
-                }
-            }
-        } else if (mode == TADD) {                                      // add_alignment per interval (:366-370)
-            if (cur_head == NIL) {
-                mode = SEARCH;
-            } else {
-                const uint32_t q = cur_head;
-                PE<T> nd;
-                cur_head = slot_read<T>(a.slots, q, nd);
-                const T L = nd.L, U = nd.U;
-                const uint32_t z = te.z;
-                const int ei = (int)(z & 0xffu);
-                const int go = (int)((z >> 24) & 15u);
-                const uint32_t alen2 = ((uint32_t)(len - ei) + (te.w & 0xffu) + (uint32_t)ei) & 0xffu;
-                bool add = true;
-                if (go && old_tail != NIL) {
-                    for (uint32_t p = hit_head;;) {
-                        PE<T> hh;
-                        const uint32_t pb = slot_read<T>(a.slots, p, hh);
-                        if (hh.L == L && hh.U == U) { add = false; break; }
-                        if (pb == old_tail) break;
-                        p = slot_next(a.slots, pb);
-                    }
-                }
-                if (add) {                                              // the node becomes slot A of the hit
-                    const uint32_t sb = lane_alloc(al, a, lane_slot);
-                    if (sb == NIL) { err = BWB_ERR_CAPACITY; mode = FLUSH; }
-                    else {
-                        slot_write<T>(a.slots, q, L, U, z, te.w, sb, te.r1, te.r2, te.r3);
-                        slot_write<T>(a.slots, sb, (T)t_bucket, (T)alen2, 0u, 0u, NIL, 0u, 0u, 0u);
-                        if (hit_tail == NIL) hit_head = q; else slot_set_next(a.slots, hit_tail, q);
-                        hit_tail = sb;
-                        n_hits++;
-                    }
-                }
-            }
-        }
-
-        // ================= the interval task: 15-code rank loop =================
+        // ================= B: rank stage =================
         __syncwarp();
         if (have_task) {
+            sLj[0][tid] = e.L;
+            sUj[0][tid] = e.U;
+            sFlag[tid] = (task_tail || !multiref) ? 1 : 0;
+            rank_general<T>(a.ix, sC, sLj, sUj, sOk, sFlag, tid, lastrow);
+        }
+
+        // ================= C: consume the result =================
+        // children of this warp's expansions are described here (owner registers) and written below, one child
+        // per lane and pass, whichever lane owns them
+        uint32_t ch_n = 0, ch_base = NIL, ch_masks = 0, ch_compat = 0, ch_bk = 0;
+        if (have_task) {
             have_task = false;
-            const T iL = (T)(e.L - 1), iU = e.U;
-            const bool negL = (e.L == 0), topU = (iU == lastrow);
-            const T aL = negL ? (T)0 : iL, aU = topU ? (T)0 : iU;
-            const uint4 *blkU = a.ix.blocks + (size_t)(aU >> 7) * 8;
-            const uint4 *blkL = a.ix.blocks + (size_t)(aL >> 7) * 8;
-            const Planes pu = load_planes(blkU);
-            Planes pl = pu;
-            if (blkL != blkU) pl = load_planes(blkL);
-            c_rank += 2;
-            // 128-bit masks of rows 0..r of both blocks
-            uint32_t kU0, kU1, kU2, kU3, kL0, kL1, kL2, kL3;
-            {
-                const int n = (int)(aU & 127u) + 1;
-                kU0 = n >= 32 ? ~0u : ((1u << n) - 1u);
-                kU1 = n >= 64 ? ~0u : (n <= 32 ? 0u : ((1u << (n - 32)) - 1u));
-                kU2 = n >= 96 ? ~0u : (n <= 64 ? 0u : ((1u << (n - 64)) - 1u));
-                kU3 = n >= 128 ? ~0u : (n <= 96 ? 0u : ((1u << (n - 96)) - 1u));
-                const int m = (int)(aL & 127u) + 1;
-                kL0 = m >= 32 ? ~0u : ((1u << m) - 1u);
-                kL1 = m >= 64 ? ~0u : (m <= 32 ? 0u : ((1u << (m - 32)) - 1u));
-                kL2 = m >= 96 ? ~0u : (m <= 64 ? 0u : ((1u << (m - 64)) - 1u));
-                kL3 = m >= 128 ? ~0u : (m <= 96 ? 0u : ((1u << (m - 96)) - 1u));
-            }
-#ifdef BWB_LANE_CNT128
-            // the 16 checkpoint counters of both blocks, four 128-bit loads each
-            uint32_t cU[16], cL[16];
-            {
-                const uint4 q0 = __ldg(blkU), q1 = __ldg(blkU + 1), q2 = __ldg(blkU + 2), q3 = __ldg(blkU + 3);
-                cU[0] = q0.x; cU[1] = q0.y; cU[2] = q0.z; cU[3] = q0.w; cU[4] = q1.x; cU[5] = q1.y; cU[6] = q1.z; cU[7] = q1.w;
-                cU[8] = q2.x; cU[9] = q2.y; cU[10] = q2.z; cU[11] = q2.w; cU[12] = q3.x; cU[13] = q3.y; cU[14] = q3.z; cU[15] = q3.w;
-                const uint4 p0 = __ldg(blkL), p1 = __ldg(blkL + 1), p2 = __ldg(blkL + 2), p3 = __ldg(blkL + 3);
-                cL[0] = p0.x; cL[1] = p0.y; cL[2] = p0.z; cL[3] = p0.w; cL[4] = p1.x; cL[5] = p1.y; cL[6] = p1.z; cL[7] = p1.w;
-                cL[8] = p2.x; cL[9] = p2.y; cL[10] = p2.z; cL[11] = p2.w; cL[12] = p3.x; cL[13] = p3.y; cL[14] = p3.z; cL[15] = p3.w;
-            }
-#else
-            const uint32_t *cU = reinterpret_cast<const uint32_t *>(blkU);   // checkpoint counters (same line as the planes)
-            const uint32_t *cL = reinterpret_cast<const uint32_t *>(blkL);
-#endif
-            // expansion-only values
-            const uint32_t z = e.z;
-            const int go = (int)((z >> 24) & 15u);
-            const bool opening = ((z >> 28) & 3u) == 0u;
-            const int b0 = eb, b1 = eb + a.mm_score, b2 = eb + (opening ? a.gapo_score : a.gape_score);
-            const bool full = t_flags & 1u, del_ok = t_flags & 2u, ins_ok = t_flags & 4u;
-            const uint32_t alen = task_tail ? 0u : (((uint32_t)(len - (int)(z & 0xffu)) + (e.w & 0xffu)) & 0xffu);
-            // gap children share everything but L,U,state
-            const uint32_t zg = (z & ~(3u << 28)) + (opening ? (1u << 24) : (1u << 16));
-            uint32_t wI = e.w, wD = e.w + 1u, r1I = e.r1, r2I = e.r2, r3I = e.r3, r1D = e.r1, r2D = e.r2, r3D = e.r3;
-            if (!task_tail) {
-                const uint32_t newrunI = alen | (1u << 8) | (1u << 16), newrunD = alen | (1u << 8) | (2u << 16);
-                if (opening) {
-                    if (go == 0) { wI = (wI & 0xffu) | (newrunI << 8); wD = (wD & 0xffu) | (newrunD << 8); }
-                    else if (WIDE && go == 1) { r1I = newrunI; r1D = newrunD; }
-                    else if (WIDE && go == 2) { r2I = newrunI; r2D = newrunD; }
-                    else if (WIDE) { r3I = newrunI; r3D = newrunD; }
-                } else {
-                    if (go == 1) { wI += 1u << 16; wD += 1u << 16; }
-                    else if (WIDE && go == 2) { r1I += 1u << 8; r1D += 1u << 8; }
-                    else if (WIDE && go == 3) { r2I += 1u << 8; r2D += 1u << 8; }
-                    else if (WIDE && go == 4) { r3I += 1u << 8; r3D += 1u << 8; }
-                }
-            }
-            const uint32_t zm = (z - 1u) & ~(3u << 28);
-            // ---- (1) ranks of all 15 codes at both ends: straight-line code, results to shared memory
-            uint32_t okmask = 0;
-#pragma unroll
-            for (int j = 1; j < 16; j++) {
-                const uint32_t x0 = (j & 1) ? 0u : ~0u, x1 = (j & 2) ? 0u : ~0u, x2 = (j & 4) ? 0u : ~0u, x3 = (j & 8) ? 0u : ~0u;
-                const uint32_t u0 = (pu.p0.x ^ x0) & (pu.p1.x ^ x1) & (pu.p2.x ^ x2) & (pu.p3.x ^ x3);
-                const uint32_t u1 = (pu.p0.y ^ x0) & (pu.p1.y ^ x1) & (pu.p2.y ^ x2) & (pu.p3.y ^ x3);
-                const uint32_t u2 = (pu.p0.z ^ x0) & (pu.p1.z ^ x1) & (pu.p2.z ^ x2) & (pu.p3.z ^ x3);
-                const uint32_t u3 = (pu.p0.w ^ x0) & (pu.p1.w ^ x1) & (pu.p2.w ^ x2) & (pu.p3.w ^ x3);
-                const uint32_t l0 = (pl.p0.x ^ x0) & (pl.p1.x ^ x1) & (pl.p2.x ^ x2) & (pl.p3.x ^ x3);
-                const uint32_t l1 = (pl.p0.y ^ x0) & (pl.p1.y ^ x1) & (pl.p2.y ^ x2) & (pl.p3.y ^ x3);
-                const uint32_t l2 = (pl.p0.z ^ x0) & (pl.p1.z ^ x1) & (pl.p2.z ^ x2) & (pl.p3.z ^ x3);
-                const uint32_t l3 = (pl.p0.w ^ x0) & (pl.p1.w ^ x1) & (pl.p2.w ^ x2) & (pl.p3.w ^ x3);
-                const uint32_t vU = BWB_CNT(cU, j) + __popc(u0 & kU0) + __popc(u1 & kU1) + __popc(u2 & kU2) + __popc(u3 & kU3);
-                const uint32_t vL = BWB_CNT(cL, j) + __popc(l0 & kL0) + __popc(l1 & kL1) + __popc(l2 & kL2) + __popc(l3 & kL3);
-                // Q1: O_alphabet skips codes 5,9,11,13 except for the checkpoint-symbol decrement
-                // (bwt.c:427-435,780); the exact search's O() counts them (bwt.c:348-372)
-                const bool quirk = (j == 5 || j == 9 || j == 11 || j == 13);
-                const T Cj = sC[j], Cj1 = sC[j + 1];
-                T Lj, Uj;
-                if (quirk) {
-                    const T qL = (task_tail || !multiref) ? (T)vL : (T)0 - (T)(l0 & 1u);
-                    const T qU = (task_tail || !multiref) ? (T)vU : (T)0 - (T)(u0 & 1u);
-                    Lj = (T)(Cj + (negL ? (T)0 : qL) + 1);
-                    Uj = topU ? Cj1 : (T)(Cj + qU);
-                } else {
-                    Lj = (T)(Cj + (negL ? (T)0 : (T)vL) + 1);
-                    Uj = topU ? Cj1 : (T)(Cj + (T)vU);
-                }
-                sLj[j][threadIdx.x] = Lj;
-                sUj[j][threadIdx.x] = Uj;
-                okmask |= (Lj <= Uj) ? (1u << j) : 0u;
-            }
+            c_rank += 2u;
+            uint32_t okmask = sOk[tid];
             // Child index space t: multi-genome t = code (1..15, the reference's loop order);
             // single-genome (-S) t = 0..3 = A,G,C,T = codes 15,3,7,1 (O_actg_alphabet's order, bwt.c:440-463).
             // compat_set = indices that MATCH the read base: nucl_bases_table[c] (io.h:102-106, N excluded)
@@ -699,15 +737,14 @@ __global__ void __launch_bounds__(128, BWB_LANE_MIN_BLOCKS) k_search_l(const __g
                 okmask = ((okmask >> 15) & 1u) | (((okmask >> 3) & 1u) << 1) | (((okmask >> 7) & 1u) << 2) | (((okmask >> 1) & 1u) << 3);
             const uint32_t compat_set = !multiref ? (cbase < 4u ? (1u << cbase) : 0u)
                 : (cbase == 0 ? 0xFB00u : (cbase == 1 ? 0x383Cu : (cbase == 2 ? 0x0BF0u : (cbase == 3 ? 0x6266u : 0u))));
-#define BWB_CODE_OF(t) (multiref ? (int)(t) : (int)((0x173Fu >> (4 * (t))) & 15u))
-            bool ok_all = true;
             if (task_tail) {
-                // ---- (2a) exact tail: ordered append with adjacent merge (align.c:93-110)
+                // ---- exact tail: ordered append with adjacent merge (align.c:93-110)
+                bool ok_all = true;
                 uint32_t m = okmask & compat_set;
                 while (m) {
                     const int j = BWB_CODE_OF(__ffs(m) - 1);
                     m &= m - 1;
-                    const T Lj = sLj[j][threadIdx.x], Uj = sUj[j][threadIdx.x];
+                    const T Lj = sLj[j][tid], Uj = sUj[j][tid];
                     nx_w += (uint32_t)(Uj - Lj + 1);
                     if (nx_n && Lj == (T)(nx_tailU + 1)) {
                         nx_tailU = Uj;
@@ -720,9 +757,16 @@ __global__ void __launch_bounds__(128, BWB_LANE_MIN_BLOCKS) k_search_l(const __g
                         nx_n++;
                     }
                 }
+                if (!ok_all) { err = BWB_ERR_CAPACITY; mode = FLUSH; }
             } else {
-                // ---- (2b) children in the reference's push order (:433-504): insertion, deletions by
-                // code, then matches/mismatches by code; the k-th child of every lane is pushed together
+                // ---- children in the reference's push order (:433-504): insertion, deletions by code, then
+                // matches/mismatches by code.  Here: which children exist, which of them is the next pop, which are
+                // dead; their slots (contiguous, in push order) and the bucket bookkeeping.
+                const uint32_t z = e.z;
+                const bool opening = ((z >> 28) & 3u) == 0u;
+                const int b0 = eb, b1 = eb + a.mm_score, b2 = eb + (opening ? a.gapo_score : a.gape_score);
+                const bool full = t_flags & 1u, del_ok = t_flags & 2u, ins_ok = t_flags & 4u;
+                const uint32_t zm = (z - 1u) & ~(3u << 28);
                 uint32_t md = del_ok ? okmask : 0u;
                 uint32_t mmk = full ? okmask : (okmask & compat_set);
                 c_push += __popc(md) + __popc(mmk) + (ins_ok ? 1u : 0u);
@@ -733,7 +777,7 @@ __global__ void __launch_bounds__(128, BWB_LANE_MIN_BLOCKS) k_search_l(const __g
                     const int jk = 31 - __clz(cand);
                     mmk &= ~(1u << jk);
                     have_next = true;
-                    nx.L = sLj[BWB_CODE_OF(jk)][threadIdx.x]; nx.U = sUj[BWB_CODE_OF(jk)][threadIdx.x];
+                    nx.L = sLj[BWB_CODE_OF(jk)][tid]; nx.U = sUj[BWB_CODE_OF(jk)][tid];
                     nx.z = zm + (((compat_set >> jk) & 1u) ? 0u : 0x100u);
                     nx.w = e.w; nx.r1 = e.r1; nx.r2 = e.r2; nx.r3 = e.r3;
                     nx_bucket = b0;
@@ -746,31 +790,131 @@ __global__ void __launch_bounds__(128, BWB_LANE_MIN_BLOCKS) k_search_l(const __g
                     if (b1 > dead_lim) { ghost += __popc(mmk & ~compat_set); mmk &= compat_set; }
                 }
 #endif
-                // occupancy bits once per score class (of what is really pushed) instead of once per child
-                if (ins_live || md) h.mark(b2);
-                if (mmk & ~compat_set) h.mark(b1);
-                if (mmk & compat_set) h.mark(b0);
-                if (ins_live) ok_all = h.push(al, a, lane_slot, b2, e.L, e.U, (zg | (1u << 28)) - 1u, wI, r1I, r2I, r3I);
-                while (md | mmk) {
-                    const bool isdel = md != 0u;
-                    const uint32_t cm = isdel ? md : mmk;
-                    const int t = __ffs(cm) - 1;
-                    const int j = BWB_CODE_OF(t);
-                    if (isdel) md &= md - 1; else mmk &= mmk - 1;
-                    const T Lj = sLj[j][threadIdx.x], Uj = sUj[j][threadIdx.x];
-                    const bool is_mm = !((compat_set >> t) & 1u);
-                    const int sc = isdel ? b2 : (is_mm ? b1 : b0);
-                    const uint32_t cz = isdel ? (zg | (2u << 28)) : (zm + (is_mm ? 0x100u : 0u));
-                    ok_all &= h.push(al, a, lane_slot, sc, Lj, Uj, cz, isdel ? wD : e.w, isdel ? r1D : e.r1,
-                                     isdel ? r2D : e.r2, isdel ? r3D : e.r3);
+                const uint32_t n = (ins_live ? 1u : 0u) + (uint32_t)__popc(md) + (uint32_t)__popc(mmk);
+                if (n) {
+                    ch_base = lane_alloc_n(al, a, lane_slot, n);
+                    if (ch_base == NIL) { err = BWB_ERR_CAPACITY; mode = FLUSH; }
+                    else {
+                        // occupancy bits once per score class (of what is really pushed)
+                        if (ins_live || md) h.mark(b2);
+                        if (mmk & ~compat_set) h.mark(b1);
+                        if (mmk & compat_set) h.mark(b0);
+                        h.n += (int)n;
+                        ch_n = n;
+                        ch_masks = md | (mmk << 16);
+                        ch_compat = (compat_set & 0xffffu) | (ins_live ? (1u << 16) : 0u);
+                        ch_bk = (uint32_t)b0 | ((uint32_t)b1 << 8) | ((uint32_t)b2 << 16) | ((uint32_t)len << 24);
+                    }
                 }
             }
-#undef BWB_CODE_OF
-            if (!ok_all) { err = BWB_ERR_CAPACITY; mode = FLUSH; }
         }
 
+        // ---- the children of all 32 lanes, flattened: child q of owner o is item P(o) + q; each pass writes 32
+        // of them.  (Round-1 pushed the k-th child of every lane together: max-over-lanes iterations with 5 of 32
+        // lanes busy, 30 % of all issued instructions.)
+        {
+            uint32_t inc = ch_n;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(FULL, inc, o);
+                if ((int)lane >= o) inc += t;
+            }
+            const uint32_t total = __shfl_sync(FULL, inc, 31);
+            const uint32_t pex = inc - ch_n;
+            for (uint32_t t0 = 0; t0 < total; t0 += 32u) {
+                const uint32_t t = t0 + lane;
+                const bool on = t < total;
+                // owner = last lane whose exclusive prefix is <= t
+                int o = 0;
+#pragma unroll
+                for (int s = 16; s > 0; s >>= 1) {
+                    const uint32_t v = __shfl_sync(FULL, pex, o + s);
+                    if (v <= t) o += s;
+                }
+                const uint32_t q = t - __shfl_sync(FULL, pex, o);
+                const uint32_t base = __shfl_sync(FULL, ch_base, o);
+                const uint32_t masks = __shfl_sync(FULL, ch_masks, o);
+                const uint32_t cmp = __shfl_sync(FULL, ch_compat, o);
+                const uint32_t bk = __shfl_sync(FULL, ch_bk, o);
+                const uint32_t pz = __shfl_sync(FULL, e.z, o), pw = __shfl_sync(FULL, e.w, o);
+                const T pL = shfl(e.L, o), pU = shfl(e.U, o);
+                uint32_t pr1 = 0, pr2 = 0, pr3 = 0;
+                if (WIDE) { pr1 = __shfl_sync(FULL, e.r1, o); pr2 = __shfl_sync(FULL, e.r2, o); pr3 = __shfl_sync(FULL, e.r3, o); }
+                const uint32_t otid = (warp << 5) + (uint32_t)o;
+                const uint32_t md = masks & 0xffffu, mmk = masks >> 16, compat = cmp & 0xffffu;
+                const uint32_t n_ins = (cmp >> 16) & 1u, n_gap = n_ins + (uint32_t)__popc(md);
+                const int b0 = (int)(bk & 0xffu), b1 = (int)((bk >> 8) & 0xffu), b2 = (int)((bk >> 16) & 0xffu);
+                const bool is_gap = q < n_gap;
+                // mm children that share a bucket with the gap children (score classes can coincide)
+                const uint32_t mm_in_b2 = mmk & (((b0 == b2) ? compat : 0u) | ((b1 == b2) ? ~compat : 0u));
+                T cL, cU;
+                uint32_t cz, cw = pw, cr1 = pr1, cr2 = pr2, cr3 = pr3, nxt_slot = NIL;
+                int X;
+                bool need_old, last;
+                if (is_gap) {
+                    const bool is_ins = q < n_ins;
+                    const bool opening = ((pz >> 28) & 3u) == 0u;
+                    const int go = (int)((pz >> 24) & 15u);
+                    const uint32_t zg = (pz & ~(3u << 28)) + (opening ? (1u << 24) : (1u << 16));
+                    const uint32_t alen = ((uint32_t)((int)(bk >> 24) - (int)(pz & 0xffu)) + (pw & 0xffu)) & 0xffu;
+                    const uint32_t newrun = alen | (1u << 8) | ((is_ins ? 1u : 2u) << 16);
+                    if (!is_ins) cw = pw + 1u;
+                    if (opening) {
+                        if (go == 0) cw = (cw & 0xffu) | (newrun << 8);
+                        else if (WIDE && go == 1) cr1 = newrun;
+                        else if (WIDE && go == 2) cr2 = newrun;
+                        else if (WIDE) cr3 = newrun;
+                    } else {
+                        if (go == 1) cw += 1u << 16;
+                        else if (WIDE && go == 2) cr1 += 1u << 8;
+                        else if (WIDE && go == 3) cr2 += 1u << 8;
+                        else if (WIDE && go == 4) cr3 += 1u << 8;
+                    }
+                    X = b2;
+                    need_old = (q == 0u);
+                    if (!need_old) nxt_slot = base + q - 1u;
+                    last = (q + 1u == n_gap) && (mm_in_b2 == 0u);
+                    if (is_ins) {
+                        cL = pL; cU = pU;
+                        cz = (zg | (1u << 28)) - 1u;
+                    } else {
+                        const int j = BWB_CODE_OF(kth_bit16(md, q - n_ins));
+                        cL = sLj[j][otid]; cU = sUj[j][otid];
+                        cz = zg | (2u << 28);
+                    }
+                } else {
+                    const int tt = on ? kth_bit16(mmk, q - n_gap) : 0;
+                    const bool is_mm = !((compat >> tt) & 1u);
+                    X = is_mm ? b1 : b0;
+                    const uint32_t same = mmk & (((b0 == X) ? compat : 0u) | ((b1 == X) ? ~compat : 0u));
+                    const uint32_t below = same & ((1u << tt) - 1u);
+                    need_old = false;
+                    if (below) {
+                        const int pc = 31 - __clz(below);
+                        nxt_slot = base + n_gap + (uint32_t)__popc(mmk & ((1u << pc) - 1u));
+                    } else if (b2 == X && n_gap > 0u) {
+                        nxt_slot = base + n_gap - 1u;
+                    } else {
+                        need_old = true;
+                    }
+                    last = (same >> (tt + 1)) == 0u;
+                    const int j = BWB_CODE_OF(tt);
+                    cL = sLj[j][otid]; cU = sUj[j][otid];
+                    cz = ((pz - 1u) & ~(3u << 28)) + (is_mm ? 0x100u : 0u);
+                }
+                uint32_t *hd = sm_heads + (uint32_t)X * 128u + otid;
+                if (on && need_old) nxt_slot = *hd;
+                __syncwarp();                                            // old heads are read before new ones are written
+                if (on) {
+                    slot_write<T>(a.slots, base + q, cL, cU, cz, cw, nxt_slot, cr1, cr2, cr3);
+                    if (last) *hd = base + q;
+                }
+            }
+        }
+#undef BWB_CODE_OF
+
         // ================= flush: hits -> output group (K5 restores input order) =================
-        if (mode == FLUSH) {
+        if (mode == FLUSH && !have_task) {
             if (err) {
                 // out of arena: with every lane busy on a big heap the shared pool can run dry.  The read is
                 // handed to the next pass, which runs only the deferred reads (so each finds far more room);
@@ -804,16 +948,20 @@ __global__ void __launch_bounds__(128, BWB_LANE_MIN_BLOCKS) k_search_l(const __g
             }
             a.read_off[r] = base;
             a.read_cnt[r] = (uint32_t)n_hits;
+            atomicAdd(a.counters + 0, (unsigned long long)c_pops);
+            atomicAdd(a.counters + 1, (unsigned long long)c_push);
+            atomicAdd(a.counters + 2, (unsigned long long)c_tails);
+            atomicAdd(a.counters + 3, (unsigned long long)c_rank);
+            c_pops = c_push = c_tails = c_rank = 0u;
             lane_alloc_reset(al, a, lane_slot);
             have_next = false;
             mode = NEED;
         }
     }
 
-    atomicAdd(a.counters + 0, c_pops);
-    atomicAdd(a.counters + 1, c_push);
-    atomicAdd(a.counters + 2, c_tails);
-    atomicAdd(a.counters + 3, c_rank);
+#undef BWB_RSEQ
+#undef BWB_D
+#undef BWB_DS
     atomicMax(a.counters + 4, (unsigned long long)c_maxheap);
     atomicMax(a.counters + 5, (unsigned long long)c_maxlist);
 }

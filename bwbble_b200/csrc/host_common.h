@@ -25,6 +25,8 @@ int prepare_index_text(const char *fasta_path, int write_ref_file, std::vector<u
 // device 0 of a context and its launch stream (cudaStream_t as void*), for host modules outside bwb_abi.cu
 int ctx_device(const struct ::bwb_ctx *ctx, int *device_id, void **stream);
 int ctx_fail(struct ::bwb_ctx *ctx, int code, const char *msg);
+// options of the device index builder: returns the "index_wide" flag, *chunk = "index_chunk" (0 = default)
+bool ctx_index_options(const struct ::bwb_ctx *ctx, long long *chunk);
 
 // .pre file of `bwbble align -P` (store_sa_interval_list / load_sa_interval_list, align.c:144-172,
 // written row by row by precalc_sa_intervals, align.c:200-224): 4^12 records {int32 n; n x (u64 L, u64 U)}

@@ -11,10 +11,17 @@ from bwbble_b200.aln import first_difference
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module", params=["lane-idx32", "lane-idx64", "group-idx32", "group-idx64", "warp-idx32", "warp-idx64"])
+import os
+
+# the two A/B engines of round 1 (warp per read, 8 lanes per read) are only built with -DBWB_AB_ENGINES
+_ENGINES = ["lane-idx32", "lane-idx64"] + (["group-idx32", "group-idx64", "warp-idx32", "warp-idx64"]
+                                           if os.environ.get("BWBBLE_TEST_AB_ENGINES") else [])
+
+
+@pytest.fixture(scope="module", params=_ENGINES)
 def gpu_case(small_case, request):
     """lane = production engine (one read per lane: k_calc_d_g + k_search_l); group (8 lanes per read)
-    and warp (k_align) are the A/B baselines the profiles compare against;
+    and warp (k_align) are the A/B baselines the round-1 profiles compare against;
     idx32 = 32-bit SA coordinates + 16-byte heap entries (indexes < 2^32 rows, max_gapo <= 1);
     idx64 = the wide kernels (genome-scale format) forced onto the same small index."""
     al = Aligner(heap_pool_mb=512, hits_per_read=256, list_cap=1024)
@@ -250,6 +257,37 @@ def test_align_empty_batch_and_all_n_read(gpu_case):
     assert got == exp
 
 
+def test_hit_buffer_regrow_after_overflow(small_case):
+    """with more hits than the output buffers hold, K5 must not touch memory; the host regrows and
+    re-runs the shard.  hit_cap0=0 forces that path on the first attempt."""
+    reads = small_case["reads"]
+    p = default_params(n=3)
+    orc = oracle.Oracle(small_case["bwt"])
+    exp, _ = orc.align(reads.seq, reads.offsets, p)
+    orc.close()
+    for wide in (0, 1):
+        with Aligner(heap_pool_mb=256) as al:
+            if wide:
+                al.set_option("force_wide", 1)
+            al.set_option("hit_cap0", 0)
+            al.load_index(small_case["bwt"], with_sa=True)          # K6 runs behind K5 as well
+            got = al.align(reads.seq, reads.offsets, p).aln_bytes()
+            assert got == exp, first_difference(got, exp)
+
+
+def test_stale_resident_results_fail_loudly(gpu_case):
+    """un-fetched results point into per-context buffers; a later launch invalidates them."""
+    from bwbble_b200 import BwbError
+    al, reads = gpu_case["al"], gpu_case["reads"]
+    p = default_params(n=2)
+    dr = al.upload_reads(reads.seq, reads.offsets)
+    first = al.align_resident(dr, p, fetch=False)
+    second = al.align_resident(dr, p, fetch=False)
+    with pytest.raises(BwbError):
+        first.fetch()
+    assert second.fetch().aln_bytes() == al.align(reads.seq, reads.offsets, p).aln_bytes()
+
+
 def test_resident_path_equals_host_path(gpu_case):
     al, reads = gpu_case["al"], gpu_case["reads"]
     p = default_params(n=3)
@@ -477,11 +515,14 @@ def test_precalc_misuse_fails_loudly(small_case):
         with pytest.raises(BwbError):                    # table of the other mode
             al.align(reads.seq, reads.offsets, default_params(n=2, use_precalc=1, is_multiref=0))
     with Aligner(heap_pool_mb=256) as al:
-        al.set_option("engine", 1)
         al.load_index(small_case["bwt"])
         al.build_precalc(True)
-        with pytest.raises(BwbError):                    # only the production engine seeds from the table
+        al.load_index(small_case["bwt"])                 # a new index drops the table computed on the old one
+        with pytest.raises(BwbError):
             al.align(reads.seq, reads.offsets, default_params(n=2, use_precalc=1))
+    with Aligner(heap_pool_mb=256) as al:                # the round-1 A/B engines are not in the default build
+        with pytest.raises(BwbError):
+            al.set_option("engine", 1)
 
 
 def test_heavy_first_queue_order_is_result_neutral(small_case):
@@ -582,3 +623,43 @@ def test_150bp_gapped_reads_config5_shape(small_case):
             assert got == exp, first_difference(got, exp)
             ctr = res.counters()
             assert ctr["pops"] == st["pops"] and ctr["pushes"] == st["pushes"]
+
+
+# ---- K7w: the chunked 64-bit suffix sorter (genome-scale builder) forced onto small genomes ---------------
+@pytest.mark.parametrize("chunk", [2500, 6000, 1 << 20])
+def test_wide_device_index_build_equals_the_reference_files(tmp_path, chunk):
+    """the builder that indexes the 6.9 G-row genome (64-bit ranks, bounded sort chunks), run with chunks far
+    smaller than the text: same bytes as the unmodified reference's `bwbble index g.fa`"""
+    import golden_util as G
+    import hashlib
+    from bwbble_b200 import index
+    fa = str(tmp_path / "g.fa")
+    open(fa, "wb").write(G.golden_bytes("g.fa"))
+    with Aligner(heap_pool_mb=64) as al:
+        al.set_option("index_wide", 1)
+        al.set_option("index_chunk", chunk)
+        index.build_index(fa, aligner=al)
+        assert al.last_index_sort_rounds >= 2
+    assert hashlib.md5(open(fa + ".bwt", "rb").read()).hexdigest() == G.MANIFEST["md5"]["g.fa.bwt"]
+    assert open(fa + ".ann", "rb").read() == G.golden_bytes("g.fa.ann")
+
+
+def test_wide_device_index_build_on_deep_repeats(tmp_path):
+    """N runs of 10^5 rows share their first symbols: groups far larger than most chunks would allow, 15+ rounds"""
+    from bwbble_b200 import BwbError, index, synth
+    g = synth.make_genome(77, 400_000, n_records=3, snp_rate=0.012, tri_frac=0.05, n_bubbles=60, n_frac=0.3,
+                          n_repeat_copies=6, repeat_len=3000, n_microsats=4, lowercase_frac=0.01)
+    a, b = str(tmp_path / "a.fa"), str(tmp_path / "b.fa")
+    g.write_fasta(a)
+    g.write_fasta(b)
+    index.build_index(a)
+    with Aligner(heap_pool_mb=64) as al:
+        al.set_option("index_wide", 1)
+        al.set_option("index_chunk", 4096)
+        with pytest.raises(BwbError):                    # the N-run group does not fit a 4096-row chunk: loud, not wrong
+            index.build_index(b, aligner=al)
+        al.set_option("index_chunk", 300_000)
+        index.build_index(b, aligner=al)
+        assert al.last_index_sort_rounds >= 10
+    assert open(a + ".bwt", "rb").read() == open(b + ".bwt", "rb").read()
+    assert open(a + ".ann", "rb").read() == open(b + ".ann", "rb").read()
