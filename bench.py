@@ -51,12 +51,12 @@ WORKLOADS = {
                         cpu_sample=131072, params_str="-n 0 (exact-match only)",
                         desc="synthetic chr21-scale multi-genome (48.1 Mbp, 27% N, 1.2% SNP, 40k bubbles); 100bp reads, 0 edits, exact search"),
     # BASELINE configs[3]: GRCh37-scale multi-genome, >= 2^32 BWT rows (64-bit kernels, HBM-resident index)
-    "genome": dict(index="genome", genome=_GENOME, reads=dict(read_len=100, max_sub=2), params=dict(n=5), batch=1 << 21,
+    "genome": dict(index="genome", genome=_GENOME, reads=dict(read_len=100, max_sub=2), params=dict(n=5), batch=1 << 20,
                    cpu_sample=8192, params_str="-n 5 -k 2 -l 32 -o 1 -e 6 -M 3 -O 11 -E 4",
                    desc="synthetic 3.1 Gbp GRCh37-scale multi-genome (6.9 G BWT rows, 24 records, 5% N, 1.2% SNP, 1.4M bubbles); 100bp reads, 0-2 subs"),
     # BASELINE configs[4]: 150 bp reads, up to 4 differences with gaps, same genome-scale index
     "genome-150": dict(index="genome", genome=_GENOME, reads=dict(read_len=150, max_sub=3, indel_frac=0.4), params=dict(n=4, o=1, e=6),
-                       batch=1 << 20, cpu_sample=4096, params_str="-n 4 -o 1 -e 6 (150 bp, gaps)",
+                       batch=1 << 19, cpu_sample=4096, params_str="-n 4 -o 1 -e 6 (150 bp, gaps)",
                        desc="synthetic 3.1 Gbp GRCh37-scale multi-genome (6.9 G BWT rows); 150bp reads, 0-3 subs + one 1-3 bp indel in 40% of the reads"),
     # 600 M-row index (HBM-resident, ~5x L2): the regime of configs[3] at 1/11 of its size
     "g300": dict(index="g300", genome=_G300, reads=dict(read_len=100, max_sub=2), params=dict(n=5), batch=1 << 21,
@@ -192,6 +192,8 @@ def run_cpu_reference(fa: str, reads, n_sample: int, params: dict, threads: int,
             t = time.time()
             subprocess.run(cmd + [fq, os.path.join(d, "s.aln")], check=True, stdout=subprocess.DEVNULL)
             full_s = time.time() - t
+            import hashlib
+            out["ref_aln_md5"] = hashlib.md5(open(os.path.join(d, "s.aln"), "rb").read()).hexdigest()
         out.update(kind="reference", value=n_sample / max(full_s - load_s, 1e-6), load_s=load_s)
     else:
         if not want_stats:
@@ -415,6 +417,12 @@ def main():
             sub = batches[args.warmup % nd].slice(0, n_q)
             got = al.align(sub.seq, sub.offsets, p).aln_bytes()
             parity = {"reads": n_q, "identical_to_oracle": got == cpu.pop("port_aln_bytes"), "aln_bytes": len(got)}
+            if cpu.get("ref_aln_md5"):
+                # and the whole CPU sample against the .aln file the unmodified reference binary just wrote
+                import hashlib
+                sub = batches[args.warmup % nd].slice(0, n_s)
+                got = al.align(sub.seq, sub.offsets, p).aln_bytes()
+                parity.update(reference_binary_reads=n_s, identical_to_reference_binary=hashlib.md5(got).hexdigest() == cpu["ref_aln_md5"])
         occ = {}
         try:
             nq = 1 << 26

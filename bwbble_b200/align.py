@@ -83,7 +83,7 @@ class AlignResult:
     def counters(self) -> dict:
         arr = (C.c_uint64 * 8)()
         _lib.check(_lib.lib().bwb_results_counters(self._h, C.byref(arr)), self._a._ctx)
-        names = ["pops", "pushes", "exact_tails", "rank_queries", "max_heap", "max_list"]
+        names = ["pops", "pushes", "exact_tails", "rank_queries", "max_heap", "max_list", "deferred_pass1", "deferred_pass2"]
         return {k: int(arr[i]) for i, k in enumerate(names)}
 
     @property

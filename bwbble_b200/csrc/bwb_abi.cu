@@ -84,6 +84,8 @@ struct bwb_ctx {
                               // 2 = 8-lane groups (k_calc_d_g + k_search_g); 1 and 2 are A/B baselines
     int use_ktab = 1;         // k-mer table for calculate_d's top of tree (0 = off, for A/B and tests)
     int force_wide = 0;       // tests: run the 64-bit / 32-byte-entry kernels on a small index
+    int recycle = 0;                 // K4 slot recycling: 0 = auto (index > 2^28 rows, reads > 128 bases, wide entries), 1 = on, 2 = off
+    int arena_private_pct = 25;      // share of the K4 arena split into private per-lane ranges (rest: shared block pool)
     long long index_chunk = 0;       // K7w: suffixes per sort chunk (0 = 2^29)
     int index_wide = 0;              // tests: force the chunked 64-bit suffix sorter on a small genome
     long long hit_cap0 = -1;  // tests: initial capacity of the hit buffers (-1 = 2 per read + 65536), forces the regrow path
@@ -287,6 +289,15 @@ int prepare_search_group(bwb_ctx *ctx, Device &d, const SmemLayout &L, bool wide
 
 #endif  // BWB_AB_ENGINES
 
+// the eight instantiations of K4: coordinate width x seeding (-P) x slot recycling
+typedef void (*K4Fn)(const LaneArgs);
+K4Fn k4_fn(bool wide, bool pre, bool recycle) {
+    static const K4Fn tab[8] = {k_search_l<false, false, false>, k_search_l<false, false, true>, k_search_l<false, true, false>,
+                                k_search_l<false, true, true>,   k_search_l<true, false, false>, k_search_l<true, false, true>,
+                                k_search_l<true, true, false>,   k_search_l<true, true, true>};
+    return tab[(wide ? 4 : 0) | (pre ? 2 : 0) | (recycle ? 1 : 0)];
+}
+
 // size the persistent grid and the per-lane arena for the lane engine (K3 groups + K4 lanes)
 int prepare_search_lane(bwb_ctx *ctx, Device &d, int nb, bool wide) {
     if (nb > 128) return fail(ctx, BWB_ERR_UNSUPPORTED, "%d score buckets: the lane engine keeps the occupancy of at most 128 in registers", nb);
@@ -294,20 +305,15 @@ int prepare_search_lane(bwb_ctx *ctx, Device &d, int nb, bool wide) {
     const int tpb = 128;
     const size_t smem = (size_t)nb * tpb * 4;                 // bucket heads [nb][128]
     // the -P instantiations differ only in how a read is seeded: same launch shape as the plain ones
-    CU(cudaFuncSetAttribute(k_search_l<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CU(cudaFuncSetAttribute(k_search_l<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CU(cudaFuncSetAttribute(k_search_l<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CU(cudaFuncSetAttribute(k_search_l<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    for (int v = 0; v < 8; v++) CU(cudaFuncSetAttribute(k4_fn(v & 4, v & 2, v & 1), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int bps = ctx->blocks_per_sm;
     if (bps <= 0) {
-        int b0 = 0, b1 = 0;
-        if (wide) {
-            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b0, k_search_l<true, false>, tpb, smem));
-            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b1, k_search_l<true, true>, tpb, smem));
-        } else {
-            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b0, k_search_l<false, false>, tpb, smem));
-            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b1, k_search_l<false, true>, tpb, smem));
+        int b0 = 1 << 30, b1 = 0;
+        for (int v = 0; v < 4; v++) {          // the -P and recycling instantiations share the launch shape of the plain one
+            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b1, k4_fn(wide, v & 2, v & 1), tpb, smem));
+            if (b1 < b0) b0 = b1;
         }
+        b1 = b0;
         bps = b0 < b1 ? b0 : b1;
         if (bps <= 0) return fail(ctx, BWB_ERR_CUDA, "k_search_l does not fit on an SM");
     }
@@ -344,7 +350,7 @@ int prepare_search_lane(bwb_ctx *ctx, Device &d, int nb, bool wide) {
             else {
                 size_t fr = 0, tot = 0;
                 CU(cudaMemGetInfo(&fr, &tot));
-                pool_bytes = (uint64_t)fr / 5 * 3;
+                pool_bytes = (uint64_t)fr / 10 * 7;
                 if (pool_bytes > (128ull << 30)) pool_bytes = 128ull << 30;
                 d.auto_pool_bytes = pool_bytes;
             }
@@ -353,7 +359,13 @@ int prepare_search_lane(bwb_ctx *ctx, Device &d, int nb, bool wide) {
         if (total < (uint64_t)n_lanes * 512) total = (uint64_t)n_lanes * 512;
         if (total > 0xfffff000ull) total = 0xfffff000ull;
         total &= ~(uint64_t)(LBLK - 1);
-        uint32_t spl = (uint32_t)((total - total / 4) / n_lanes);
+        // private : shared.  A quarter of the arena as private per-lane ranges is plenty for the common read now that
+        // popped slots are recycled (chr21: < 100 KB live per read); the rest is the shared pool the few heavy reads
+        // draw 8 KB blocks from -- at genome scale their heaps reach 2x10^5 live entries (6.6 MB), and with 3/4 of the
+        // arena locked into private ranges 8 % of the reads ran out and waited for the 1/8-occupancy retry pass.
+        const uint64_t priv_pct = ctx->arena_private_pct > 0 && ctx->arena_private_pct < 100 ? (uint64_t)ctx->arena_private_pct : 25;
+        uint32_t spl = (uint32_t)(total * priv_pct / 100 / n_lanes);
+        if (spl < 256) spl = 256;
         uint64_t priv = ((uint64_t)spl * n_lanes + LBLK - 1) & ~(uint64_t)(LBLK - 1);
         d.slots_per_lane = spl; d.total_slots = (uint32_t)total; d.priv_total = (uint32_t)priv;
         if ((rc = ensure(ctx, d.chunks, total * 32, false))) return rc;
@@ -627,7 +639,7 @@ int bwb_device_count(const bwb_ctx *ctx) { return ctx ? (int)ctx->dev.size() : 0
 int bwb_set_option(bwb_ctx *ctx, const char *key, long long value) {
     if (!ctx || !key) return BWB_ERR_ARG;
     std::string k(key);
-    if (value <= 0 && k != "blocks_per_sm" && k != "force_wide" && k != "engine" && k != "heap_pool_mb" && k != "kmer_table" && k != "heavy_first" && k != "hit_cap0" && k != "index_wide" && k != "index_chunk") return fail(ctx, BWB_ERR_ARG, "option %s needs a positive value", key);
+    if (value <= 0 && k != "blocks_per_sm" && k != "force_wide" && k != "engine" && k != "heap_pool_mb" && k != "kmer_table" && k != "heavy_first" && k != "hit_cap0" && k != "index_wide" && k != "index_chunk" && k != "arena_private_pct" && k != "recycle") return fail(ctx, BWB_ERR_ARG, "option %s needs a positive value", key);
     if (k == "heap_pool_mb") ctx->heap_pool_mb = value;
     else if (k == "list_cap") ctx->list_cap = (int)(value < SL + 4 ? SL + 4 : value);
     else if (k == "hits_per_read") ctx->hits_per_read = (int)value;
@@ -644,6 +656,8 @@ int bwb_set_option(bwb_ctx *ctx, const char *key, long long value) {
     else if (k == "kmer_table") ctx->use_ktab = value > 1 ? 0 : 1;
     else if (k == "heavy_first") ctx->heavy_first = value > 1 ? 0 : 1;
     else if (k == "hit_cap0") ctx->hit_cap0 = value;
+    else if (k == "arena_private_pct") ctx->arena_private_pct = (int)value;
+    else if (k == "recycle") { ctx->recycle = (value == 1 || value == 2) ? (int)value : 0; return BWB_OK; }
     else if (k == "index_wide") { ctx->index_wide = value == 1 ? 1 : 0; return BWB_OK; }
     else if (k == "index_chunk") { ctx->index_chunk = value > 0 ? value : 0; return BWB_OK; }
     else if (k == "engine") {
@@ -1227,6 +1241,8 @@ static int launch_shard(bwb_ctx *ctx, Device &d, const bwb_params *p, int nb, co
         g.out_hits = a.out_hits; g.out_cap = a.out_cap; g.out_cursor = a.out_cursor;
         g.read_off = a.read_off; g.read_cnt = a.read_cnt; g.status = a.status; g.counters = a.counters;
         g.pre_off = d.pre_off; g.pre_cnt = d.pre_cnt; g.pre_iv = d.pre_iv;
+        // popped slots are recycled where heaps get large (see k_search_l): big indexes, long reads, the wide entry format
+        const bool recycle = ctx->recycle == 1 || (ctx->recycle != 2 && (wide || ctx->length > (1ull << 28) || max_len > 128));
         // three passes: all reads; the reads pass 0 deferred for lack of arena; what pass 1 deferred (an
         // overflow there is reported).  Passes 1 and 2 read their queue length on the device: no host sync,
         // and an empty pass costs a few microseconds.
@@ -1242,13 +1258,7 @@ static int launch_shard(bwb_ctx *ctx, Device &d, const bwb_params *p, int nb, co
                 g.order = rl1; g.n_queue_ptr = (const uint32_t *)(sm + 124); g.queue = (uint32_t *)(sm + 116);
                 g.retry_list = nullptr; g.retry_count = nullptr;
             }
-            if (p->use_precalc) {
-                if (wide) k_search_l<true, true><<<d.grid, 128, d.smem_bytes, d.stream>>>(g);
-                else k_search_l<false, true><<<d.grid, 128, d.smem_bytes, d.stream>>>(g);
-            } else {
-                if (wide) k_search_l<true, false><<<d.grid, 128, d.smem_bytes, d.stream>>>(g);
-                else k_search_l<false, false><<<d.grid, 128, d.smem_bytes, d.stream>>>(g);
-            }
+            k4_fn(wide, p->use_precalc != 0, recycle)<<<d.grid, 128, d.smem_bytes, d.stream>>>(g);
             CU(cudaGetLastError());
         }
         CU(cudaGetLastError());
@@ -1384,6 +1394,12 @@ static int align_impl(bwb_ctx *ctx, const bwb_params *p, const bwb_reads *R, bwb
             for (int k = 0; k < 4; k++) res->counters[k] += ctr[k];
 
             for (int k = 4; k < 6; k++) if (ctr[k] > res->counters[k]) res->counters[k] = ctr[k];
+            {   // reads K4 deferred for lack of arena: queue lengths of its retry passes (8x / 64x the arena per read)
+                uint32_t dq[2];
+                memcpy(dq, hs + 120, 8);
+                res->counters[6] += dq[0];
+                res->counters[7] += dq[1];
+            }
         }
         if (!again) break;
     }

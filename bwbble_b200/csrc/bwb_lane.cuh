@@ -229,9 +229,9 @@ struct LaneHeap {
     }
     __device__ __forceinline__ void mark(int b) { set_bit(b); }
     // heap_pop (inexact_match.c:594-610); returns the bucket
-    __device__ __forceinline__ int pop(const LaneArgs &a, PE<T> &e) {
+    __device__ __forceinline__ int pop(const LaneArgs &a, PE<T> &e, uint32_t &s) {
         const int b = best();
-        const uint32_t s = heads[b * 128];
+        s = heads[b * 128];
         const uint32_t rest = slot_read<T>(a.slots, s, e);
         heads[b * 128] = rest;
         if (rest == NIL) clear_bit(b);
@@ -335,6 +335,9 @@ __device__ __forceinline__ void rank_general(const IndexView &ix, const T *sC, T
     // ends side by side, which is what lets 4 blocks of 128 lanes share an SM.
     uint32_t vU[16];
     uint32_t firstU = 0;                          // bit j: row 0 of the upper block holds code j (Q1)
+    // (A/B, round 2: prefetch.global.L1 of the lower end's four sectors here, and of the next pop's blocks when the
+    // keeper child is chosen, made K4 17-22 % SLOWER on the 600 M-row index and 3-6 % slower on chr21 -- CCTL.PF1 is
+    // not free and the L1 left beside 54 KB of shared memory per block is small; profiles/r02_ab_log.md)
     {
         const Planes pu = load_planes(blkU);
         const uint4 q0 = __ldg(blkU), q1 = __ldg(blkU + 1), q2 = __ldg(blkU + 2), q3 = __ldg(blkU + 3);
@@ -394,19 +397,31 @@ __device__ __forceinline__ void rank_general(const IndexView &ix, const T *sC, T
 //   C  the result is consumed: next level of the exact tail (align.c:93-110), or the children of the
 //      expansion (inexact_match.c:433-504) -- described per lane, then written by the whole warp, one
 //      child per lane and pass; then [flush] of finished reads.
-// Narrow coordinates: 4 blocks of 128 lanes per SM (128 registers, 55 KB shared memory per block at -n 5);
-// wide (64-bit) coordinates: 3 blocks (the shared-memory child arrays are twice the size).
+// 3 blocks of 128 lanes per SM.  (A/B on B200, chr21, 2 M reads: 4 blocks at 128 registers -- 12 bytes of spills --
+// run 5 % slower, 0.94 against 0.99 M reads/s: 4 x 54 KB of shared memory leave the SM almost no L1.)
+#ifndef BWB_FREE_RING
+#define BWB_FREE_RING 8
+#endif
+constexpr int FREE_RING = BWB_FREE_RING;   // free slot ids kept per lane
+static_assert(FREE_RING > 0 && FREE_RING < 256 && (FREE_RING & (FREE_RING - 1)) == 0, "FREE_RING: a power of two below 256");
 #ifndef BWB_LANE_BLOCKS_NARROW
-#define BWB_LANE_BLOCKS_NARROW 4
+#define BWB_LANE_BLOCKS_NARROW 3
 #endif
 #define BWB_LANE_MIN_BLOCKS(WIDE) ((WIDE) ? 3 : BWB_LANE_BLOCKS_NARROW)
-template <bool WIDE, bool PRE>
+template <bool WIDE, bool PRE, bool RECYCLE>
 __global__ void __launch_bounds__(128, BWB_LANE_MIN_BLOCKS(WIDE)) k_search_l(const __grid_constant__ LaneArgs a) {
     typedef typename Coord<WIDE>::type T;
     __shared__ T sC[17];
     __shared__ T sLj[16][128], sUj[16][128];      // row 0: the lane's interval; rows 1..15: child intervals by code
     __shared__ uint32_t sOk[128];                 // valid-child mask per lane
     __shared__ uint8_t sFlag[128];                // quirk mode of the lane's task
+    // Slots of popped entries are handed straight to the next children (a small per-lane stack of free slot ids):
+    // the arena a read needs is its LIVE heap, not every push it ever made -- 3-4x less at genome scale, where
+    // bump-only allocation (round 1) overflowed the private ranges of most lanes and sent the reads to the
+    // retry passes; recently freed lines are also still in L2 when they are written again.
+    // RECYCLE is chosen by the host: on for indexes beyond 2^28 rows, reads longer than 128 bases and the wide entry
+    // format (there it is worth 1.8-2.4x); off at chr21 scale, where nothing overflows and the bookkeeping costs 4 %.
+    __shared__ uint32_t sFree[RECYCLE ? FREE_RING : 1][128];
     __shared__ uint32_t sTe[5][128];              // z, w, r1, r2, r3 of the entry whose exact tail is in progress
                                                   // (touched when a tail starts / ends: kept out of the register file)
     extern __shared__ uint32_t sm_heads[];        // [nb][128] bucket heads
@@ -467,6 +482,7 @@ __global__ void __launch_bounds__(128, BWB_LANE_MIN_BLOCKS(WIDE)) k_search_l(con
     // as one is popped (inexact_match.c:309) and best_score never grows.  They are only COUNTED (num_entries
     // feeds the max_entries check, :301), not written to the arena.
     int ghost = 0;
+    uint32_t nfree = 0;                       // entries of this lane's free-slot stack
     uint32_t c_pops = 0, c_push = 0, c_tails = 0, c_rank = 0;         // per read, added to the launch counters at its flush
     uint32_t c_maxheap = 0, c_maxlist = 0;
     __syncthreads();
@@ -490,6 +506,7 @@ __global__ void __launch_bounds__(128, BWB_LANE_MIN_BLOCKS(WIDE)) k_search_l(con
             const int nN = (int)a.n_count[r];                           // counted by K3
             h.clear();
             ghost = 0;
+            nfree = 0;
             n_hits = 0; hit_head = hit_tail = NIL; err = 0;
             best_score = a.nb; max_diff = a.max_diff; num_best = 0;
             for (int b = 0; b < a.nb; b++) h.heads[b * 128] = NIL;
@@ -620,7 +637,11 @@ __global__ void __launch_bounds__(128, BWB_LANE_MIN_BLOCKS(WIDE)) k_search_l(con
                 mode = FLUSH;
             } else {
                 if (have_next) { e = nx; eb = nx_bucket; have_next = false; }
-                else eb = h.pop(a, e);
+                else {
+                    uint32_t freed;
+                    eb = h.pop(a, e, freed);
+                    if (RECYCLE && nfree < (uint32_t)FREE_RING) sFree[nfree++][tid] = freed;   // nothing reads a slot after it is unlinked
+                }
                 c_pops++;
                 const uint32_t z = e.z;
                 const int ei = (int)(z & 0xffu);
@@ -724,7 +745,7 @@ __global__ void __launch_bounds__(128, BWB_LANE_MIN_BLOCKS(WIDE)) k_search_l(con
         // ================= C: consume the result =================
         // children of this warp's expansions are described here (owner registers) and written below, one child
         // per lane and pass, whichever lane owns them
-        uint32_t ch_n = 0, ch_base = NIL, ch_masks = 0, ch_compat = 0, ch_bk = 0;
+        uint32_t ch_n = 0, ch_base = NIL, ch_masks = 0, ch_compat = 0, ch_bk = 0, ch_free = 0;
         if (have_task) {
             have_task = false;
             c_rank += 2u;
@@ -792,9 +813,13 @@ __global__ void __launch_bounds__(128, BWB_LANE_MIN_BLOCKS(WIDE)) k_search_l(con
 #endif
                 const uint32_t n = (ins_live ? 1u : 0u) + (uint32_t)__popc(md) + (uint32_t)__popc(mmk);
                 if (n) {
-                    ch_base = lane_alloc_n(al, a, lane_slot, n);
+                    // recycled slots first (top of the free stack), the rest contiguous from the bump allocator
+                    const uint32_t f = RECYCLE ? (n < nfree ? n : nfree) : 0u;
+                    ch_base = (n > f) ? lane_alloc_n(al, a, lane_slot, n - f) : 0u;
                     if (ch_base == NIL) { err = BWB_ERR_CAPACITY; mode = FLUSH; }
                     else {
+                        ch_free = f | (nfree << 8);
+                        nfree -= f;
                         // occupancy bits once per score class (of what is really pushed)
                         if (ins_live || md) h.mark(b2);
                         if (mmk & ~compat_set) h.mark(b1);
@@ -836,11 +861,15 @@ __global__ void __launch_bounds__(128, BWB_LANE_MIN_BLOCKS(WIDE)) k_search_l(con
                 const uint32_t masks = __shfl_sync(FULL, ch_masks, o);
                 const uint32_t cmp = __shfl_sync(FULL, ch_compat, o);
                 const uint32_t bk = __shfl_sync(FULL, ch_bk, o);
+                const uint32_t fr = RECYCLE ? __shfl_sync(FULL, ch_free, o) : 0u;
                 const uint32_t pz = __shfl_sync(FULL, e.z, o), pw = __shfl_sync(FULL, e.w, o);
                 const T pL = shfl(e.L, o), pU = shfl(e.U, o);
                 uint32_t pr1 = 0, pr2 = 0, pr3 = 0;
                 if (WIDE) { pr1 = __shfl_sync(FULL, e.r1, o); pr2 = __shfl_sync(FULL, e.r2, o); pr3 = __shfl_sync(FULL, e.r3, o); }
                 const uint32_t otid = (warp << 5) + (uint32_t)o;
+                const uint32_t fcnt = fr & 0xffu, ftop = fr >> 8;
+                // slot of the child at position `pos` of the owner's push order
+#define BWB_SLOT_OF(pos) ((RECYCLE && (pos) < fcnt) ? sFree[(ftop - 1u - (pos)) & (uint32_t)(FREE_RING - 1)][otid] : base + ((pos) - fcnt))
                 const uint32_t md = masks & 0xffffu, mmk = masks >> 16, compat = cmp & 0xffffu;
                 const uint32_t n_ins = (cmp >> 16) & 1u, n_gap = n_ins + (uint32_t)__popc(md);
                 const int b0 = (int)(bk & 0xffu), b1 = (int)((bk >> 8) & 0xffu), b2 = (int)((bk >> 16) & 0xffu);
@@ -872,7 +901,7 @@ __global__ void __launch_bounds__(128, BWB_LANE_MIN_BLOCKS(WIDE)) k_search_l(con
                     }
                     X = b2;
                     need_old = (q == 0u);
-                    if (!need_old) nxt_slot = base + q - 1u;
+                    if (!need_old) nxt_slot = BWB_SLOT_OF(q - 1u);
                     last = (q + 1u == n_gap) && (mm_in_b2 == 0u);
                     if (is_ins) {
                         cL = pL; cU = pU;
@@ -891,9 +920,10 @@ __global__ void __launch_bounds__(128, BWB_LANE_MIN_BLOCKS(WIDE)) k_search_l(con
                     need_old = false;
                     if (below) {
                         const int pc = 31 - __clz(below);
-                        nxt_slot = base + n_gap + (uint32_t)__popc(mmk & ((1u << pc) - 1u));
+                        const uint32_t pp = n_gap + (uint32_t)__popc(mmk & ((1u << pc) - 1u));
+                        nxt_slot = BWB_SLOT_OF(pp);
                     } else if (b2 == X && n_gap > 0u) {
-                        nxt_slot = base + n_gap - 1u;
+                        nxt_slot = BWB_SLOT_OF(n_gap - 1u);
                     } else {
                         need_old = true;
                     }
@@ -906,9 +936,11 @@ __global__ void __launch_bounds__(128, BWB_LANE_MIN_BLOCKS(WIDE)) k_search_l(con
                 if (on && need_old) nxt_slot = *hd;
                 __syncwarp();                                            // old heads are read before new ones are written
                 if (on) {
-                    slot_write<T>(a.slots, base + q, cL, cU, cz, cw, nxt_slot, cr1, cr2, cr3);
-                    if (last) *hd = base + q;
+                    const uint32_t mine = BWB_SLOT_OF(q);
+                    slot_write<T>(a.slots, mine, cL, cU, cz, cw, nxt_slot, cr1, cr2, cr3);
+                    if (last) *hd = mine;
                 }
+#undef BWB_SLOT_OF
             }
         }
 #undef BWB_CODE_OF

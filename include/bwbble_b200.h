@@ -193,7 +193,9 @@ uint64_t bwb_results_num_hits(const bwb_results *r);
 const uint32_t *bwb_results_counts(const bwb_results *r);   /* hits per read, input order */
 const bwb_hit *bwb_results_hits(const bwb_results *r);      /* flat, grouped by read, input order */
 /* kernel-side counters of the last call: [0] pops [1] pushes [2] exact-tail calls [3] block loads
- * (physical 128-B rank gathers) [4] max heap entries of any read [5] max interval-list length */
+ * (physical 128-B rank gathers) [4] max heap entries of any read [5] max interval-list length
+ * [6], [7] reads deferred to K4's 2nd / 3rd pass (their heap outgrew the arena share of a lane; those passes run
+ * with 8x / 64x the arena per read) */
 int bwb_results_counters(const bwb_results *r, uint64_t out[8]);
 /* Duration of the search kernel (K4) of the call that produced r, in ms: CUDA events on the launch
  * stream, max over the context's devices. */

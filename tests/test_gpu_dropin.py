@@ -63,3 +63,20 @@ def test_dropin_precalc_P(tmp_path, tag):
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "Pre-calculating" not in r.stdout          # the table came from the file
     assert open(aln, "rb").read() == G.golden_bytes("aln_%s.aln" % tag)
+
+
+def _ngpu():
+    import torch
+    return torch.cuda.device_count() if torch.cuda.is_available() else 0
+
+
+@pytest.mark.skipif(_ngpu() < 2, reason="needs 2 GPUs")
+def test_dropin_cli_on_two_gpus(tmp_path):
+    """BWBBLE_GPUS=2: the shim shards every batch over two devices inside the one process; same .aln bytes"""
+    fa = G.materialise_index(tmp_path)
+    fq = os.path.join(G.GOLDEN, "r.fq")
+    aln = str(tmp_path / "out.aln")
+    env = dict(os.environ, BWBBLE_GPUS="2")
+    r = subprocess.run([GPU_BIN, "align", *G.grid()["n3"], fa, fq, aln], capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert open(aln, "rb").read() == G.golden_bytes("aln_n3.aln")

@@ -14,7 +14,7 @@ pytestmark = pytest.mark.gpu
 import os
 
 # the two A/B engines of round 1 (warp per read, 8 lanes per read) are only built with -DBWB_AB_ENGINES
-_ENGINES = ["lane-idx32", "lane-idx64"] + (["group-idx32", "group-idx64", "warp-idx32", "warp-idx64"]
+_ENGINES = ["lane-idx32", "lane-idx64", "lane-idx32-recycle"] + (["group-idx32", "group-idx64", "warp-idx32", "warp-idx64"]
                                            if os.environ.get("BWBBLE_TEST_AB_ENGINES") else [])
 
 
@@ -23,11 +23,15 @@ def gpu_case(small_case, request):
     """lane = production engine (one read per lane: k_calc_d_g + k_search_l); group (8 lanes per read)
     and warp (k_align) are the A/B baselines the round-1 profiles compare against;
     idx32 = 32-bit SA coordinates + 16-byte heap entries (indexes < 2^32 rows, max_gapo <= 1);
-    idx64 = the wide kernels (genome-scale format) forced onto the same small index."""
+    idx64 = the wide kernels (genome-scale format) forced onto the same small index;
+    recycle = K4's slot recycling (the genome-scale / long-read configuration) forced on with 32-bit coordinates."""
     al = Aligner(heap_pool_mb=512, hits_per_read=256, list_cap=1024)
     if request.param.endswith("idx64"):
-        al.set_option("force_wide", 1)
-    al.set_option("engine", {"lane": 0, "warp": 1, "group": 2}[request.param.split("-")[0]])
+        al.set_option("force_wide", 1)           # (the wide format also recycles popped heap slots)
+    if request.param.endswith("recycle"):
+        al.set_option("recycle", 1)              # auto: only beyond 2^28 rows / 128-base reads / wide entries
+    if not request.param.startswith("lane"):
+        al.set_option("engine", {"warp": 1, "group": 2}[request.param.split("-")[0]])
     al.load_index(small_case["bwt"])
     orc = oracle.Oracle(small_case["bwt"])
     yield {"al": al, "orc": orc, **small_case}
