@@ -84,6 +84,8 @@ struct bwb_ctx {
                               // 2 = 8-lane groups (k_calc_d_g + k_search_g); 1 and 2 are A/B baselines
     int use_ktab = 1;         // k-mer table for calculate_d's top of tree (0 = off, for A/B and tests)
     int force_wide = 0;       // tests: run the 64-bit / 32-byte-entry kernels on a small index
+    int throttle_forced = 0;         // set by bwb_set_option("throttle_pct"): apply it whatever the workload
+    int throttle_pct = 60;           // K4 admission control: lanes wait while more than this share of the pool is lent out (0/100 = off)
     int recycle = 0;                 // K4 slot recycling: 0 = auto (index > 2^28 rows, reads > 128 bases, wide entries), 1 = on, 2 = off
     int arena_private_pct = 25;      // share of the K4 arena split into private per-lane ranges (rest: shared block pool)
     long long index_chunk = 0;       // K7w: suffixes per sort chunk (0 = 2^29)
@@ -639,7 +641,7 @@ int bwb_device_count(const bwb_ctx *ctx) { return ctx ? (int)ctx->dev.size() : 0
 int bwb_set_option(bwb_ctx *ctx, const char *key, long long value) {
     if (!ctx || !key) return BWB_ERR_ARG;
     std::string k(key);
-    if (value <= 0 && k != "blocks_per_sm" && k != "force_wide" && k != "engine" && k != "heap_pool_mb" && k != "kmer_table" && k != "heavy_first" && k != "hit_cap0" && k != "index_wide" && k != "index_chunk" && k != "arena_private_pct" && k != "recycle") return fail(ctx, BWB_ERR_ARG, "option %s needs a positive value", key);
+    if (value <= 0 && k != "blocks_per_sm" && k != "force_wide" && k != "engine" && k != "heap_pool_mb" && k != "kmer_table" && k != "heavy_first" && k != "hit_cap0" && k != "index_wide" && k != "index_chunk" && k != "arena_private_pct" && k != "recycle" && k != "throttle_pct") return fail(ctx, BWB_ERR_ARG, "option %s needs a positive value", key);
     if (k == "heap_pool_mb") ctx->heap_pool_mb = value;
     else if (k == "list_cap") ctx->list_cap = (int)(value < SL + 4 ? SL + 4 : value);
     else if (k == "hits_per_read") ctx->hits_per_read = (int)value;
@@ -657,6 +659,7 @@ int bwb_set_option(bwb_ctx *ctx, const char *key, long long value) {
     else if (k == "heavy_first") ctx->heavy_first = value > 1 ? 0 : 1;
     else if (k == "hit_cap0") ctx->hit_cap0 = value;
     else if (k == "arena_private_pct") ctx->arena_private_pct = (int)value;
+    else if (k == "throttle_pct") { ctx->throttle_pct = (int)value; ctx->throttle_forced = 1; return BWB_OK; }
     else if (k == "recycle") { ctx->recycle = (value == 1 || value == 2) ? (int)value : 0; return BWB_OK; }
     else if (k == "index_wide") { ctx->index_wide = value == 1 ? 1 : 0; return BWB_OK; }
     else if (k == "index_chunk") { ctx->index_chunk = value > 0 ? value : 0; return BWB_OK; }
@@ -1238,11 +1241,17 @@ static int launch_shard(bwb_ctx *ctx, Device &d, const bwb_params *p, int nb, co
         g.slots = (uint4 *)d.chunks.p;
         g.slots_per_lane = d.slots_per_lane; g.priv_total = d.priv_total;
         g.pool = (PoolState *)d.pool.p; g.blk_link = (uint32_t *)d.blk_link.p;
+        // popped slots are recycled where heaps get large (see k_search_l): big indexes, long reads, the wide entry format
+        const bool recycle = ctx->recycle == 1 || (ctx->recycle != 2 && (wide || ctx->length > (1ull << 28) || max_len > 128));
+        {   // admission control: no new reads while more than throttle_pct % of the shared blocks are lent out
+            const uint64_t shared_blocks = d.total_slots / LBLK > d.priv_total / LBLK ? d.total_slots / LBLK - d.priv_total / LBLK : 0;
+            // (with the heavy-heap configurations only, i.e. together with slot recycling, unless the option forces it)
+            const bool on = ctx->throttle_pct > 0 && ctx->throttle_pct < 100 && (recycle || ctx->throttle_forced);
+            g.throttle_blocks = on ? shared_blocks * (uint64_t)ctx->throttle_pct / 100 : 0;
+        }
         g.out_hits = a.out_hits; g.out_cap = a.out_cap; g.out_cursor = a.out_cursor;
         g.read_off = a.read_off; g.read_cnt = a.read_cnt; g.status = a.status; g.counters = a.counters;
         g.pre_off = d.pre_off; g.pre_cnt = d.pre_cnt; g.pre_iv = d.pre_iv;
-        // popped slots are recycled where heaps get large (see k_search_l): big indexes, long reads, the wide entry format
-        const bool recycle = ctx->recycle == 1 || (ctx->recycle != 2 && (wide || ctx->length > (1ull << 28) || max_len > 128));
         // three passes: all reads; the reads pass 0 deferred for lack of arena; what pass 1 deferred (an
         // overflow there is reported).  Passes 1 and 2 read their queue length on the device: no host sync,
         // and an empty pass costs a few microseconds.

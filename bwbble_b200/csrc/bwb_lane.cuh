@@ -54,6 +54,7 @@ struct LaneArgs {
     uint32_t slots_per_lane;                 // private range of lane-slot s: [s*spl, (s+1)*spl)
     uint32_t priv_total;                     // first slot of the shared region (multiple of LBLK)
     PoolState *pool;                         // shared region, in blocks of LBLK slots
+    unsigned long long throttle_blocks;      // lanes do not start a new read while more shared blocks than this are lent out (0 = off)
     uint32_t *blk_link;                      // link word per block (pool free lists, borrowed lists)
     bwb_hit *out_hits;
     unsigned long long out_cap;
@@ -70,6 +71,7 @@ struct LaneAlloc {
     uint32_t ov_cur, ov_end;                 // current borrowed block
     uint32_t borrowed;                       // list of borrowed blocks (through blk_link)
     uint32_t borrowed_last;
+    uint32_t n_borrowed;                     // blocks on the borrowed list
 };
 
 // slow path: take a block of LBLK slots from the shared pool (own shard first); NIL if exhausted.
@@ -84,12 +86,12 @@ __device__ __noinline__ uint32_t pool_take_block(PoolState *pool, uint32_t *blk_
             if (id == NIL) break;
             const uint32_t nx = *reinterpret_cast<volatile uint32_t *>(blk_link + id);
             const unsigned long long prev = atomicCAS(head, old, (((old >> 32) + 1ull) << 32) | nx);
-            if (prev == old) return id;
+            if (prev == old) { atomicAdd(&pool->n_borrowed, 1ull); return id; }
             old = prev;
         }
         if (*reinterpret_cast<volatile uint32_t *>(&pool->bump[sh]) < pool->limit[sh]) {
             const uint32_t o = atomicAdd(&pool->bump[sh], 1u);
-            if (o < pool->limit[sh]) return o;
+            if (o < pool->limit[sh]) { atomicAdd(&pool->n_borrowed, 1ull); return o; }
         }
     }
     return NIL;
@@ -103,6 +105,7 @@ __device__ __forceinline__ uint32_t lane_alloc(LaneAlloc &al, const LaneArgs &a,
     a.blk_link[blk] = al.borrowed;
     if (al.borrowed == NIL) al.borrowed_last = blk;
     al.borrowed = blk;
+    al.n_borrowed++;
     al.ov_cur = blk * LBLK;
     al.ov_end = al.ov_cur + LBLK;
     return al.ov_cur++;
@@ -117,6 +120,7 @@ __device__ __forceinline__ uint32_t lane_alloc_n(LaneAlloc &al, const LaneArgs &
     a.blk_link[blk] = al.borrowed;
     if (al.borrowed == NIL) al.borrowed_last = blk;
     al.borrowed = blk;
+    al.n_borrowed++;
     al.ov_cur = blk * LBLK + n;
     al.ov_end = blk * LBLK + LBLK;
     return blk * LBLK;
@@ -146,7 +150,9 @@ __device__ __forceinline__ void lane_alloc_reset(LaneAlloc &al, const LaneArgs &
             if (prev == old) break;
             old = prev;
         }
+        atomicAdd(&a.pool->n_borrowed, 0ull - (unsigned long long)al.n_borrowed);
     }
+    al.n_borrowed = 0;
     al.bump = al.priv_lo;
     al.ov_cur = al.ov_end = 0;
     al.borrowed = NIL;
@@ -442,6 +448,7 @@ __global__ void __launch_bounds__(128, BWB_LANE_MIN_BLOCKS(WIDE)) k_search_l(con
     al.ov_cur = al.ov_end = 0;
     al.borrowed = NIL;
     al.borrowed_last = NIL;
+    al.n_borrowed = 0;
     LaneHeap<WIDE> h;
     h.heads = sm_heads + tid;
     h.clear();
@@ -483,6 +490,10 @@ __global__ void __launch_bounds__(128, BWB_LANE_MIN_BLOCKS(WIDE)) k_search_l(con
     // feeds the max_entries check, :301), not written to the arena.
     int ghost = 0;
     uint32_t nfree = 0;                       // entries of this lane's free-slot stack
+#ifdef BWB_PF_D
+    uint32_t pf_d = 0, pf_s = 0, pf_b = 0;
+    bool pf_ok = false;
+#endif
     uint32_t c_pops = 0, c_push = 0, c_tails = 0, c_rank = 0;         // per read, added to the launch counters at its flush
     uint32_t c_maxheap = 0, c_maxlist = 0;
     __syncthreads();
@@ -490,13 +501,21 @@ __global__ void __launch_bounds__(128, BWB_LANE_MIN_BLOCKS(WIDE)) k_search_l(con
 #define BWB_CODE_OF(t) (multiref ? (int)(t) : (int)((0x173Fu >> (4 * (t))) & 15u))
     for (;;) {
         if (__all_sync(FULL, mode == DONE)) break;
-        if (!have_task) {
         // ================= A: take the next read =================
-        if (mode == NEED) {
-            r = atomicAdd(a.queue, 1u);
-            if (r >= n_queue) mode = DONE;
+        // Admission control: while most of the shared arena blocks are lent out, finished lanes wait instead of
+        // starting another read -- the reads in flight then find room for their heaps and end normally, instead of
+        // running out, being thrown away and searched again in the 1/8-occupancy retry pass (genome-scale 150 bp
+        // reads with gaps: 27 % of the reads went that way).
+        bool take = mode == NEED;
+        if (a.throttle_blocks && __any_sync(FULL, take)) {            // (uniform; a lane needs a read once in ~10^4 iterations)
+            if (take && *reinterpret_cast<volatile unsigned long long *>(&a.pool->n_borrowed) > a.throttle_blocks) take = false;
+            if (__all_sync(FULL, mode == DONE || (mode == NEED && !take))) __nanosleep(2000);      // a whole warp waiting
         }
-        if (mode == NEED) {
+        if (take) {
+            r = atomicAdd(a.queue, 1u);
+            if (r >= n_queue) { mode = DONE; take = false; }
+        }
+        if (take) {
             if (a.order) r = a.order[r];
             const uint64_t off64 = a.offsets[r];
             off = (uint32_t)off64;
@@ -636,6 +655,9 @@ __global__ void __launch_bounds__(128, BWB_LANE_MIN_BLOCKS(WIDE)) k_search_l(con
                 c_pops++;
                 mode = FLUSH;
             } else {
+#ifdef BWB_PF_D
+                const bool from_keeper = have_next && pf_ok;
+#endif
                 if (have_next) { e = nx; eb = nx_bucket; have_next = false; }
                 else {
                     uint32_t freed;
@@ -653,11 +675,31 @@ __global__ void __launch_bounds__(128, BWB_LANE_MIN_BLOCKS(WIDE)) k_search_l(con
                 const int si = ei - (len - a.seed_len);
                 // everything this entry may need from the read's arrays, fetched in one go (one latency)
                 const uint16_t *D = BWB_D, *Ds = BWB_DS;
+#ifdef BWB_PF_D
+                // the keeper child (i - 1) needs D[i-2], D[i-3], D_seed[si-2], D_seed[si-3], seq[len-i+1]: two of them are
+                // this entry's own, the other three are fetched now, a whole iteration before they are looked at
+                uint32_t dA, dB, sA, sB, base_i1;
+                if (from_keeper) {
+                    dA = pf_d & 0xffffu; dB = pf_d >> 16; sA = pf_s & 0xffffu; sB = pf_s >> 16; base_i1 = pf_b;
+                } else {
+                    dA = D[ei > 0 ? ei - 1 : 0]; dB = D[ei > 1 ? ei - 2 : 0];
+                    sA = Ds[si > 0 ? si - 1 : 0]; sB = Ds[si > 1 ? si - 2 : 0];
+                    base_i1 = BWB_RSEQ[ei > 0 ? len - ei : 0];
+                }
+                {
+                    const uint32_t dC = D[ei > 2 ? ei - 3 : 0], sCn = Ds[si > 2 ? si - 3 : 0];
+                    pf_b = BWB_RSEQ[ei > 1 ? len - ei + 1 : 0];
+                    pf_d = dB | (dC << 16);
+                    pf_s = sB | (sCn << 16);
+                    pf_ok = false;                                      // set when a keeper is chosen below
+                }
+#else
                 const uint32_t dA = D[ei > 0 ? ei - 1 : 0];                 // D[i-1]
                 const uint32_t dB = D[ei > 1 ? ei - 2 : 0];                 // D[i-2]
                 const uint32_t sA = Ds[si > 0 ? si - 1 : 0];                // D_seed[si-1]
                 const uint32_t sB = Ds[si > 1 ? si - 2 : 0];                // D_seed[si-2]
                 const uint32_t base_i1 = BWB_RSEQ[ei > 0 ? len - ei : 0];   // seq[len-1-(i-1)]
+#endif
                 if ((eb & 0xff) > best_score + a.mm_score) {
                     mode = FLUSH;                                       // inexact_match.c:309
                 } else if (dl < 0 || (ei > 0 && dl < (int)(dA & 0x1ff)) || (si > 0 && dls < (int)(sA & 0x1ff))) {
@@ -731,7 +773,6 @@ __global__ void __launch_bounds__(128, BWB_LANE_MIN_BLOCKS(WIDE)) k_search_l(con
                 }
             }
         }
-        }   // !have_task
 
         // ================= B: rank stage =================
         __syncwarp();
@@ -802,6 +843,9 @@ __global__ void __launch_bounds__(128, BWB_LANE_MIN_BLOCKS(WIDE)) k_search_l(con
                     nx.z = zm + (((compat_set >> jk) & 1u) ? 0u : 0x100u);
                     nx.w = e.w; nx.r1 = e.r1; nx.r2 = e.r2; nx.r3 = e.r3;
                     nx_bucket = b0;
+#ifdef BWB_PF_D
+                    pf_ok = true;
+#endif
                 }
                 bool ins_live = ins_ok;
 #ifndef BWB_LANE_NO_GHOST

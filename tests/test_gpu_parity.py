@@ -600,13 +600,22 @@ def test_arena_overflow_defers_reads_to_retry_passes(small_case):
     orc = oracle.Oracle(small_case["bwt"])
     exp1, st = orc.align(reads.seq, reads.offsets, p)
     orc.close()
-    with Aligner(heap_pool_mb=1, hits_per_read=64) as al:      # clamps to the minimum: 512 slots per lane
-        al.load_index(small_case["bwt"])
+    with Aligner(heap_pool_mb=1, hits_per_read=64, throttle_pct=100) as al:      # clamps to the minimum: 512 slots per lane
+        al.load_index(small_case["bwt"])                                         # (admission control off: let it overflow)
         res = al.align(seq, offsets, p)
         got = res.aln_bytes()
         assert got == exp1 * rep, first_difference(got, exp1 * rep)
         # deferred reads are searched twice: the pop total exceeds the oracle's iff something was deferred
-        assert res.counters()["pops"] > st["pops"] * rep, "the arena never overflowed: the test does not bite"
+        ctr = res.counters()
+        assert ctr["pops"] > st["pops"] * rep and ctr["deferred_pass1"] > 0, "the arena never overflowed: the test does not bite"
+        deferred_without_throttle = ctr["deferred_pass1"]
+    # admission control (on by default together with slot recycling, i.e. for big indexes / long reads; forced here):
+    # lanes wait for arena instead of starting reads that would overflow
+    with Aligner(heap_pool_mb=1, hits_per_read=64, throttle_pct=60, recycle=1) as al:
+        al.load_index(small_case["bwt"])
+        res = al.align(seq, offsets, p)
+        assert res.aln_bytes() == exp1 * rep
+        assert res.counters()["deferred_pass1"] < deferred_without_throttle
 
 
 def test_150bp_gapped_reads_config5_shape(small_case):
