@@ -217,6 +217,7 @@ def main():
     ap.add_argument("--workload", default="chr21", choices=list(WORKLOADS))
     ap.add_argument("--index-chunk", type=int, default=0, help="K7w: suffixes per sort chunk (0 = default 2^29)")
     ap.add_argument("--opt", action="append", default=[], help="key=value for bwb_set_option (experiments)")
+    ap.add_argument("--cli-reads", type=int, default=-1, help="reads of the FASTQ-file-to-.aln-file leg (e2e_cli); 0 = skip, -1 = auto")
     ap.add_argument("--cpu-sample", type=int, default=0, help="reads in the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--quick", action="store_true", help="A/B experiments: resident timing only, short JSON")
@@ -395,6 +396,43 @@ def main():
                         "sharded_stream_equals_single_gpu": whole == alone, "check_reads": common.n,
                         "check_md5": hashlib.md5(whole).hexdigest()}
 
+    # ---- e2e_cli: the real entry points, FASTQ file in, .aln file out --------------------------
+    cli = None
+    if rank == 0 and world == 1 and args.cli_reads != 0:
+        try:
+            n_cli = args.cli_reads if args.cli_reads > 0 else min(w["batch"], 1 << 22)
+            sub = batches[0].slice(0, min(n_cli, batches[0].n))
+            d = os.path.join(CACHE, "cli")
+            os.makedirs(d, exist_ok=True)
+            fq, aln = os.path.join(d, "r.fq"), os.path.join(d, "out.aln")
+            sub.write_fastq(fq)
+            t = time.time()
+            n_done = al.align_fastq(fq, aln, p, batch=0)
+            dt = time.time() - t
+            cli = {"value": n_done / dt, "unit": "reads/s", "reads": n_done, "seconds": dt,
+                   "what": "bwb_align_fastq: FASTQ file -> parse -> H2D -> K3/K4/K5 -> D2H -> serialise -> .aln file (3 threads)",
+                   "fastq_bytes": os.path.getsize(fq), "aln_bytes": os.path.getsize(aln)}
+            import hashlib
+            cli["aln_md5_equals_bwb_align"] = (hashlib.md5(open(aln, "rb").read()).hexdigest()
+                                               == hashlib.md5(al.align(sub.seq, sub.offsets, p).aln_bytes()).hexdigest())
+            gpu_bin = os.path.join(ROOT, "oracle", "_ref", "bwbble_gpu")
+            if os.path.exists(gpu_bin):      # the reference's own main()/fastq2reads()/alns2alnf_bin around the shim
+                cmd = [gpu_bin, "align", "-n", str(PARAMS["n"])]
+                for k, flag in (("o", "-o"), ("e", "-e")):
+                    if k in PARAMS:
+                        cmd += [flag, str(PARAMS[k])]
+                out2 = os.path.join(d, "dropin.aln")
+                al_free = True
+                t = time.time()
+                r = subprocess.run(cmd + [fa, fq, out2], capture_output=True, text=True)
+                dt2 = time.time() - t
+                cli["dropin_binary"] = {"value": n_done / dt2, "unit": "reads/s", "seconds": dt2, "rc": r.returncode,
+                                        "what": "oracle/_ref/bwbble_gpu align (reference main.o/align.o/io.o + shim), wall clock incl. "
+                                                "index load, fastq2reads of all reads, context creation",
+                                        "aln_identical": r.returncode == 0 and open(out2, "rb").read() == open(aln, "rb").read()}
+        except Exception as ex:
+            cli = {"error": repr(ex)}
+
     if rank == 0:
         cpu, stats, n_s, n_q = None, None, 0, 0
         if not args.no_cpu and world == 1:
@@ -501,7 +539,7 @@ def main():
                 "roofline": roof, "cpu_baseline": None if cpu is None else
                 {"value": cpu["value"], "unit": "reads/s", "cores": cpu["cores"], "kind": cpu["kind"], "sample": cpu["sample"],
                  "port_reads_per_s": cpu.get("port_reads_per_s")},
-                "parity_check": parity, "occ_gather": occ, "e2e_gathered": gathered,
+                "parity_check": parity, "occ_gather": occ, "e2e_gathered": gathered, "e2e_cli": cli,
                 "index_build": getattr(al, "index_build_info", None),
                 "counters_per_read": {k: (v if k.startswith("max") else v / (w["batch"] * args.steps)) for k, v in ctr_sum.items()},
                 "hits_per_read": hits_total / (w["batch"] * args.steps)}

@@ -329,6 +329,19 @@ class Aligner:
                                         len(offsets) - 1, C.byref(h)), self._ctx)
         return AlignResult(self, h.value)
 
+    def align_fastq(self, fastq_path: str, aln_path: Optional[str], params: Optional[Params] = None, batch: int = 0,
+                    sam_path: Optional[str] = None, ann_path: Optional[str] = None, max_mm: int = 6) -> int:
+        """bwb_align_fastq on this context (index already loaded): FASTQ file -> .aln / SAM file, streamed."""
+        params = params or default_params()
+        n = _lib.lib().bwb_align_fastq(self._ctx, C.byref(params), os.fsencode(fastq_path),
+                                       os.fsencode(aln_path) if aln_path else None,
+                                       os.fsencode(sam_path) if sam_path else None,
+                                       os.fsencode(ann_path) if ann_path else None,
+                                       self.index_length(), int(max_mm), int(batch))
+        if n < 0:
+            _lib.check(int(n), self._ctx)
+        return int(n)
+
     def upload_reads(self, seq, offsets) -> DeviceReads:
         seq, offsets = _u8(seq), _u64(offsets)
         h = C.c_void_p()

@@ -10,6 +10,7 @@
 #include <cstring>
 #include <cmath>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "bwbble_b200.h"
@@ -24,32 +25,41 @@ const std::vector<bwb_loc> *results_loc(const bwb_results *r);
 
 namespace {
 
-inline void put32(std::vector<uint8_t> &o, int32_t v) {
-    const uint8_t *p = reinterpret_cast<const uint8_t *>(&v);
-    o.insert(o.end(), p, p + 4);
-}
-inline void put64(std::vector<uint8_t> &o, uint64_t v) {
-    const uint8_t *p = reinterpret_cast<const uint8_t *>(&v);
-    o.insert(o.end(), p, p + 8);
-}
+// bytes one hit can take at most: 8 fixed fields (44 B) + n_pairs + up to 256 pairs
+constexpr size_t HIT_MAX = 44 + 4 + 256 * 4;
 
-void serialise(const bwb_results *r, std::vector<uint8_t> &o) {
-    const auto &counts = bwb_host::results_counts(r);
-    const auto &hits = bwb_host::results_hits(r);
-    o.reserve(counts.size() * 4 + hits.size() * 52);
-    size_t h = 0;
+inline uint8_t *put32(uint8_t *p, int32_t v) { memcpy(p, &v, 4); return p + 4; }
+inline uint8_t *put64(uint8_t *p, uint64_t v) { memcpy(p, &v, 8); return p + 8; }
+
+// reads [r0, r1) whose first hit is hits[h]; appends to o
+void serialise_range(const std::vector<uint32_t> &counts, const std::vector<bwb_hit> &hits, size_t r0, size_t r1, size_t h,
+                     std::vector<uint8_t> &o) {
+    size_t nh = 0;
+    for (size_t rd = r0; rd < r1; rd++) nh += counts[rd];
+    o.resize((r1 - r0) * 4 + nh * 52 + HIT_MAX);         // 52 B = a hit without gaps; grown below when gaps make it longer
+    uint8_t *p = o.data();
     uint8_t path[256];
-    for (size_t rd = 0; rd < counts.size(); rd++) {
-        put32(o, (int32_t)counts[rd]);
+    for (size_t rd = r0; rd < r1; rd++) {
+        p = put32(p, (int32_t)counts[rd]);
         for (uint32_t k = 0; k < counts[rd]; k++, h++) {
+            if ((size_t)(p - o.data()) + HIT_MAX + 4 > o.size()) {           // gapped hits carry more pairs
+                const size_t used = (size_t)(p - o.data());
+                o.resize(o.size() + o.size() / 4 + 4 * HIT_MAX);
+                p = o.data() + used;
+            }
             const bwb_hit &t = hits[h];
-            put32(o, t.score); put64(o, t.L); put64(o, t.U);
-            put32(o, t.num_mm); put32(o, t.num_gapo); put32(o, t.num_gape); put32(o, t.aln_length);
+            p = put32(p, t.score); p = put64(p, t.L); p = put64(p, t.U);
+            p = put32(p, t.num_mm); p = put32(p, t.num_gapo); p = put32(p, t.num_gape); p = put32(p, t.aln_length);
             const int alen = t.aln_length;
-            if (alen == 0) { put32(o, 0); continue; }
+            if (alen == 0) { p = put32(p, 0); continue; }
+            if (t.n_runs == 0) {                         // all STATE_M: one pair
+                p = put32(p, 1);
+                p = put32(p, (int32_t)((uint32_t)(uint16_t)alen << 2));
+                continue;
+            }
             memset(path, 0, sizeof path);
             for (int q = 0; q < t.n_runs && q < BWB_MAX_GAP_RUNS; q++)
-                for (int s = 0; s < t.runs[q].len; s++) path[(uint8_t)(t.runs[q].start + s)] = t.runs[q].state;
+                for (int s2 = 0; s2 < t.runs[q].len; s2++) path[(uint8_t)(t.runs[q].start + s2)] = t.runs[q].state;
             int32_t pairs[256];
             int np = 0;
             int state = path[alen - 1];
@@ -59,10 +69,36 @@ void serialise(const bwb_results *r, std::vector<uint8_t> &o) {
                 else { pairs[np++] = state | (run << 2); state = path[q]; run = 1; }
             }
             pairs[np++] = state | (run << 2);
-            put32(o, np);
-            for (int q = 0; q < np; q++) put32(o, pairs[q]);
+            p = put32(p, np);
+            for (int q = 0; q < np; q++) p = put32(p, pairs[q]);
         }
     }
+    o.resize((size_t)(p - o.data()));
+}
+
+// the records of all reads, in input order, as a list of chunks (one per worker thread)
+void serialise(const bwb_results *r, std::vector<std::vector<uint8_t>> &chunks) {
+    const auto &counts = bwb_host::results_counts(r);
+    const auto &hits = bwb_host::results_hits(r);
+    const size_t n = counts.size();
+    unsigned hw = std::thread::hardware_concurrency();
+    size_t nt = n < (1u << 16) ? 1 : (hw ? (hw > 16 ? 16 : hw) : 4);
+    chunks.assign(nt, std::vector<uint8_t>());
+    std::vector<size_t> r0(nt + 1), h0(nt + 1, 0);
+    for (size_t t = 0; t <= nt; t++) r0[t] = n * t / nt;
+    {
+        size_t h = 0, t = 1;
+        for (size_t rd = 0; rd < n; rd++) {
+            while (t <= nt && r0[t] == rd) h0[t++] = h;
+            h += counts[rd];
+        }
+        while (t <= nt) h0[t++] = h;
+    }
+    if (nt == 1) { serialise_range(counts, hits, 0, n, 0, chunks[0]); return; }
+    std::vector<std::thread> th;
+    for (size_t t = 0; t < nt; t++)
+        th.emplace_back([&, t] { serialise_range(counts, hits, r0[t], r0[t + 1], h0[t], chunks[t]); });
+    for (auto &x : th) x.join();
 }
 
 }  // namespace
@@ -70,25 +106,29 @@ void serialise(const bwb_results *r, std::vector<uint8_t> &o) {
 extern "C" int bwb_results_aln_bytes(const bwb_results *r, uint8_t **buf, uint64_t *len) {
     if (!r || !buf || !len) return BWB_ERR_ARG;
     if (!bwb_host::results_fetched(r)) return BWB_ERR_ARG;
-    std::vector<uint8_t> o;
-    serialise(r, o);
-    uint8_t *p = (uint8_t *)malloc(o.size() ? o.size() : 1);
+    std::vector<std::vector<uint8_t>> chunks;
+    serialise(r, chunks);
+    size_t total = 0;
+    for (auto &c : chunks) total += c.size();
+    uint8_t *p = (uint8_t *)malloc(total ? total : 1);
     if (!p) return BWB_ERR_IO;
-    memcpy(p, o.data(), o.size());
+    size_t w = 0;
+    for (auto &c : chunks) { memcpy(p + w, c.data(), c.size()); w += c.size(); }
     *buf = p;
-    *len = o.size();
+    *len = total;
     return BWB_OK;
 }
 
 extern "C" int bwb_results_write_aln(const bwb_results *r, const char *path, int append) {
     if (!r || !path) return BWB_ERR_ARG;
     if (!bwb_host::results_fetched(r)) return BWB_ERR_ARG;
-    std::vector<uint8_t> o;
-    serialise(r, o);
+    std::vector<std::vector<uint8_t>> chunks;
+    serialise(r, chunks);
     FILE *f = fopen(path, append ? "ab" : "wb");
     if (!f) return BWB_ERR_IO;
-    const bool ok = fwrite(o.data(), 1, o.size(), f) == o.size();
-    fclose(f);
+    bool ok = true;
+    for (auto &c : chunks) ok = ok && fwrite(c.data(), 1, c.size(), f) == c.size();
+    ok = (fclose(f) == 0) && ok;
     return ok ? BWB_OK : BWB_ERR_IO;
 }
 

@@ -25,32 +25,73 @@
 
 namespace {
 
+// Buffered input with two primitives the record grammar needs: "consume through the next occurrence of a
+// character" and "the rest of the current line", both memchr over 4 MB blocks instead of a call per byte.
 class Reader {
   public:
-    explicit Reader(FILE *f) : f_(f), buf_(1 << 20), pos_(0), end_(0) {}
-    int get() {
-        if (pos_ == end_) {
-            end_ = fread(buf_.data(), 1, buf_.size(), f_);
-            pos_ = 0;
-            if (end_ == 0) return EOF;
+    explicit Reader(FILE *f) : f_(f), buf_(4u << 20), pos_(0), end_(0), eof_(false) {}
+    // consume up to and including the next `c`; false at end of file
+    bool skip_through(char c) {
+        for (;;) {
+            if (pos_ == end_ && !fill()) return false;
+            const char *q = (const char *)memchr(buf_.data() + pos_, c, end_ - pos_);
+            if (q) { pos_ = (size_t)(q - buf_.data()) + 1; return true; }
+            pos_ = end_;
         }
-        return (unsigned char)buf_[pos_++];
+    }
+    // the rest of the current line (without its '\n', which is consumed); *p points into the buffer and stays valid
+    // until the next call.  false if the file ends before a '\n'.
+    bool rest_of_line(const char **p, size_t *n, bool eof_ends_line = false) {
+        size_t from = pos_;
+        for (;;) {
+            const char *q = end_ > from ? (const char *)memchr(buf_.data() + from, '\n', end_ - from) : nullptr;
+            if (q) {
+                *p = buf_.data() + pos_;
+                *n = (size_t)(q - (buf_.data() + pos_));
+                pos_ = (size_t)(q - buf_.data()) + 1;
+                return true;
+            }
+            // keep the partial line, read more behind it
+            const size_t have = end_ - pos_;
+            if (pos_ > 0) { memmove(buf_.data(), buf_.data() + pos_, have); pos_ = 0; end_ = have; }
+            if (end_ == buf_.size()) buf_.resize(buf_.size() * 2);
+            from = end_;
+            size_t got = 0;
+            if (!eof_) got = fread(buf_.data() + end_, 1, buf_.size() - end_, f_);
+            if (got == 0) {
+                eof_ = true;
+                if (!eof_ends_line) return false;
+                *p = buf_.data() + pos_;              // the file ends inside this line: it is the line (io.c:487-495)
+                *n = end_ - pos_;
+                pos_ = end_;
+                return true;
+            }
+            end_ += got;
+        }
     }
   private:
+    bool fill() {
+        if (eof_) return false;
+        end_ = fread(buf_.data(), 1, buf_.size(), f_);
+        pos_ = 0;
+        if (end_ == 0) { eof_ = true; return false; }
+        return true;
+    }
     FILE *f_;
     std::vector<char> buf_;
     size_t pos_, end_;
+    bool eof_;
 };
 
-inline uint8_t nt4(int c) {
-    switch (c) {
-        case 'A': case 'a': return 0;
-        case 'G': case 'g': return 1;
-        case 'C': case 'c': return 2;
-        case 'T': case 't': return 3;
-        default: return 4;
+struct Nt4Table {
+    uint8_t t[256];
+    Nt4Table() {
+        memset(t, 4, sizeof t);
+        t[(int)'A'] = t[(int)'a'] = 0; t[(int)'G'] = t[(int)'g'] = 1;
+        t[(int)'C'] = t[(int)'c'] = 2; t[(int)'T'] = t[(int)'t'] = 3;
     }
-}
+};
+const Nt4Table NT4;          // nt4_table, io.h:113-130
 
 struct Batch {
     std::vector<uint8_t> seq;
@@ -61,26 +102,22 @@ struct Batch {
 
 // returns 1 = read parsed, 0 = clean end of file, <0 = malformed
 int next_read(Reader &in, Batch &b, bool keep_text) {
-    int c;
-    while ((c = in.get()) != EOF && c != '@') {}
-    if (c == EOF) return 0;
-    std::string name;
-    while ((c = in.get()) != EOF && c != '\n') if (name.size() < 256) name.push_back((char)c);
-    if (c == EOF) return BWB_ERR_IO;
-    const size_t start = b.seq.size();
-    while ((c = in.get()) != EOF && c != '\n') b.seq.push_back(nt4(c));
-    if (c == EOF) return BWB_ERR_IO;
-    const size_t len = b.seq.size() - start;
-    while ((c = in.get()) != EOF && c != '+') {}
-    if (c == EOF) return BWB_ERR_IO;
-    while ((c = in.get()) != EOF && c != '\n') {}
-    if (c == EOF) return BWB_ERR_IO;
-    std::string qual;
-    size_t qlen = 0;
-    while ((c = in.get()) != EOF && c != '\n') { if (keep_text) qual.push_back((char)c); qlen++; }
-    if (qlen != len) return BWB_ERR_ARG;          // "number of quality score symbols does not match" (io.c:497-500)
+    const char *p;
+    size_t n;
+    if (!in.skip_through('@')) return 0;
+    if (!in.rest_of_line(&p, &n)) return BWB_ERR_IO;
+    if (keep_text) b.names.emplace_back(p, n < 256 ? n : 256);
+    if (!in.rest_of_line(&p, &n)) return BWB_ERR_IO;
+    const size_t start = b.seq.size(), len = n;
+    b.seq.resize(start + len);
+    uint8_t *dst = b.seq.data() + start;
+    for (size_t i = 0; i < len; i++) dst[i] = NT4.t[(unsigned char)p[i]];
+    if (!in.skip_through('+')) return BWB_ERR_IO;
+    if (!in.rest_of_line(&p, &n)) return BWB_ERR_IO;
+    in.rest_of_line(&p, &n, true);                // the quality line may end with the file
+    if (n != len) return BWB_ERR_ARG;             // "number of quality score symbols does not match" (io.c:497-500)
     b.off.push_back(b.seq.size());
-    if (keep_text) { b.names.push_back(std::move(name)); b.quals.push_back(std::move(qual)); }
+    if (keep_text) b.quals.emplace_back(p, n);
     return 1;
 }
 
@@ -122,6 +159,40 @@ extern "C" long long bwb_align_fastq(bwb_ctx *ctx, const bwb_params *params, con
             if (last) return;
         }
     });
+    // consumer side: this thread aligns batch k while a writer thread serialises batch k-1 (results are host-side
+    // once fetched, so they outlive the next launch) and the producer parses batch k+1
+    struct Done { std::unique_ptr<Parsed> p; bwb_results *res = nullptr; bool first = false; };
+    std::deque<Done> to_write;
+    bool write_stop = false;
+    int rc_w = BWB_OK;
+    std::thread writer([&] {
+        for (;;) {
+            Done d;
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&] { return write_stop || !to_write.empty(); });
+                if (to_write.empty()) return;
+                d = std::move(to_write.front());
+                to_write.pop_front();
+                cv.notify_all();
+            }
+            int rcw = BWB_OK;
+            Batch &b = d.p->b;
+            const uint64_t n = b.off.size() - 1;
+            static const uint8_t none = 0;
+            if (rc_w == BWB_OK) {
+                if (aln_path) rcw = bwb_results_write_aln(d.res, aln_path, 1);
+                if (rcw == BWB_OK && sam_path) {
+                    std::vector<const char *> nm(n ? n : 1), ql(n ? n : 1);
+                    for (uint64_t i = 0; i < n; i++) { nm[i] = b.names[i].c_str(); ql[i] = b.quals[i].c_str(); }
+                    rcw = bwb_results_write_sam(d.res, ann_path, nm.data(), n ? b.seq.data() : &none, b.off.data(), ql.data(),
+                                                index_length, max_mm, sam_path, d.first ? 1 : 0, d.first ? 0 : 1);
+                }
+            }
+            bwb_results_free(d.res);
+            if (rcw != BWB_OK) { std::lock_guard<std::mutex> lk(mu); if (rc_w == BWB_OK) rc_w = rcw; cv.notify_all(); }
+        }
+    });
     long long total = 0;
     bool first = true;
     int rc = BWB_OK;
@@ -133,6 +204,7 @@ extern "C" long long bwb_align_fastq(bwb_ctx *ctx, const bwb_params *params, con
             p = std::move(ready.front());
             ready.pop_front();
             cv.notify_all();
+            if (rc_w != BWB_OK) { rc = rc_w; break; }
         }
         if (p->status != BWB_OK) { rc = p->status; break; }
         Batch &b = p->b;
@@ -142,19 +214,26 @@ extern "C" long long bwb_align_fastq(bwb_ctx *ctx, const bwb_params *params, con
         static const uint8_t none = 0;
         rc = bwb_align(ctx, params, n ? b.seq.data() : &none, b.off.data(), n, &res);
         if (rc != BWB_OK) break;
-        if (aln_path) rc = bwb_results_write_aln(res, aln_path, 1);
-        if (rc == BWB_OK && sam_path) {
-            std::vector<const char *> nm(n ? n : 1), ql(n ? n : 1);
-            for (uint64_t i = 0; i < n; i++) { nm[i] = b.names[i].c_str(); ql[i] = b.quals[i].c_str(); }
-            rc = bwb_results_write_sam(res, ann_path, nm.data(), n ? b.seq.data() : &none, b.off.data(), ql.data(),
-                                       index_length, max_mm, sam_path, first ? 1 : 0, first ? 0 : 1);
+        const bool eof = p->eof;
+        {
+            std::unique_lock<std::mutex> lk(mu);
+            cv.wait(lk, [&] { return to_write.size() < 2; });
+            Done d;
+            d.p = std::move(p); d.res = res; d.first = first;
+            to_write.push_back(std::move(d));
+            cv.notify_all();
         }
-        bwb_results_free(res);
-        if (rc != BWB_OK) break;
         total += (long long)n;
         first = false;
-        if (p->eof) break;
+        if (eof) break;
     }
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        write_stop = true;
+        cv.notify_all();
+    }
+    writer.join();
+    if (rc == BWB_OK && rc_w != BWB_OK) rc = rc_w;
     {
         std::lock_guard<std::mutex> lk(mu);
         stop = true;
@@ -162,5 +241,10 @@ extern "C" long long bwb_align_fastq(bwb_ctx *ctx, const bwb_params *params, con
     }
     producer.join();
     fclose(f);
+    if (rc != BWB_OK) {
+        // earlier batches are already on disk: do not leave a truncated file under the name of a complete one
+        if (aln_path) rename(aln_path, (std::string(aln_path) + ".partial").c_str());
+        if (sam_path) rename(sam_path, (std::string(sam_path) + ".partial").c_str());
+    }
     return rc == BWB_OK ? total : (long long)rc;
 }

@@ -231,7 +231,9 @@ int bwb_results_write_sam(const bwb_results *r, const char *ann_path, const char
 /* Parse `fastq_path` in batches of `batch_reads` (0 = 4 Mi) reads, align every batch and append its
  * records to `aln_path` (binary .aln, removed first like align.c:48) and/or `sam_path` (needs the
  * sampled SA uploaded, `ann_path` = <fasta>.ann, index_length, max_mm as for bwb_results_write_sam).
- * Returns the number of reads, or a negative bwb_status. */
+ * Three threads: the parser (memchr over 4 MB blocks) works on batch k+1 and the writer on batch k-1 while
+ * batch k is on the device.  Returns the number of reads, or a negative bwb_status -- in which case the
+ * output written so far is renamed to <path>.partial rather than left under the final name. */
 long long bwb_align_fastq(bwb_ctx *ctx, const bwb_params *params, const char *fastq_path, const char *aln_path,
                           const char *sam_path, const char *ann_path, uint64_t index_length, int max_mm,
                           uint64_t batch_reads);
