@@ -400,16 +400,17 @@ def main():
     cli = None
     if rank == 0 and world == 1 and args.cli_reads != 0:
         try:
-            n_cli = args.cli_reads if args.cli_reads > 0 else min(w["batch"], 1 << 22)
+            n_cli = args.cli_reads if args.cli_reads > 0 else min(w["batch"], 1 << 23)
+            cli_batch = max(1 << 16, n_cli // 8)            # 8 launches: parse k+1 | device k | write k-1 overlap
             sub = batches[0].slice(0, min(n_cli, batches[0].n))
             d = os.path.join(CACHE, "cli")
             os.makedirs(d, exist_ok=True)
             fq, aln = os.path.join(d, "r.fq"), os.path.join(d, "out.aln")
             sub.write_fastq(fq)
             t = time.time()
-            n_done = al.align_fastq(fq, aln, p, batch=0)
+            n_done = al.align_fastq(fq, aln, p, batch=cli_batch)
             dt = time.time() - t
-            cli = {"value": n_done / dt, "unit": "reads/s", "reads": n_done, "seconds": dt,
+            cli = {"value": n_done / dt, "unit": "reads/s", "reads": n_done, "seconds": dt, "reads_per_launch": cli_batch,
                    "what": "bwb_align_fastq: FASTQ file -> parse -> H2D -> K3/K4/K5 -> D2H -> serialise -> .aln file (3 threads)",
                    "fastq_bytes": os.path.getsize(fq), "aln_bytes": os.path.getsize(aln)}
             import hashlib

@@ -11,7 +11,9 @@ seeded multi-genome + reads, and records what the real reference produces:
     aln_<tag>.aln for PGRID         the same with -P (12-mer seed table); the 68 MB g.fa.pre the
                                     reference computes on the way is pinned by its md5 and its interval count
     manifest.json                   tag -> flags, md5 of every file
-`python tests/golden/make_golden.py --precalc-only` adds the PGRID files to an existing golden set.
+`python tests/golden/make_golden.py --precalc-only` adds the PGRID files to an existing golden set;
+`--shipped-fastq` adds the reference's own test_data/sim_chr21_N100.fastq (BASELINE configs[0]) with the outputs
+the reference produces for it on a small multi-genome the reads' loci were planted into (g21.fa).
 The reference repository ships no golden vectors of its own, so these ARE the pin.
 """
 import gzip
@@ -79,7 +81,67 @@ def add_precalc(ref, manifest):
                                      "intervals": int((raw.size - 4 * (1 << 24)) // 16)}
 
 
+def add_shipped_fastq(ref, manifest):
+    """BASELINE configs[0]: the one real input the reference ships, test_data/sim_chr21_N100.fastq (100 reads of
+    100 bp simulated from chr21; mg-aligner/README.md:33-38).  Its FASTA is not in the tree, so the reads are planted
+    into a small multi-genome (each read's locus + random spacers, some sites turned into IUPAC SNP codes) and the
+    reference's own index / align / aln2sam outputs on it are recorded."""
+    import numpy as np
+    src = "/root/reference/test_data/sim_chr21_N100.fastq"
+    shutil.copy(src, os.path.join(HERE, "sim_chr21_N100.fastq"))
+    os.chmod(os.path.join(HERE, "sim_chr21_N100.fastq"), 0o644)
+    lines = open(src).read().split("\n")
+    seqs = [lines[i + 1] for i in range(0, len(lines) - 3, 4)]
+    rng = np.random.default_rng(2121)
+    iupac = {"A": "RWM", "C": "YSM", "G": "RSK", "T": "YWK"}
+    parts = []
+    for k, sq in enumerate(seqs):
+        sq = list(sq.upper())
+        for pos in rng.choice(len(sq), size=2, replace=False):          # two SNP sites per locus
+            if sq[pos] in iupac:
+                sq[pos] = iupac[sq[pos]][int(rng.integers(0, 3))]
+        if k % 7 == 3:                                                    # a substitution the read has to pay for
+            pos = int(rng.integers(20, 80))
+            sq[pos] = "ACGT"[("ACGT".index(sq[pos]) + 1) % 4] if sq[pos] in "ACGT" else sq[pos]
+        parts.append("".join(sq))
+        parts.append("".join("ACGT"[i] for i in rng.integers(0, 4, size=int(rng.integers(30, 90)))))
+    genome = "".join(parts)
+    with tempfile.TemporaryDirectory() as d:
+        fa = os.path.join(d, "g21.fa")
+        with open(fa, "w") as f:
+            f.write(">chr21_loci planted sim_chr21_N100 reads\n")
+            for i in range(0, len(genome), 60):
+                f.write(genome[i:i + 60] + "\n")
+        run = lambda *a: subprocess.run([ref, *a], check=True, stdout=subprocess.DEVNULL)
+        run("index", fa)
+        shutil.copy(fa, os.path.join(HERE, "g21.fa"))
+        shutil.copy(fa + ".ann", os.path.join(HERE, "g21.fa.ann"))
+        with open(fa + ".bwt", "rb") as s2, gzip.GzipFile(os.path.join(HERE, "g21.fa.bwt.gz"), "wb", mtime=0) as dst:
+            dst.write(s2.read())
+        manifest["md5"]["g21.fa.bwt"] = md5(fa + ".bwt")
+        manifest["shipped"] = {"sim_n0": ["-n", "0"], "sim_n5": ["-n", "5"]}
+        for tag, flags in manifest["shipped"].items():
+            aln = os.path.join(d, "out.aln")
+            run("align", *flags, fa, src, aln)
+            shutil.copy(aln, os.path.join(HERE, "aln_%s.aln" % tag))
+            manifest["md5"]["aln_%s.aln" % tag] = md5(aln)
+            sam = os.path.join(d, "out.sam")
+            run("aln2sam", "-n", flags[1], fa, src, aln, sam)
+            shutil.copy(sam, os.path.join(HERE, "sam_%s.sam" % tag))
+            manifest["md5"]["sam_%s.sam" % tag] = md5(sam)
+        for f in ("g21.fa", "g21.fa.ann", "sim_chr21_N100.fastq"):
+            manifest["md5"][f] = md5(os.path.join(HERE, f))
+
+
 def main():
+    if "--shipped-fastq" in sys.argv:
+        import oracle
+        ref = oracle.ensure_ref_binary()
+        assert ref, "/root/reference is required to (re)generate the golden files"
+        manifest = json.load(open(os.path.join(HERE, "manifest.json")))
+        add_shipped_fastq(ref, manifest)
+        json.dump(manifest, open(os.path.join(HERE, "manifest.json"), "w"), indent=1, sort_keys=True)
+        return
     if "--precalc-only" in sys.argv:
         import oracle
         ref = oracle.ensure_ref_binary()

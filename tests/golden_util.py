@@ -38,13 +38,14 @@ def golden_bytes(name):
     return open(os.path.join(GOLDEN, name), "rb").read()
 
 
-def materialise_index(tmpdir):
-    """g.fa + g.fa.bwt (+ .ann) as the reference wrote them, in tmpdir; returns the fasta path."""
-    fa = os.path.join(str(tmpdir), "g.fa")
+def materialise_index(tmpdir, name="g.fa"):
+    """<name> + .bwt (+ .ann) as the reference wrote them, in tmpdir; returns the fasta path.
+    name = "g21.fa": the multi-genome the reference's shipped sim_chr21_N100.fastq reads were planted into."""
+    fa = os.path.join(str(tmpdir), name)
     with open(fa, "wb") as f:
-        f.write(golden_bytes("g.fa"))
+        f.write(golden_bytes(name))
     with open(fa + ".bwt", "wb") as f:
-        f.write(gzip.decompress(golden_bytes("g.fa.bwt.gz")))
+        f.write(gzip.decompress(golden_bytes(name + ".bwt.gz")))
     with open(fa + ".ann", "wb") as f:
-        f.write(golden_bytes("g.fa.ann"))
+        f.write(golden_bytes(name + ".ann"))
     return fa

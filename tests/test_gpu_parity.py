@@ -391,6 +391,23 @@ def test_streaming_fastq_ingest_writes_reference_aln_and_sam(tmp_path, batch):
     assert open(sam, "rb").read() == G.golden_bytes("sam_n3.sam")
 
 
+@pytest.mark.parametrize("tag", ["sim_n0", "sim_n5"])
+def test_reference_shipped_fastq_through_the_streaming_entry_point(tmp_path, tag):
+    """BASELINE configs[0]: the reference's own test_data/sim_chr21_N100.fastq through bwb_align_fastq (.aln + SAM)
+    against what the unmodified reference wrote for it (index g21.fa: the reads' loci planted, IUPAC SNP sites)"""
+    import golden_util as G
+    from bwbble_b200 import align_reads
+    import os
+    fa = G.materialise_index(tmp_path, "g21.fa")
+    kw = G.flags_to_kwargs(G.MANIFEST["shipped"][tag])
+    aln, sam = str(tmp_path / "o.aln"), str(tmp_path / "o.sam")
+    n = align_reads(fa, os.path.join(G.GOLDEN, "sim_chr21_N100.fastq"), aln, default_params(**kw), sam_path=sam,
+                    max_mm=kw["max_diff"])
+    assert n == 100
+    assert open(aln, "rb").read() == G.golden_bytes("aln_%s.aln" % tag)
+    assert open(sam, "rb").read() == G.golden_bytes("sam_%s.sam" % tag)
+
+
 def test_kmer_table_on_dense_genome(dense_case):
     """10-mer table of calculate_d's top of tree: adoption of tabulated lists (dozens of intervals), restarts inside
     the window, N inside the window, reads shorter than the window -- D arrays equal the oracle's."""

@@ -59,3 +59,19 @@ def test_golden_fixture_exercises_the_hard_cases():
 
 def test_threaded_driver_equals_serial_on_golden():
     assert G.golden_bytes("aln_n3.aln") == G.golden_bytes("aln_n3_t4.aln")
+
+
+@pytest.mark.parametrize("tag", ["sim_n0", "sim_n5"])
+def test_oracle_on_the_reference_shipped_fastq(tmp_path, tag):
+    """BASELINE configs[0]: test_data/sim_chr21_N100.fastq, the one input the reference ships, on the multi-genome its
+    reads were planted into (tests/golden/make_golden.py --shipped-fastq): the reference's own .aln"""
+    fa = G.materialise_index(tmp_path, "g21.fa")
+    reads = read_fastq(os.path.join(G.GOLDEN, "sim_chr21_N100.fastq"))
+    assert reads.n == 100
+    orc = oracle.Oracle(fa + ".bwt")
+    kw = G.flags_to_kwargs(G.MANIFEST["shipped"][tag])
+    got, _ = orc.align(reads.seq, reads.offsets, default_params(**kw))
+    orc.close()
+    exp = G.golden_bytes("aln_%s.aln" % tag)
+    assert got == exp, first_difference(got, exp)
+    assert sum(1 for r in parse_aln(exp) if r) >= (90 if tag == "sim_n5" else 50)      # the reads do map
