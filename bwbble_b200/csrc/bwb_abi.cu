@@ -75,7 +75,7 @@ struct bwb_ctx {
     uint64_t length = 0, num_blocks = 0, sa0 = 0;
     uint64_t C[17] = {0};
     // options
-    long long heap_pool_mb = 0;      // 0 = auto: half of the free device memory, at most 64 GB
+    long long heap_pool_mb = 0;      // 0 = auto: 70 % of the free device memory, at most 128 GB
     int list_cap = 4096;
     int hits_per_read = 512;
     int warps_per_block = 8;
@@ -1105,6 +1105,11 @@ static int check_params(bwb_ctx *ctx, const bwb_params *p, int max_len, int &nb)
     if (p->max_gapo > BWB_MAX_GAP_RUNS) return fail(ctx, BWB_ERR_UNSUPPORTED, "max_gapo > %d", BWB_MAX_GAP_RUNS);
     nb = (p->max_diff + 1) * p->mm_score + (p->max_gapo + 1) * p->gapo_score + (p->max_gape + 1) * p->gape_score;
     if (nb <= 0 || nb > 1024) return fail(ctx, BWB_ERR_UNSUPPORTED, "%d score buckets (supported: 1..1024)", nb);
+    // the engine limits, all in one place and before anything is launched (INTEGRATION.md "Limits of the device path")
+    if (ctx->engine == 0 && nb > 128)
+        return fail(ctx, BWB_ERR_UNSUPPORTED, "%d score buckets = (n+1)*M + (o+1)*O + (e+1)*E with -n %d -o %d -e %d -M %d -O %d -E %d; the device "
+                    "search keeps the occupancy of at most 128 buckets in registers (the reference allocates any number, inexact_match.c:510-528)",
+                    nb, p->max_diff, p->max_gapo, p->max_gape, p->mm_score, p->gapo_score, p->gape_score);
     if (p->seed_length > 255) return fail(ctx, BWB_ERR_ARG, "seed_length > 255");
     int gaps = p->max_gapo + p->max_gape;
     if (gaps > p->max_diff) gaps = p->max_diff;
