@@ -81,6 +81,8 @@ SIGNATURES = {
     "bwb_index_build_device": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int, C.POINTER(C.c_int)]),
     "bwb_align_fastq": (C.c_longlong, [C.c_void_p, C.POINTER(Params), C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p,
                                        C.c_uint64, C.c_int, C.c_uint64]),
+    "bwb_fastq_parse": (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_uint64),
+                                  C.POINTER(C.c_void_p), C.POINTER(C.c_uint64), C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]),
     "bwb_sa_upload": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64]),
     "bwb_index_load_file_sa": (C.c_int, [C.c_void_p, C.c_char_p]),
     "bwb_results_locations": (C.c_void_p, [C.c_void_p]),

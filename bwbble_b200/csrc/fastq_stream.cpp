@@ -123,6 +123,43 @@ int next_read(Reader &in, Batch &b, bool keep_text) {
 
 }  // namespace
 
+// Host-only: the whole file through the same record grammar (no context, no device) -- what the Python mirror and
+// the tests use, so that every entry point reads a FASTQ file the way fastq2reads does.  Arrays are malloc'ed
+// (bwb_free); names / quals (optional) are the strings concatenated with a NUL after each.
+extern "C" int bwb_fastq_parse(const char *fastq_path, uint8_t **seq, uint64_t **offsets, uint64_t *n_reads,
+                               char **names, uint64_t *names_bytes, char **quals, uint64_t *quals_bytes) {
+    if (!fastq_path || !seq || !offsets || !n_reads) return BWB_ERR_ARG;
+    FILE *f = fopen(fastq_path, "rb");
+    if (!f) return BWB_ERR_IO;
+    Reader in(f);
+    Batch b;
+    b.clear();
+    const bool keep = names != nullptr || quals != nullptr;
+    int st;
+    while ((st = next_read(in, b, keep)) == 1) {}
+    fclose(f);
+    if (st < 0) return st;
+    const uint64_t n = b.off.size() - 1;
+    *seq = (uint8_t *)malloc(b.seq.size() ? b.seq.size() : 1);
+    *offsets = (uint64_t *)malloc(b.off.size() * 8);
+    if (!*seq || !*offsets) return BWB_ERR_IO;
+    memcpy(*seq, b.seq.data(), b.seq.size());
+    memcpy(*offsets, b.off.data(), b.off.size() * 8);
+    *n_reads = n;
+    auto pack = [](const std::vector<std::string> &v, char **out, uint64_t *bytes) {
+        size_t tot = 0;
+        for (auto &x : v) tot += x.size() + 1;
+        char *p = (char *)malloc(tot ? tot : 1);
+        size_t w = 0;
+        for (auto &x : v) { memcpy(p + w, x.data(), x.size()); w += x.size(); p[w++] = 0; }
+        *out = p;
+        if (bytes) *bytes = tot;
+    };
+    if (names) pack(b.names, names, names_bytes);
+    if (quals) pack(b.quals, quals, quals_bytes);
+    return BWB_OK;
+}
+
 extern "C" long long bwb_align_fastq(bwb_ctx *ctx, const bwb_params *params, const char *fastq_path, const char *aln_path,
                                      const char *sam_path, const char *ann_path, uint64_t index_length, int max_mm,
                                      uint64_t batch_reads) {

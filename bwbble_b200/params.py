@@ -24,4 +24,6 @@ def params_to_cli(p: Params) -> list:
         out += ["-" + flag, str(getattr(p, field))]
     if not p.is_multiref:
         out.append("-S")
+    if p.use_precalc:
+        out.append("-P")
     return out

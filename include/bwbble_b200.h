@@ -234,6 +234,10 @@ int bwb_results_write_sam(const bwb_results *r, const char *ann_path, const char
  * Three threads: the parser (memchr over 4 MB blocks) works on batch k+1 and the writer on batch k-1 while
  * batch k is on the device.  Returns the number of reads, or a negative bwb_status -- in which case the
  * output written so far is renamed to <path>.partial rather than left under the final name. */
+/* Host-only FASTQ reader with fastq2reads' record grammar (io.c:410-515): nt4 codes of all reads concatenated,
+ * n_reads+1 offsets; optionally the names / quality strings, each followed by a NUL.  malloc'ed: bwb_free(). */
+int bwb_fastq_parse(const char *fastq_path, uint8_t **seq, uint64_t **offsets, uint64_t *n_reads,
+                    char **names, uint64_t *names_bytes, char **quals, uint64_t *quals_bytes);
 long long bwb_align_fastq(bwb_ctx *ctx, const bwb_params *params, const char *fastq_path, const char *aln_path,
                           const char *sam_path, const char *ann_path, uint64_t index_length, int max_mm,
                           uint64_t batch_reads);
