@@ -323,14 +323,13 @@ __device__ __forceinline__ void low_bits128(int n, uint32_t &k0, uint32_t &k1, u
     k3 = n >= 128 ? ~0u : (n <= 96 ? 0u : ((1u << (n - 96)) - 1u));
 }
 
-// Task of owner lane o: interval in sLj[0][o], sUj[0][o]; sFlag[o] bit 0 = "true counts for codes 5,9,11,13"
-// (exact tails use O(), bwt.c:348-372, and -S never sees those codes; expansions in multi-genome mode use
-// O_alphabet with quirk Q1, bwt.c:427-435,780).  Results: sLj[j][o], sUj[j][o] for every j, sOk[o] = valid mask.
+// The interval task [L, iU] of lane `o`: child intervals -> sLj[j][o], sUj[j][o] for every code j; returns the mask of
+// the codes with L_j <= U_j.  trueq = "true counts for codes 5,9,11,13" (exact tails use O(), bwt.c:348-372, and -S
+// never sees those codes; expansions in multi-genome mode use O_alphabet with quirk Q1, bwt.c:427-435,780).
+// C[] comes straight from the kernel's constant-bank parameters (compile-time index: no load instruction).
 template <class T>
-__device__ __forceinline__ void rank_general(const IndexView &ix, const T *sC, T (*sLj)[128], T (*sUj)[128],
-                                             uint32_t *sOk, const uint8_t *sFlag, uint32_t o, T lastrow) {
-    const T L = sLj[0][o], iU = sUj[0][o];
-    const bool trueq = (sFlag[o] & 1u) != 0u;
+__device__ __forceinline__ uint32_t rank_general(const IndexView &ix, T (*sLj)[128], T (*sUj)[128], uint32_t o,
+                                                 const T L, const T iU, const bool trueq, const T lastrow) {
     const T iL = (T)(L - 1);
     const bool negL = (L == 0), topU = (iU == lastrow);
     const T aL = negL ? (T)0 : iL, aU = topU ? (T)0 : iU;
@@ -378,7 +377,7 @@ __device__ __forceinline__ void rank_general(const IndexView &ix, const T *sC, T
         // Q1: O_alphabet skips codes 5,9,11,13 except for the checkpoint-symbol decrement
         // (bwt.c:427-435,780); the exact search's O() counts them (bwt.c:348-372)
         const bool quirk = (j == 5 || j == 9 || j == 11 || j == 13);
-        const T Cj = sC[j], Cj1 = sC[j + 1];
+        const T Cj = (T)ix.C[j], Cj1 = (T)ix.C[j + 1];
         T Lj, Uj;
         if (quirk) {
             const T qL = trueq ? (T)vL : (T)0 - (T)(l0 & 1u);
@@ -393,7 +392,7 @@ __device__ __forceinline__ void rank_general(const IndexView &ix, const T *sC, T
         sUj[j][o] = Uj;
         okmask |= (Lj <= Uj) ? (1u << j) : 0u;
     }
-    sOk[o] = okmask;
+    return okmask;
 }
 
 // Per warp iteration (the 32 reads of a warp advance in lock-step, one interval task each):
@@ -417,10 +416,7 @@ static_assert(FREE_RING > 0 && FREE_RING < 256 && (FREE_RING & (FREE_RING - 1)) 
 template <bool WIDE, bool PRE, bool RECYCLE>
 __global__ void __launch_bounds__(128, BWB_LANE_MIN_BLOCKS(WIDE)) k_search_l(const __grid_constant__ LaneArgs a) {
     typedef typename Coord<WIDE>::type T;
-    __shared__ T sC[17];
-    __shared__ T sLj[16][128], sUj[16][128];      // row 0: the lane's interval; rows 1..15: child intervals by code
-    __shared__ uint32_t sOk[128];                 // valid-child mask per lane
-    __shared__ uint8_t sFlag[128];                // quirk mode of the lane's task
+    __shared__ T sLj[16][128], sUj[16][128];      // child intervals of the lane's task, by code (row 0 unused)
     // Slots of popped entries are handed straight to the next children (a small per-lane stack of free slot ids):
     // the arena a read needs is its LIVE heap, not every push it ever made -- 3-4x less at genome scale, where
     // bump-only allocation (round 1) overflowed the private ranges of most lanes and sent the reads to the
@@ -432,8 +428,6 @@ __global__ void __launch_bounds__(128, BWB_LANE_MIN_BLOCKS(WIDE)) k_search_l(con
                                                   // (touched when a tail starts / ends: kept out of the register file)
     extern __shared__ uint32_t sm_heads[];        // [nb][128] bucket heads
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-    stage_C<T>(a.ix, sC);
-
     const uint32_t lane_slot = blockIdx.x * blockDim.x + tid;
     const T lastrow = (T)(a.ix.length - 1);
     const bool multiref = a.is_multiref != 0;
@@ -776,12 +770,8 @@ __global__ void __launch_bounds__(128, BWB_LANE_MIN_BLOCKS(WIDE)) k_search_l(con
 
         // ================= B: rank stage =================
         __syncwarp();
-        if (have_task) {
-            sLj[0][tid] = e.L;
-            sUj[0][tid] = e.U;
-            sFlag[tid] = (task_tail || !multiref) ? 1 : 0;
-            rank_general<T>(a.ix, sC, sLj, sUj, sOk, sFlag, tid, lastrow);
-        }
+        uint32_t okmask = 0;
+        if (have_task) okmask = rank_general<T>(a.ix, sLj, sUj, tid, e.L, e.U, task_tail || !multiref, lastrow);
 
         // ================= C: consume the result =================
         // children of this warp's expansions are described here (owner registers) and written below, one child
@@ -790,7 +780,6 @@ __global__ void __launch_bounds__(128, BWB_LANE_MIN_BLOCKS(WIDE)) k_search_l(con
         if (have_task) {
             have_task = false;
             c_rank += 2u;
-            uint32_t okmask = sOk[tid];
             // Child index space t: multi-genome t = code (1..15, the reference's loop order);
             // single-genome (-S) t = 0..3 = A,G,C,T = codes 15,3,7,1 (O_actg_alphabet's order, bwt.c:440-463).
             // compat_set = indices that MATCH the read base: nucl_bases_table[c] (io.h:102-106, N excluded)
