@@ -42,6 +42,7 @@ assert C.sizeof(Hit) == 48 and C.sizeof(Params) == 60
 # name -> (restype, argtypes); the test-suite checks that every symbol of the header is exported
 SIGNATURES = {
     "bwb_default_params": (None, [C.POINTER(Params)]),
+    "bwb_score_buckets": (C.c_int, [C.POINTER(Params), C.POINTER(C.c_uint8), C.c_int]),
     "bwb_create": (C.c_void_p, [C.POINTER(C.c_int), C.c_int]),
     "bwb_destroy": (None, [C.c_void_p]),
     "bwb_last_error": (C.c_char_p, [C.c_void_p]),

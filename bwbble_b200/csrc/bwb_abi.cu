@@ -53,7 +53,7 @@ struct Device {
     uint32_t chunks_per_warp = 0, n_chunks = 0;
     // per-call buffers
     DevBuf seq, offsets, read_off, read_cnt, ordered_off, unordered, ordered, cub_tmp, small, d_main, d_seed, pool;
-    DevBuf pk_main, pk_seed, n_count, nxt, blk_link, heads, order, retry;      // lane engine
+    DevBuf pk_main, pk_seed, n_count, nxt, blk_link, heads, order, retry, bmap;      // lane engine
     DevBuf loc;                                                  // K6 output
     uint32_t slots_per_lane = 0, total_slots = 0, priv_total = 0;
     uint64_t auto_pool_bytes = 0;
@@ -99,6 +99,9 @@ struct bwb_ctx {
     std::vector<uint64_t> pre_lu_h;  // L,U pairs
     // every align call overwrites the per-device result buffers: un-fetched results of an older call are stale
     uint64_t launch_generation = 0;
+    // K4's score <-> bucket tables for the parameters of the current call (bucket_map)
+    int nbc = 0;
+    std::vector<uint8_t> bmap;
 };
 
 struct bwb_reads {
@@ -302,10 +305,12 @@ K4Fn k4_fn(bool wide, bool pre, bool recycle) {
 
 // size the persistent grid and the per-lane arena for the lane engine (K3 groups + K4 lanes)
 int prepare_search_lane(bwb_ctx *ctx, Device &d, int nb, bool wide) {
-    if (nb > 128) return fail(ctx, BWB_ERR_UNSUPPORTED, "%d score buckets: the lane engine keeps the occupancy of at most 128 in registers", nb);
+    if (ctx->nbc <= 0 || ctx->nbc > 128 || ctx->bmap.size() != (size_t)(256 + nb))
+        return fail(ctx, BWB_ERR_UNSUPPORTED, "%d reachable score buckets: the lane engine keeps the occupancy of at most 128 in registers", ctx->nbc);
     CU(cudaSetDevice(d.id));
     const int tpb = 128;
-    const size_t smem = (size_t)nb * tpb * 4;                 // bucket heads [nb][128]
+    // bucket heads [nbc][128], then score_of[128] (u16) and bucket_of[nb] (u8)
+    const size_t smem = ((size_t)ctx->nbc * tpb * 4 + 256 + (size_t)nb + 15) & ~(size_t)15;
     // the -P instantiations differ only in how a read is seeded: same launch shape as the plain ones
     for (int v = 0; v < 8; v++) CU(cudaFuncSetAttribute(k4_fn(v & 4, v & 2, v & 1), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int bps = ctx->blocks_per_sm;
@@ -625,7 +630,7 @@ void bwb_destroy(bwb_ctx *ctx) {
         if (d.pre_cnt) cudaFree(d.pre_cnt);
         if (d.pre_iv) cudaFree(d.pre_iv);
         DevBuf *bufs[] = {&d.glists, &d.chunks, &d.chunk_link, &d.stage, &d.seq, &d.offsets, &d.read_off, &d.read_cnt,
-                          &d.ordered_off, &d.unordered, &d.ordered, &d.cub_tmp, &d.small, &d.d_main, &d.d_seed, &d.pool, &d.loc, &d.pk_main, &d.pk_seed, &d.n_count, &d.nxt, &d.blk_link, &d.heads, &d.order, &d.retry};
+                          &d.ordered_off, &d.unordered, &d.ordered, &d.cub_tmp, &d.small, &d.d_main, &d.d_seed, &d.pool, &d.loc, &d.pk_main, &d.pk_seed, &d.n_count, &d.nxt, &d.blk_link, &d.heads, &d.order, &d.retry, &d.bmap};
         for (DevBuf *b : bufs) release(*b);
         if (d.h_small) cudaFreeHost(d.h_small);
         if (d.ev0) cudaEventDestroy(d.ev0);
@@ -1090,6 +1095,44 @@ void bwb_reads_free(bwb_reads *r) {
     delete r;
 }
 
+// The scores a partial alignment can have: m*M + o*O + e*E for m mismatches, o gap openings and e gap extensions with
+// m + o + e <= max_diff (children are only made of entries with differences to spare, inexact_match.c:377-389),
+// o <= max_gapo, e <= max_gape (:413-416) and e > 0 only once a gap is open (an extension continues state I/D).  K4 gives
+// only those scores a bucket, in ascending order (the order heap_pop looks at them, inexact_match.c:594-610).
+// Layout of `map`: uint16 score_of[128], then uint8 bucket_of[nb] (0xff = unreachable).  Returns the bucket count.
+static int bucket_map(const bwb_params *p, int nb, std::vector<uint8_t> &map) {
+    std::vector<char> reach((size_t)nb, 0);
+    for (int o = 0; o <= p->max_gapo && o <= p->max_diff; o++)
+        for (int e = 0; e <= (o ? p->max_gape : 0) && o + e <= p->max_diff; e++)
+            for (int m = 0; m + o + e <= p->max_diff; m++) {
+                const long long sc = (long long)m * p->mm_score + (long long)o * p->gapo_score + (long long)e * p->gape_score;
+                if (sc < nb) reach[(size_t)sc] = 1;
+            }
+    map.assign((size_t)256 + nb, 0xff);
+    int nbc = 0;
+    for (int sc = 0; sc < nb; sc++) {
+        if (!reach[(size_t)sc]) continue;
+        if (nbc < 128) {
+            map[(size_t)256 + sc] = (uint8_t)nbc;
+            const uint16_t v = (uint16_t)sc;
+            memcpy(&map[2 * (size_t)nbc], &v, 2);
+        }
+        nbc++;
+    }
+    return nbc;
+}
+
+extern "C" int bwb_score_buckets(const bwb_params *p, uint8_t *bucket_of, int cap) {
+    if (!p || p->max_diff < 0 || p->max_gapo < 0 || p->max_gape < 0 || p->mm_score < 0 || p->gapo_score < 0 || p->gape_score < 0 || p->max_diff > 200)
+        return fail(nullptr, BWB_ERR_ARG, "negative or out-of-range alignment parameter");
+    const int nb = (p->max_diff + 1) * p->mm_score + (p->max_gapo + 1) * p->gapo_score + (p->max_gape + 1) * p->gape_score;
+    if (nb <= 0 || nb > 1024) return fail(nullptr, BWB_ERR_UNSUPPORTED, "%d score buckets (supported: 1..1024)", nb);
+    std::vector<uint8_t> map;
+    const int nbc = bucket_map(p, nb, map);
+    for (int s = 0; bucket_of && s < cap && s < nb; s++) bucket_of[s] = map[(size_t)256 + s];
+    return nbc;
+}
+
 static int check_params(bwb_ctx *ctx, const bwb_params *p, int max_len, int &nb) {
     if (p->use_precalc) {
         if (ctx->engine != 0) return fail(ctx, BWB_ERR_UNSUPPORTED, "-P (pre-calculated intervals) is only built in the lane engine");
@@ -1106,10 +1149,14 @@ static int check_params(bwb_ctx *ctx, const bwb_params *p, int max_len, int &nb)
     nb = (p->max_diff + 1) * p->mm_score + (p->max_gapo + 1) * p->gapo_score + (p->max_gape + 1) * p->gape_score;
     if (nb <= 0 || nb > 1024) return fail(ctx, BWB_ERR_UNSUPPORTED, "%d score buckets (supported: 1..1024)", nb);
     // the engine limits, all in one place and before anything is launched (INTEGRATION.md "Limits of the device path")
-    if (ctx->engine == 0 && nb > 128)
-        return fail(ctx, BWB_ERR_UNSUPPORTED, "%d score buckets = (n+1)*M + (o+1)*O + (e+1)*E with -n %d -o %d -e %d -M %d -O %d -E %d; the device "
-                    "search keeps the occupancy of at most 128 buckets in registers (the reference allocates any number, inexact_match.c:510-528)",
-                    nb, p->max_diff, p->max_gapo, p->max_gape, p->mm_score, p->gapo_score, p->gape_score);
+    if (ctx->engine == 0) {
+        ctx->nbc = bucket_map(p, nb, ctx->bmap);
+        if (ctx->nbc > 128)
+            return fail(ctx, BWB_ERR_UNSUPPORTED, "%d distinct alignment scores m*M + o*O + e*E are reachable with -n %d -o %d -e %d -M %d -O %d -E %d; "
+                        "the device search keeps the occupancy of at most 128 score buckets in registers (the reference allocates "
+                        "(n+1)*M + (o+1)*O + (e+1)*E = %d of them, inexact_match.c:510-528)",
+                        ctx->nbc, p->max_diff, p->max_gapo, p->max_gape, p->mm_score, p->gapo_score, p->gape_score, nb);
+    }
     if (p->seed_length > 255) return fail(ctx, BWB_ERR_ARG, "seed_length > 255");
     int gaps = p->max_gapo + p->max_gape;
     if (gaps > p->max_diff) gaps = p->max_diff;
@@ -1242,6 +1289,9 @@ static int launch_shard(bwb_ctx *ctx, Device &d, const bwb_params *p, int nb, co
         g.mm_score = a.mm_score; g.gapo_score = a.gapo_score; g.gape_score = a.gape_score;
         g.seed_len = a.seed_len; g.max_diff_seed = a.max_diff_seed; g.max_best = a.max_best; g.no_indel_len = a.no_indel_len;
         g.nb = a.nb; g.queue = a.queue; g.is_multiref = p->is_multiref;
+        if ((rc = ensure(ctx, d.bmap, ctx->bmap.size()))) return rc;
+        CU(cudaMemcpyAsync(d.bmap.p, ctx->bmap.data(), ctx->bmap.size(), cudaMemcpyHostToDevice, d.stream));
+        g.nbc = ctx->nbc; g.bmap = (const uint8_t *)d.bmap.p;
         g.pk_main = c.pk_main; g.pk_seed = c.pk_seed; g.n_count = c.n_count;
         g.slots = (uint4 *)d.chunks.p;
         g.slots_per_lane = d.slots_per_lane; g.priv_total = d.priv_total;
@@ -1393,6 +1443,8 @@ static int align_impl(bwb_ctx *ctx, const bwb_params *p, const bwb_reads *R, bwb
             memcpy(&used, hs + 16, 8);
             if (st[0]) {
                 delete res;
+                if ((int)st[0] == -BWB_ERR_UNSUPPORTED)
+                    return fail(ctx, BWB_ERR_UNSUPPORTED, "internal: read %u produced an alignment score that has no bucket (bucket_map)", st[1]);
                 return fail(ctx, -(int)st[0], "device pool overflow while aligning read %u (heap_pool_mb=%lld [0=auto] list_cap=%d hits_per_read=%d)",
                             st[1], ctx->heap_pool_mb, ctx->list_cap, ctx->hits_per_read);
             }

@@ -19,6 +19,12 @@
 //     link in front of the bucket head, pop = unlink the head of the lowest non-empty bucket --
 //     exactly "last entry of the lowest non-empty bucket" (inexact_match.c:594-610).  Bucket
 //     heads live in shared memory ([bucket][lane], conflict-free), occupancy bits in registers.
+//     Only the scores an entry can really have get a bucket: score = m*M + o*O + e*E with
+//     m + o + e <= max_diff, o <= max_gapo, e <= max_gape and e > 0 only after an opening -- 19 of
+//     the 68 buckets at the default parameters.  The host enumerates them (bucket_map, bwb_abi.cu) in
+//     ascending score order, so "lowest non-empty bucket" is unchanged, the heads take 9.5 KB instead of
+//     34 KB of shared memory per block (the L1 gets the difference), and the limit of 128 applies to
+//     reachable scores, not to (n+1)*M + (o+1)*O + (e+1)*E.
 // Each loop iteration of a lane is: [take a read] -> [pop + prune + classify] -> [one interval
 // task: the 15-code rank loop, feeding either heap children or the next exact-tail list] ->
 // [flush].  No warp-synchronous intrinsic is needed anywhere: lanes are independent.
@@ -38,7 +44,10 @@ struct LaneArgs {
     uint32_t read_id_base;
     int max_diff, max_gapo, max_gape, max_entries, mm_score, gapo_score, gape_score;
     int seed_len, max_diff_seed, max_best, no_indel_len;
-    int nb;
+    int nb;                                  // score buckets of the reference's heap (scores 0 .. nb-1)
+    int nbc;                                 // buckets that can hold an entry with these parameters (<= 128), see bmap
+    const uint8_t *bmap;                     // uint16 score_of[128] (compact bucket -> score), then uint8 bucket_of[nb]
+                                             // (score -> compact bucket, 0xff = no entry can have this score)
     int is_multiref;                         // 0 = -S single-genome mode (codes A,G,C,T only)
     uint32_t *queue;
     const uint16_t *pk_main, *pk_seed;       // packed lower bounds from K3
@@ -190,7 +199,8 @@ __device__ __forceinline__ uint32_t slot_next(const uint4 *slots, uint32_t s) {
     return reinterpret_cast<const uint32_t *>(slots + 2 * (size_t)s + 1)[0];
 }
 
-// Bucket heap of one lane.  heads = shared memory, column of this lane ([bucket][lane]);
+// Bucket heap of one lane.  heads = shared memory, column of this lane ([bucket][lane]); buckets are
+// COMPACT indices (reachable scores in ascending order; LaneArgs::bmap translates both ways);
 // bm0..bm3 = occupancy bits of up to 128 buckets, so heads never need resetting between reads and
 // "next non-empty bucket" is a find-first-set.
 template <bool WIDE>
@@ -234,7 +244,7 @@ struct LaneHeap {
         return true;
     }
     __device__ __forceinline__ void mark(int b) { set_bit(b); }
-    // heap_pop (inexact_match.c:594-610); returns the bucket
+    // heap_pop (inexact_match.c:594-610); returns the (compact) bucket
     __device__ __forceinline__ int pop(const LaneArgs &a, PE<T> &e, uint32_t &s) {
         const int b = best();
         s = heads[b * 128];
@@ -426,7 +436,9 @@ __global__ void __launch_bounds__(128, BWB_LANE_MIN_BLOCKS(WIDE)) k_search_l(con
     __shared__ uint32_t sFree[RECYCLE ? FREE_RING : 1][128];
     __shared__ uint32_t sTe[5][128];              // z, w, r1, r2, r3 of the entry whose exact tail is in progress
                                                   // (touched when a tail starts / ends: kept out of the register file)
-    extern __shared__ uint32_t sm_heads[];        // [nb][128] bucket heads
+    extern __shared__ uint32_t sm_heads[];        // [nbc][128] bucket heads, then the two score <-> bucket tables
+    uint16_t *const score_of = reinterpret_cast<uint16_t *>(sm_heads + (size_t)a.nbc * 128);   // [128]
+    uint8_t *const bucket_of = reinterpret_cast<uint8_t *>(score_of + 128);                     // [nb]
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const uint32_t lane_slot = blockIdx.x * blockDim.x + tid;
     const T lastrow = (T)(a.ix.length - 1);
@@ -490,6 +502,8 @@ __global__ void __launch_bounds__(128, BWB_LANE_MIN_BLOCKS(WIDE)) k_search_l(con
 #endif
     uint32_t c_pops = 0, c_push = 0, c_tails = 0, c_rank = 0;         // per read, added to the launch counters at its flush
     uint32_t c_maxheap = 0, c_maxlist = 0;
+    score_of[tid] = reinterpret_cast<const uint16_t *>(a.bmap)[tid];
+    for (int b = (int)tid; b < a.nb; b += 128) bucket_of[b] = a.bmap[256 + b];
     __syncthreads();
 
 #define BWB_CODE_OF(t) (multiref ? (int)(t) : (int)((0x173Fu >> (4 * (t))) & 15u))
@@ -522,7 +536,7 @@ __global__ void __launch_bounds__(128, BWB_LANE_MIN_BLOCKS(WIDE)) k_search_l(con
             nfree = 0;
             n_hits = 0; hit_head = hit_tail = NIL; err = 0;
             best_score = a.nb; max_diff = a.max_diff; num_best = 0;
-            for (int b = 0; b < a.nb; b++) h.heads[b * 128] = NIL;
+            for (int b = 0; b < a.nbc; b++) h.heads[b * 128] = NIL;
             have_next = false;
             mode = FLUSH;
             if (PRE) {
@@ -655,7 +669,7 @@ __global__ void __launch_bounds__(128, BWB_LANE_MIN_BLOCKS(WIDE)) k_search_l(con
                 if (have_next) { e = nx; eb = nx_bucket; have_next = false; }
                 else {
                     uint32_t freed;
-                    eb = h.pop(a, e, freed);
+                    eb = (int)score_of[h.pop(a, e, freed)];
                     if (RECYCLE && nfree < (uint32_t)FREE_RING) sFree[nfree++][tid] = freed;   // nothing reads a slot after it is unlinked
                 }
                 c_pops++;
@@ -694,7 +708,7 @@ __global__ void __launch_bounds__(128, BWB_LANE_MIN_BLOCKS(WIDE)) k_search_l(con
                 const uint32_t sB = Ds[si > 1 ? si - 2 : 0];                // D_seed[si-2]
                 const uint32_t base_i1 = BWB_RSEQ[ei > 0 ? len - ei : 0];   // seq[len-1-(i-1)]
 #endif
-                if ((eb & 0xff) > best_score + a.mm_score) {
+                if (eb > best_score + a.mm_score) {
                     mode = FLUSH;                                       // inexact_match.c:309
                 } else if (dl < 0 || (ei > 0 && dl < (int)(dA & 0x1ff)) || (si > 0 && dls < (int)(sA & 0x1ff))) {
                     // pruned
@@ -846,22 +860,27 @@ __global__ void __launch_bounds__(128, BWB_LANE_MIN_BLOCKS(WIDE)) k_search_l(con
 #endif
                 const uint32_t n = (ins_live ? 1u : 0u) + (uint32_t)__popc(md) + (uint32_t)__popc(mmk);
                 if (n) {
+                    // the three score classes as compact buckets (equal scores <=> equal buckets)
+                    const uint32_t k0 = bucket_of[b0], k1 = bucket_of[b1 < a.nb ? b1 : a.nb - 1], k2 = bucket_of[b2 < a.nb ? b2 : a.nb - 1];
+                    const bool no_bucket = ((ins_live || md) && k2 == 0xffu) || ((mmk & ~compat_set) && k1 == 0xffu) ||
+                                           ((mmk & compat_set) && k0 == 0xffu);
                     // recycled slots first (top of the free stack), the rest contiguous from the bump allocator
                     const uint32_t f = RECYCLE ? (n < nfree ? n : nfree) : 0u;
                     ch_base = (n > f) ? lane_alloc_n(al, a, lane_slot, n - f) : 0u;
-                    if (ch_base == NIL) { err = BWB_ERR_CAPACITY; mode = FLUSH; }
+                    if (no_bucket) { err = BWB_ERR_UNSUPPORTED; mode = FLUSH; ch_base = NIL; }     // bucket_map() missed a score: a bug, reported
+                    else if (ch_base == NIL) { err = BWB_ERR_CAPACITY; mode = FLUSH; }
                     else {
                         ch_free = f | (nfree << 8);
                         nfree -= f;
                         // occupancy bits once per score class (of what is really pushed)
-                        if (ins_live || md) h.mark(b2);
-                        if (mmk & ~compat_set) h.mark(b1);
-                        if (mmk & compat_set) h.mark(b0);
+                        if (ins_live || md) h.mark((int)k2);
+                        if (mmk & ~compat_set) h.mark((int)k1);
+                        if (mmk & compat_set) h.mark((int)k0);
                         h.n += (int)n;
                         ch_n = n;
                         ch_masks = md | (mmk << 16);
                         ch_compat = (compat_set & 0xffffu) | (ins_live ? (1u << 16) : 0u);
-                        ch_bk = (uint32_t)b0 | ((uint32_t)b1 << 8) | ((uint32_t)b2 << 16) | ((uint32_t)len << 24);
+                        ch_bk = k0 | (k1 << 8) | (k2 << 16) | ((uint32_t)len << 24);
                     }
                 }
             }
@@ -984,7 +1003,7 @@ __global__ void __launch_bounds__(128, BWB_LANE_MIN_BLOCKS(WIDE)) k_search_l(con
                 // out of arena: with every lane busy on a big heap the shared pool can run dry.  The read is
                 // handed to the next pass, which runs only the deferred reads (so each finds far more room);
                 // the last pass reports the overflow.
-                if (a.retry_list) a.retry_list[atomicAdd(a.retry_count, 1u)] = r;
+                if (a.retry_list && err == BWB_ERR_CAPACITY) a.retry_list[atomicAdd(a.retry_count, 1u)] = r;
                 else if (atomicCAS(a.status, 0u, (uint32_t)(-err)) == 0u) a.status[1] = read_id;
                 n_hits = 0;
             }

@@ -32,7 +32,7 @@ typedef enum {
     BWB_ERR_IO = -3,           /* file could not be read / written */
     BWB_ERR_NO_INDEX = -4,     /* bwb_align before bwb_index_upload */
     BWB_ERR_CAPACITY = -5,     /* a device pool (heap chunks, interval lists, hits) overflowed */
-    BWB_ERR_UNSUPPORTED = -6   /* feature of the reference not built yet (-P; max_gapo > 4; > 128 score buckets) */
+    BWB_ERR_UNSUPPORTED = -6   /* parameter combination outside the device path (max_gapo > 4; > 128 reachable scores) */
 } bwb_status;
 
 /* Mirror of aln_params_t (mg-aligner/align.h:48-79): the same 15 ints in the same order, so a
@@ -57,6 +57,15 @@ typedef struct {
 
 /* set_default_aln_params, align.c:22-38 */
 void bwb_default_params(bwb_params *p);
+
+/* The score buckets the device search keeps for these parameters.  The reference's heap has
+ * nb = (n+1)*M + (o+1)*O + (e+1)*E buckets, one per score (heap_init, inexact_match.c:510-528); an
+ * entry can only score m*M + o*O + e*E with m + o + e <= max_diff, o <= max_gapo, e <= max_gape
+ * (e > 0 only after an opening), and only those scores get a bucket on the device, in ascending
+ * order.  Returns their number (bwb_align needs it <= 128) or a negative bwb_status; when
+ * bucket_of is not NULL, bucket_of[s] for s < min(cap, nb) is the bucket of score s or 0xff.
+ * Host only: needs no device. */
+int bwb_score_buckets(const bwb_params *p, uint8_t *bucket_of, int cap);
 
 /* One gap run of an alignment path.  A path (aln_entry_t.aln_path, align.h:118) is all STATE_M
  * except for at most num_gapo runs of STATE_I(1)/STATE_D(2); `start` is the index of the run's

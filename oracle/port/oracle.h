@@ -92,6 +92,8 @@ void orc_calculate_d(const orc_bwt *b, const uint8_t *read, int len, orc_dbound 
 int orc_align(const orc_bwt *b, const orc_params *p, const uint8_t *seq, const uint64_t *offsets,
               uint64_t n_reads, uint8_t **aln, uint64_t *aln_len, orc_stats *stats);
 void orc_free(void *p);
+/* test hook: bit sc of out[sc/64] = an entry with score sc was pushed since the last reset (scores < 1024) */
+void orc_score_mask(uint64_t out[16], int reset);
 
 #ifdef __cplusplus
 }

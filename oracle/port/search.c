@@ -162,6 +162,7 @@ static void heap_del(heap_t *h) {
     for (int i = 0; i < h->nb; i++) free(h->b[i].e);
     free(h->b); free(h);
 }
+static uint64_t g_score_mask[16];   /* bit sc: an entry of score sc was pushed (process-wide, test hook) */
 static void heap_clear(heap_t *h) {
     for (int i = 0; i < h->nb; i++) h->b[i].n = 0;
     h->best = h->nb; h->n = 0;
@@ -187,6 +188,14 @@ static void heap_push(heap_t *h, int i, uint64_t L, uint64_t U, int mm, int go, 
     if (h->best > sc) h->best = sc;
     orc_tls_stats.pushes++;
     if ((uint64_t)h->n > orc_tls_stats.max_heap) orc_tls_stats.max_heap = (uint64_t)h->n;
+    if (sc >= 0 && sc < 1024) __atomic_fetch_or(&g_score_mask[sc >> 6], 1ull << (sc & 63), __ATOMIC_RELAXED);
+}
+/* which scores were ever pushed since the last reset (tests: the device's bucket map must cover them) */
+void orc_score_mask(uint64_t out[16], int reset) {
+    for (int k = 0; k < 16; k++) {
+        out[k] = __atomic_load_n(&g_score_mask[k], __ATOMIC_RELAXED);
+        if (reset) __atomic_store_n(&g_score_mask[k], 0ull, __ATOMIC_RELAXED);
+    }
 }
 /* inexact_match.c:594-610: last entry of the lowest non-empty bucket */
 static void heap_pop(heap_t *h, entry_t *out) {

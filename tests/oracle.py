@@ -67,6 +67,7 @@ def lib():
         L.orc_align.argtypes = [C.POINTER(OrcBwt), C.POINTER(OrcParams), C.c_void_p, C.c_void_p, C.c_uint64,
                                 C.POINTER(C.c_void_p), C.POINTER(C.c_uint64), C.POINTER(OrcStats)]
         L.orc_free.argtypes = [C.c_void_p]
+        L.orc_score_mask.argtypes = [C.POINTER(C.c_uint64 * 16), C.c_int]
         L.orc_default_params.argtypes = [C.POINTER(OrcParams)]
         _lib = L
     return _lib
@@ -154,6 +155,13 @@ class Oracle:
         finally:
             lib().orc_free(buf)
         return data, {n: int(getattr(st, n)) for n, _ in OrcStats._fields_}
+
+
+def pushed_scores(reset: bool = True) -> set:
+    """scores of every heap entry the oracle pushed since the last reset (process-wide test hook)"""
+    m = (C.c_uint64 * 16)()
+    lib().orc_score_mask(C.byref(m), 1 if reset else 0)
+    return {64 * k + b for k in range(16) for b in range(64) if (int(m[k]) >> b) & 1}
 
 
 def have_reference_sources() -> bool:

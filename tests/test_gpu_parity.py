@@ -202,6 +202,7 @@ GRID = [
     dict(n=4, o=2, e=3, k=3, l=20), dict(n=3, M=2, O=5, E=2), dict(n=4, l=0), dict(n=3, k=1),
     dict(n=6, o=2, M=4, O=4, E=4), dict(n=3, o=0), dict(n=2, e=0), dict(n=4, m=200),
     dict(n=4, M=0, m=3000), dict(n=4, E=0, o=2), dict(n=3, M=11), dict(n=3, O=3, E=3),     # score classes sharing a bucket
+    dict(n=3, M=10, O=30, E=10), dict(n=4, o=2, e=4, M=7, O=23, E=9),    # 170 / 149 buckets in the reference's heap (> 128), 6 / 20 reachable
 ]
 
 

@@ -40,7 +40,8 @@ def test_product_index_builder_equals_reference_index(case, tmp_path):
 
 GRID = [dict(n=0), dict(n=2), dict(n=3), dict(n=5), dict(n=4, o=2, e=3, k=3, l=20), dict(n=3, M=2, O=5, E=2),
         dict(n=4, l=0), dict(n=3, t=3, k=1), dict(n=6, o=2, M=4, O=4, E=4), dict(n=2, is_multiref=0),
-        dict(n=4, M=0), dict(n=4, E=0, o=2), dict(n=3, m=150)]
+        dict(n=4, M=0), dict(n=4, E=0, o=2), dict(n=3, m=150),
+        dict(n=3, M=10, O=30, E=10), dict(n=4, o=2, e=4, M=7, O=23, E=9)]      # more than 128 buckets in heap_init
 
 
 @pytest.mark.parametrize("kw", GRID, ids=lambda k: "-".join("%s%d" % kv for kv in k.items()))
