@@ -324,6 +324,18 @@ int prepare_search_lane(bwb_ctx *ctx, Device &d, int nb, bool wide) {
         bps = b0 < b1 ? b0 : b1;
         if (bps <= 0) return fail(ctx, BWB_ERR_CUDA, "k_search_l does not fit on an SM");
     }
+    {   // shared-memory carve-out: exactly what the resident blocks need (+1 KB per block the driver reserves), so that
+        // what the compact bucket heads freed goes to the L1 (heap slots, lower-bound arrays and the second end of an
+        // interval are L1 traffic)
+        for (int v = 0; v < 4; v++) {
+            cudaFuncAttributes fa;
+            CU(cudaFuncGetAttributes(&fa, k4_fn(wide, v & 2, v & 1)));
+            const size_t need = (size_t)bps * (fa.sharedSizeBytes + smem + 1024);
+            int pct = (int)((need * 100 + 228 * 1024 - 1) / (228 * 1024));
+            if (pct > 100) pct = 100;
+            CU(cudaFuncSetAttribute(k4_fn(wide, v & 2, v & 1), cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+        }
+    }
     const int grid = bps * d.sm_count;
     const int n_lanes = grid * tpb;
     if (n_lanes != d.n_warps || d.engine != 0) {

@@ -337,9 +337,17 @@ __device__ __forceinline__ void low_bits128(int n, uint32_t &k0, uint32_t &k1, u
 // the codes with L_j <= U_j.  trueq = "true counts for codes 5,9,11,13" (exact tails use O(), bwt.c:348-372, and -S
 // never sees those codes; expansions in multi-genome mode use O_alphabet with quirk Q1, bwt.c:427-435,780).
 // C[] comes straight from the kernel's constant-bank parameters (compile-time index: no load instruction).
-template <class T>
+// the upper end's index block, when it was requested before the task was known to exist (HOIST)
+struct UpperBlock { Planes p; uint4 q0, q1, q2, q3; };
+__device__ __forceinline__ void load_upper(UpperBlock &b, const uint4 *__restrict__ blk) {
+    b.p = load_planes(blk);
+    b.q0 = __ldg(blk); b.q1 = __ldg(blk + 1); b.q2 = __ldg(blk + 2); b.q3 = __ldg(blk + 3);
+}
+
+template <class T, bool HOIST>
 __device__ __forceinline__ uint32_t rank_general(const IndexView &ix, T (*sLj)[128], T (*sUj)[128], uint32_t o,
-                                                 const T L, const T iU, const bool trueq, const T lastrow) {
+                                                 const T L, const T iU, const bool trueq, const T lastrow,
+                                                 const bool have_ub, const UpperBlock &ub) {
     const T iL = (T)(L - 1);
     const bool negL = (L == 0), topU = (iU == lastrow);
     const T aL = negL ? (T)0 : iL, aU = topU ? (T)0 : iU;
@@ -354,8 +362,10 @@ __device__ __forceinline__ uint32_t rank_general(const IndexView &ix, T (*sLj)[1
     // keeper child is chosen, made K4 17-22 % SLOWER on the 600 M-row index and 3-6 % slower on chr21 -- CCTL.PF1 is
     // not free and the L1 left beside 54 KB of shared memory per block is small; profiles/r02_ab_log.md)
     {
-        const Planes pu = load_planes(blkU);
-        const uint4 q0 = __ldg(blkU), q1 = __ldg(blkU + 1), q2 = __ldg(blkU + 2), q3 = __ldg(blkU + 3);
+        UpperBlock mine;
+        if (HOIST && have_ub) mine = ub; else load_upper(mine, blkU);
+        const Planes pu = mine.p;
+        const uint4 q0 = mine.q0, q1 = mine.q1, q2 = mine.q2, q3 = mine.q3;
         const uint32_t cU[16] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, q3.x, q3.y, q3.z, q3.w};
         uint32_t k0, k1, k2, k3;
         low_bits128((int)(aU & 127u) + 1, k0, k1, k2, k3);
@@ -412,15 +422,21 @@ __device__ __forceinline__ uint32_t rank_general(const IndexView &ix, T (*sLj)[1
 //   C  the result is consumed: next level of the exact tail (align.c:93-110), or the children of the
 //      expansion (inexact_match.c:433-504) -- described per lane, then written by the whole warp, one
 //      child per lane and pass; then [flush] of finished reads.
-// 3 blocks of 128 lanes per SM.  (A/B on B200, chr21, 2 M reads: 4 blocks at 128 registers -- 12 bytes of spills --
-// run 5 % slower, 0.94 against 0.99 M reads/s: 4 x 54 KB of shared memory leave the SM almost no L1.)
+// 32-bit coordinates: 4 blocks of 128 lanes per SM at 128 registers (20-32 bytes of spills); 64-bit: 3 blocks at 168.
+// (A/B on B200, chr21, 2 M reads per launch.  With 68 bucket heads per lane a block took 54 KB of shared memory, four
+// of them left the SM almost no L1 and ran 5 % slower than three, 0.94 against 0.99 M reads/s; with the compact heads
+// -- 30 KB per block -- four blocks are 2 % faster than three, and 4 % with the early request of the upper index
+// block: 0.98 / 1.00 / 1.02 M reads/s, profiles/r02_ab_log.md.)
 #ifndef BWB_FREE_RING
 #define BWB_FREE_RING 8
 #endif
 constexpr int FREE_RING = BWB_FREE_RING;   // free slot ids kept per lane
 static_assert(FREE_RING > 0 && FREE_RING < 256 && (FREE_RING & (FREE_RING - 1)) == 0, "FREE_RING: a power of two below 256");
 #ifndef BWB_LANE_BLOCKS_NARROW
-#define BWB_LANE_BLOCKS_NARROW 3
+#define BWB_LANE_BLOCKS_NARROW 4
+#endif
+#ifndef BWB_HOIST_NARROW
+#define BWB_HOIST_NARROW 1
 #endif
 #define BWB_LANE_MIN_BLOCKS(WIDE) ((WIDE) ? 3 : BWB_LANE_BLOCKS_NARROW)
 template <bool WIDE, bool PRE, bool RECYCLE>
@@ -580,6 +596,8 @@ __global__ void __launch_bounds__(128, BWB_LANE_MIN_BLOCKS(WIDE)) k_search_l(con
         // ================= A: exact tail -- level end, then the next interval of the level =================
         if (mode == TAIL) {
             if (cur_head == NIL) {                                      // level finished
+                // (A/B, round 2: handing a level of ONE interval to the next level in registers -- node neither written
+                // nor read back -- was 1 % SLOWER, 972 k against 982 k reads/s: profiles/r02_ab_log.md)
                 if (nx_n) slot_write<T>(a.slots, nx_tail, nx_tailL, nx_tailU, 0u, 0u, NIL, 0u, 0u, 0u);
                 if ((uint32_t)nx_n > c_maxlist) c_maxlist = (uint32_t)nx_n;
                 if (nx_n == 0) {
@@ -654,6 +672,11 @@ __global__ void __launch_bounds__(128, BWB_LANE_MIN_BLOCKS(WIDE)) k_search_l(con
         }
 
         // ================= A: pop + prune + classify (inexact_match.c:293-375) =================
+        // 32-bit coordinates only (A/B on B200: +2.5 % at 4 blocks/SM, nothing at 3; the 64-bit kernel has no registers to spare)
+        constexpr bool HOIST = !WIDE && BWB_HOIST_NARROW;
+        UpperBlock ub;
+        bool have_ub = false;
+        if (HOIST) ub.p.p0 = ub.p.p1 = ub.p.p2 = ub.p.p3 = ub.q0 = ub.q1 = ub.q2 = ub.q3 = make_uint4(0u, 0u, 0u, 0u);
         if (mode == SEARCH) {
             const int nvirt = h.n + ghost + (have_next ? 1 : 0);      // heap->num_entries of the reference
             if ((uint32_t)nvirt > c_maxheap) c_maxheap = (uint32_t)nvirt;
@@ -673,6 +696,13 @@ __global__ void __launch_bounds__(128, BWB_LANE_MIN_BLOCKS(WIDE)) k_search_l(con
                     if (RECYCLE && nfree < (uint32_t)FREE_RING) sFree[nfree++][tid] = freed;   // nothing reads a slot after it is unlinked
                 }
                 c_pops++;
+                if (HOIST) {
+                    // The popped entry's interval is the task of this iteration unless the entry is pruned or a hit: its
+                    // upper block is requested NOW, so that the round trip overlaps the one of the lower-bound arrays
+                    // below (heap slot -> bounds -> index block was three dependent latencies, now two).
+                    load_upper(ub, a.ix.blocks + (size_t)((e.U == lastrow ? (T)0 : e.U) >> 7) * 8);
+                    have_ub = true;
+                }
                 const uint32_t z = e.z;
                 const int ei = (int)(z & 0xffu);
                 const int go = (int)((z >> 24) & 15u), ge = (int)((z >> 16) & 0xffu);
@@ -785,7 +815,7 @@ __global__ void __launch_bounds__(128, BWB_LANE_MIN_BLOCKS(WIDE)) k_search_l(con
         // ================= B: rank stage =================
         __syncwarp();
         uint32_t okmask = 0;
-        if (have_task) okmask = rank_general<T>(a.ix, sLj, sUj, tid, e.L, e.U, task_tail || !multiref, lastrow);
+        if (have_task) okmask = rank_general<T, HOIST>(a.ix, sLj, sUj, tid, e.L, e.U, task_tail || !multiref, lastrow, have_ub, ub);
 
         // ================= C: consume the result =================
         // children of this warp's expansions are described here (owner registers) and written below, one child
