@@ -43,6 +43,8 @@ assert C.sizeof(Hit) == 48 and C.sizeof(Params) == 60
 SIGNATURES = {
     "bwb_default_params": (None, [C.POINTER(Params)]),
     "bwb_score_buckets": (C.c_int, [C.POINTER(Params), C.POINTER(C.c_uint8), C.c_int]),
+    "bwb_set_seed_carry": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
+    "bwb_seed_donor_plan": (C.c_int, [C.POINTER(Params), C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p]),
     "bwb_create": (C.c_void_p, [C.POINTER(C.c_int), C.c_int]),
     "bwb_destroy": (None, [C.c_void_p]),
     "bwb_last_error": (C.c_char_p, [C.c_void_p]),

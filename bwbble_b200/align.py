@@ -329,6 +329,15 @@ class Aligner:
                                         len(offsets) - 1, C.byref(h)), self._ctx)
         return AlignResult(self, h.value)
 
+    def set_seed_carry(self, read_seq=None):
+        """SURVEY Q6 across calls: the read (nt4 codes) whose D_seed short reads at the start of the next align() call
+        inherit (dist.seed_carry_read); None clears it.  Later calls keep the chain going by themselves."""
+        if read_seq is None or len(read_seq) == 0:
+            _lib.check(_lib.lib().bwb_set_seed_carry(self._ctx, None, 0), self._ctx)
+        else:
+            rs = _u8(read_seq)
+            _lib.check(_lib.lib().bwb_set_seed_carry(self._ctx, rs.ctypes.data, len(rs)), self._ctx)
+
     def align_fastq(self, fastq_path: str, aln_path: Optional[str], params: Optional[Params] = None, batch: int = 0,
                     sam_path: Optional[str] = None, ann_path: Optional[str] = None, max_mm: int = 6) -> int:
         """bwb_align_fastq on this context (index already loaded): FASTQ file -> .aln / SAM file, streamed."""

@@ -35,6 +35,16 @@ def parse_aln(buf: bytes) -> List[List[AlnHit]]:
     return out
 
 
+def record_end(buf: bytes, p: int = 0) -> int:
+    """offset just past the record (one read: count + hits) that starts at p"""
+    (n,) = struct.unpack_from("<i", buf, p)
+    p += 4
+    for _ in range(n):
+        (npairs,) = struct.unpack_from("<i", buf, p + 36)
+        p += 40 + 4 * npairs
+    return p
+
+
 def first_difference(a: bytes, b: bytes):
     """(read index, hits_a, hits_b) of the first read whose records differ, or None."""
     pa, pb = parse_aln(a), parse_aln(b)

@@ -53,10 +53,11 @@ struct Device {
     uint32_t chunks_per_warp = 0, n_chunks = 0;
     // per-call buffers
     DevBuf seq, offsets, read_off, read_cnt, ordered_off, unordered, ordered, cub_tmp, small, d_main, d_seed, pool;
-    DevBuf pk_main, pk_seed, n_count, nxt, blk_link, heads, order, retry, bmap;      // lane engine
+    DevBuf pk_main, pk_seed, n_count, nxt, blk_link, heads, order, retry, bmap, seed_src, seed_ext;      // lane engine
     DevBuf loc;                                                  // K6 output
     uint32_t slots_per_lane = 0, total_slots = 0, priv_total = 0;
     uint64_t auto_pool_bytes = 0;
+    bool use_seed_src = false;       // this call: K3 takes the D_seed of short reads from donor reads (seed_donors)
     int engine = -1;          // engine the scratch was sized for
     // pinned staging for small D2H
     unsigned long long *h_small = nullptr;
@@ -102,6 +103,11 @@ struct bwb_ctx {
     // K4's score <-> bucket tables for the parameters of the current call (bucket_map)
     int nbc = 0;
     std::vector<uint8_t> bmap;
+    // SURVEY Q6 across calls (serial driver): the last read longer than the seed that the previous calls of a run saw;
+    // short reads at the start of the next call inherit ITS D_seed (option "seed_carry", bwb_set_seed_carry)
+    int seed_carry = 0;
+    int carry_len = 0;
+    uint8_t carry_seq[256] = {0};
 };
 
 struct bwb_reads {
@@ -111,6 +117,10 @@ struct bwb_reads {
     std::vector<uint64_t> shard_lo;      // per device, n_dev+1 entries
     std::vector<void *> d_seq, d_off;    // per device
     std::vector<uint64_t> shard_bases;   // per device
+    // Q6 bookkeeping (seed_donors): only kept when the reads differ in length
+    int min_len = 0;
+    std::vector<uint8_t> len8;           // length of every read
+    std::vector<uint8_t> skip_pre;       // 1 = -P skips the read: an N among its first 12 bases, or shorter than that
 };
 
 struct bwb_results {
@@ -197,15 +207,18 @@ IndexView make_view(const bwb_ctx *ctx, const Device &d) {
     return v;
 }
 
-int check_reads(bwb_ctx *ctx, const uint64_t *offsets, uint64_t n_reads, int &max_len) {
+int check_reads(bwb_ctx *ctx, const uint64_t *offsets, uint64_t n_reads, int &max_len, int *min_len = nullptr) {
     max_len = 0;
+    int mn = n_reads ? 256 : 0;
     if (n_reads >= 0xffffffffull) return fail(ctx, BWB_ERR_ARG, "too many reads in one call");
     for (uint64_t r = 0; r < n_reads; r++) {
         if (offsets[r + 1] < offsets[r]) return fail(ctx, BWB_ERR_ARG, "offsets not monotone at read %llu", (unsigned long long)r);
         uint64_t l = offsets[r + 1] - offsets[r];
         if (l > 255) return fail(ctx, BWB_ERR_ARG, "read %llu is %llu bases; positions are 8-bit (align.h:104)", (unsigned long long)r, (unsigned long long)l);
         if ((int)l > max_len) max_len = (int)l;
+        if ((int)l < mn) mn = (int)l;
     }
+    if (min_len) *min_len = mn;
     // K4 addresses a read's bases and lower bounds with 32-bit offsets
     if (offsets[n_reads] - offsets[0] + n_reads >= 0xffffffffull)
         return fail(ctx, BWB_ERR_ARG, "more than 2^32 bases in one call: split the batch");
@@ -642,7 +655,7 @@ void bwb_destroy(bwb_ctx *ctx) {
         if (d.pre_cnt) cudaFree(d.pre_cnt);
         if (d.pre_iv) cudaFree(d.pre_iv);
         DevBuf *bufs[] = {&d.glists, &d.chunks, &d.chunk_link, &d.stage, &d.seq, &d.offsets, &d.read_off, &d.read_cnt,
-                          &d.ordered_off, &d.unordered, &d.ordered, &d.cub_tmp, &d.small, &d.d_main, &d.d_seed, &d.pool, &d.loc, &d.pk_main, &d.pk_seed, &d.n_count, &d.nxt, &d.blk_link, &d.heads, &d.order, &d.retry, &d.bmap};
+                          &d.ordered_off, &d.unordered, &d.ordered, &d.cub_tmp, &d.small, &d.d_main, &d.d_seed, &d.pool, &d.loc, &d.pk_main, &d.pk_seed, &d.n_count, &d.nxt, &d.blk_link, &d.heads, &d.order, &d.retry, &d.bmap, &d.seed_src, &d.seed_ext};
         for (DevBuf *b : bufs) release(*b);
         if (d.h_small) cudaFreeHost(d.h_small);
         if (d.ev0) cudaEventDestroy(d.ev0);
@@ -658,7 +671,7 @@ int bwb_device_count(const bwb_ctx *ctx) { return ctx ? (int)ctx->dev.size() : 0
 int bwb_set_option(bwb_ctx *ctx, const char *key, long long value) {
     if (!ctx || !key) return BWB_ERR_ARG;
     std::string k(key);
-    if (value <= 0 && k != "blocks_per_sm" && k != "force_wide" && k != "engine" && k != "heap_pool_mb" && k != "kmer_table" && k != "heavy_first" && k != "hit_cap0" && k != "index_wide" && k != "index_chunk" && k != "arena_private_pct" && k != "recycle" && k != "throttle_pct") return fail(ctx, BWB_ERR_ARG, "option %s needs a positive value", key);
+    if (value <= 0 && k != "blocks_per_sm" && k != "force_wide" && k != "engine" && k != "heap_pool_mb" && k != "kmer_table" && k != "heavy_first" && k != "hit_cap0" && k != "index_wide" && k != "index_chunk" && k != "arena_private_pct" && k != "recycle" && k != "throttle_pct" && k != "seed_carry") return fail(ctx, BWB_ERR_ARG, "option %s needs a positive value", key);
     if (k == "heap_pool_mb") ctx->heap_pool_mb = value;
     else if (k == "list_cap") ctx->list_cap = (int)(value < SL + 4 ? SL + 4 : value);
     else if (k == "hits_per_read") ctx->hits_per_read = (int)value;
@@ -677,6 +690,7 @@ int bwb_set_option(bwb_ctx *ctx, const char *key, long long value) {
     else if (k == "hit_cap0") ctx->hit_cap0 = value;
     else if (k == "arena_private_pct") ctx->arena_private_pct = (int)value;
     else if (k == "throttle_pct") { ctx->throttle_pct = (int)value; ctx->throttle_forced = 1; return BWB_OK; }
+    else if (k == "seed_carry") { ctx->seed_carry = value == 1 ? 1 : 0; ctx->carry_len = 0; return BWB_OK; }     // (re)starts a run
     else if (k == "recycle") { ctx->recycle = (value == 1 || value == 2) ? (int)value : 0; return BWB_OK; }
     else if (k == "index_wide") { ctx->index_wide = value == 1 ? 1 : 0; return BWB_OK; }
     else if (k == "index_chunk") { ctx->index_chunk = value > 0 ? value : 0; return BWB_OK; }
@@ -1071,10 +1085,21 @@ int bwb_lower_bounds(bwb_ctx *ctx, const uint8_t *seq, const uint64_t *offsets, 
 // ---- K4 + K5 ----------------------------------------------------------------------------------
 int bwb_reads_upload(bwb_ctx *ctx, const uint8_t *seq, const uint64_t *offsets, uint64_t n_reads, bwb_reads **out) {
     if (!ctx || !seq || !offsets || !out) return BWB_ERR_ARG;
-    int max_len, rc;
-    if ((rc = check_reads(ctx, offsets, n_reads, max_len))) return rc;
+    int max_len, min_len, rc;
+    if ((rc = check_reads(ctx, offsets, n_reads, max_len, &min_len))) return rc;
     bwb_reads *R = new bwb_reads();
-    R->ctx = ctx; R->n_reads = n_reads; R->max_len = max_len;
+    R->ctx = ctx; R->n_reads = n_reads; R->max_len = max_len; R->min_len = min_len;
+    if (min_len != max_len) {            // mixed lengths: what seed_donors() needs to know about every read
+        R->len8.resize(n_reads);
+        R->skip_pre.resize(n_reads);
+        for (uint64_t r = 0; r < n_reads; r++) {
+            const uint64_t o = offsets[r], l = offsets[r + 1] - o;
+            R->len8[r] = (uint8_t)l;
+            uint8_t bad = l < (uint64_t)PRECALC_LEN;
+            for (uint64_t k = 0; k < (uint64_t)PRECALC_LEN && !bad; k++) bad = seq[o + k] > 3;
+            R->skip_pre[r] = bad;
+        }
+    }
     const int G = (int)ctx->dev.size();
     R->shard_lo.resize(G + 1);
     for (int g = 0; g <= G; g++) R->shard_lo[g] = (uint64_t)g * n_reads / G;
@@ -1176,6 +1201,153 @@ static int check_params(bwb_ctx *ctx, const bwb_params *p, int max_len, int &nb)
     return BWB_OK;
 }
 
+constexpr uint64_t READ_BATCH_REF = 0x40000;      // READ_BATCH_SIZE, align.h:14
+
+// first `want` bases of read r of a resident batch -> host (Q6: donor reads that live on another device, the carry)
+static int fetch_read_prefix(bwb_ctx *ctx, const bwb_reads *R, uint64_t r, int want, uint8_t *out, int *got) {
+    const int G = (int)ctx->dev.size();
+    int g = 0;
+    while (g + 1 < G && r >= R->shard_lo[g + 1]) g++;
+    uint64_t off = 0;
+    int len = R->max_len;
+    if (!R->len8.empty()) {
+        for (uint64_t q = R->shard_lo[g]; q < r; q++) off += R->len8[q];
+        len = R->len8[r];
+    } else {
+        off = (r - R->shard_lo[g]) * (uint64_t)R->max_len;
+    }
+    const int n = len < want ? len : want;
+    Device &d = ctx->dev[g];
+    CU(cudaSetDevice(d.id));
+    CU(cudaMemcpyAsync(out, (const uint8_t *)R->d_seq[g] + off, (size_t)n, cudaMemcpyDeviceToHost, d.stream));
+    CU(cudaStreamSynchronize(d.stream));
+    *got = n;
+    return BWB_OK;
+}
+
+// SURVEY Q6.  The reference computes D_seed only for reads longer than the seed (inexact_match.c:62-64,141-143); a
+// shorter read consults whatever the array holds: the bounds of the last longer read its driver thread aligned before
+// it, or the calloc'ed zeros.  "Before it" = in the whole run for the serial driver (one array per
+// align_reads_inexact call, :36), inside the thread's static chunk of the 262144-read batch for the OpenMP driver
+// (:115-121); with -P a read skipped for an N in its 12-mer leaves the array alone (:50-57).  One bwb_align call is one
+// driver call: params->n_threads picks the driver, and with option "seed_carry" the serial chain continues across calls
+// (streaming entry points).  The donor of every short read goes to K3 as an offset into the shard's bases
+// (CalcArgs::seed_src); the one donor per shard that can lie outside it travels as its first seed_length bases.
+// donor[r] for every read of one driver call: r itself (the read is longer than the seed), DONOR_NONE (zeros),
+// DONOR_CARRY (the run's carry) or the index of an earlier read of the call.  len8 / skip may be null (all reads
+// `uniform_len` long / no read skipped by -P).  Pure host arithmetic: bwb_seed_donor_plan exposes it to the CPU tests.
+constexpr long long DONOR_NONE = -1, DONOR_CARRY = -2;
+static void plan_seed_donors(const uint8_t *len8, int uniform_len, const uint8_t *skip, uint64_t n, int sl, int n_threads,
+                             bool use_precalc, bool carry, long long *donor_of) {
+    const bool serial = n_threads <= 1;
+    const uint64_t nt = serial ? 1 : (uint64_t)n_threads;
+    long long donor = (serial && carry) ? DONOR_CARRY : DONOR_NONE;
+    for (uint64_t r = 0; r < n; r++) {
+        if (!serial) {                            // a new thread chunk starts with a fresh (zero) array
+            const uint64_t w0 = r / READ_BATCH_REF * READ_BATCH_REF, bs = std::min<uint64_t>(READ_BATCH_REF, n - w0), q = r - w0;
+            const uint64_t t = ((q + 1) * nt - 1) / bs;                        // the chunk q falls in: [t*bs/nt, (t+1)*bs/nt)
+            if (t * bs / nt == q) donor = DONOR_NONE;
+        }
+        const int len = len8 ? (int)len8[r] : uniform_len;
+        const bool skipped = use_precalc && (skip ? skip[r] != 0 : len < PRECALC_LEN);
+        if (skipped) { donor_of[r] = DONOR_NONE; continue; }                   // never searched: no array consulted
+        if (len > sl) donor = (long long)r;
+        donor_of[r] = donor;
+    }
+}
+
+static int seed_donors(bwb_ctx *ctx, const bwb_params *p, const bwb_reads *R) {
+    const int G = (int)ctx->dev.size();
+    for (int g = 0; g < G; g++) ctx->dev[g].use_seed_src = false;
+    const int sl = p->seed_length;
+    if (sl <= 0 || R->n_reads == 0 || R->min_len > sl) return BWB_OK;         // every read has its own D_seed
+    const bool carry = p->n_threads <= 1 && ctx->seed_carry && ctx->carry_len > sl;
+    if (R->len8.empty() && !carry) return BWB_OK;                              // all reads short and equally long: zeros
+    std::vector<long long> donor_of(R->n_reads);
+    plan_seed_donors(R->len8.empty() ? nullptr : R->len8.data(), R->max_len, R->skip_pre.empty() ? nullptr : R->skip_pre.data(),
+                     R->n_reads, sl, p->n_threads, p->use_precalc != 0, carry, donor_of.data());
+    int rc;
+    for (int g = 0; g < G; g++) {
+        Device &d = ctx->dev[g];
+        const uint64_t lo = R->shard_lo[g], hi = R->shard_lo[g + 1];
+        std::vector<uint32_t> src(hi - lo, SEED_SRC_NONE), first_base(hi - lo);
+        long long ext = DONOR_NONE;               // the one donor outside this shard, if it is used
+        bool any = false;
+        uint64_t off = 0;
+        for (uint64_t r = lo; r < hi; r++) {
+            first_base[r - lo] = (uint32_t)off;
+            const int len = R->len8.empty() ? R->max_len : (int)R->len8[r];
+            const long long dn = donor_of[r];
+            if (len <= sl && dn != DONOR_NONE) {
+                any = true;
+                if (dn >= (long long)lo) src[r - lo] = first_base[(uint64_t)dn - lo];
+                else {
+                    if (ext != DONOR_NONE && ext != dn) return fail(ctx, BWB_ERR_ARG, "internal: two outside D_seed donors for one shard");
+                    src[r - lo] = SEED_SRC_EXT;
+                    ext = dn;
+                }
+            }
+            off += (uint64_t)len;
+        }
+        if (!any) continue;
+        CU(cudaSetDevice(d.id));
+        if ((rc = ensure(ctx, d.seed_src, src.size() * 4))) return rc;
+        if ((rc = ensure(ctx, d.seed_ext, 256))) return rc;
+        uint8_t ext_seq[256] = {0};
+        if (ext == DONOR_CARRY) memcpy(ext_seq, ctx->carry_seq, 256);
+        else if (ext >= 0) {
+            int got = 0;
+            if ((rc = fetch_read_prefix(ctx, R, (uint64_t)ext, sl, ext_seq, &got))) return rc;
+            CU(cudaSetDevice(d.id));
+        }
+        CU(cudaMemcpyAsync(d.seed_src.p, src.data(), src.size() * 4, cudaMemcpyHostToDevice, d.stream));
+        CU(cudaMemcpyAsync(d.seed_ext.p, ext_seq, 256, cudaMemcpyHostToDevice, d.stream));
+        CU(cudaStreamSynchronize(d.stream));           // src / ext_seq are locals
+        d.use_seed_src = true;
+    }
+    return BWB_OK;
+}
+
+extern "C" int bwb_seed_donor_plan(const bwb_params *p, const uint8_t *seq, const uint64_t *offsets, uint64_t n_reads,
+                                   int have_carry, int64_t *donor_of) {
+    if (!p || !seq || !offsets || !donor_of) return fail(nullptr, BWB_ERR_ARG, "bwb_seed_donor_plan: null argument");
+    std::vector<uint8_t> len8(n_reads), skip(n_reads);
+    for (uint64_t r = 0; r < n_reads; r++) {
+        const uint64_t o = offsets[r], l = offsets[r + 1] - o;
+        if (offsets[r + 1] < o || l > 255) return fail(nullptr, BWB_ERR_ARG, "read %llu: bad offsets or longer than 255 bases", (unsigned long long)r);
+        len8[r] = (uint8_t)l;
+        uint8_t bad = l < (uint64_t)PRECALC_LEN;
+        for (uint64_t k = 0; k < (uint64_t)PRECALC_LEN && !bad; k++) bad = seq[o + k] > 3;
+        skip[r] = bad;
+    }
+    std::vector<long long> d(n_reads);
+    plan_seed_donors(len8.data(), 0, skip.data(), n_reads, p->seed_length, p->n_threads, p->use_precalc != 0, have_carry != 0, d.data());
+    for (uint64_t r = 0; r < n_reads; r++) donor_of[r] = (int64_t)d[r];
+    return BWB_OK;
+}
+
+// after a call of a run with "seed_carry": remember the last read longer than the seed (serial driver only)
+static int seed_carry_update(bwb_ctx *ctx, const bwb_params *p, const bwb_reads *R) {
+    if (!ctx->seed_carry || p->n_threads > 1 || p->seed_length <= 0 || R->n_reads == 0 || R->max_len <= p->seed_length) return BWB_OK;
+    for (uint64_t r = R->n_reads; r-- > 0;) {
+        const int len = R->len8.empty() ? R->max_len : (int)R->len8[r];
+        if (len <= p->seed_length) continue;
+        if (p->use_precalc && !R->skip_pre.empty() && R->skip_pre[r]) continue;      // -P skipped it: D_seed untouched
+        uint8_t tmp[256] = {0};
+        int got = 0, rc;
+        if ((rc = fetch_read_prefix(ctx, R, r, 255, tmp, &got))) return rc;
+        if (p->use_precalc && R->skip_pre.empty()) {       // equally long reads: the skip condition was not recorded at upload
+            bool bad = got < PRECALC_LEN;
+            for (int k = 0; k < PRECALC_LEN && !bad; k++) bad = tmp[k] > 3;
+            if (bad) continue;
+        }
+        memcpy(ctx->carry_seq, tmp, sizeof tmp);
+        ctx->carry_len = len;
+        return BWB_OK;
+    }
+    return BWB_OK;
+}
+
 // enqueue K4 + scan + K5 for one shard on its device stream
 static int launch_shard(bwb_ctx *ctx, Device &d, const bwb_params *p, int nb, const SmemLayout &L, int max_len, bool wide,
                         const void *d_seq, const void *d_off, uint64_t n, uint64_t total_bases, uint64_t read_base, unsigned long long out_cap) {
@@ -1265,7 +1437,8 @@ static int launch_shard(bwb_ctx *ctx, Device &d, const bwb_params *p, int nb, co
         c.glists = d.glists.p; c.list_cap = ctx->list_cap;
         c.pk_main = (uint16_t *)d.pk_main.p; c.pk_seed = (uint16_t *)d.pk_seed.p; c.n_count = (uint16_t *)d.n_count.p;
         c.status = a.status; c.counters = a.counters;
-        c.smem_per_group = G_LIST_SMEM + ((max_len + 15) & ~15);
+        c.smem_per_group = G_LIST_SMEM + ((std::max(max_len, p->seed_length) + 15) & ~15);     // (a donor's seed is staged there too)
+        if (d.use_seed_src) { c.seed_src = (const uint32_t *)d.seed_src.p; c.seed_ext = (const uint8_t *)d.seed_ext.p; }
         set_ktab(ctx, d, c);
         const size_t smem3 = (size_t)(256 / GL) * c.smem_per_group;
         const int grid3 = d.grid3;
@@ -1419,6 +1592,7 @@ static int align_impl(bwb_ctx *ctx, const bwb_params *p, const bwb_reads *R, bwb
     res->have_loc = ctx->have_sa;
     res->generation = ++ctx->launch_generation;
 
+    if ((rc = seed_donors(ctx, p, R))) { delete res; return rc; }
     std::vector<unsigned long long> cap(G);
     for (int g = 0; g < G; g++) {
 #ifdef BWB_AB_ENGINES
@@ -1483,7 +1657,17 @@ static int align_impl(bwb_ctx *ctx, const bwb_params *p, const bwb_reads *R, bwb
     }
     for (int g = 0; g < G; g++)
         if (!done[g]) { delete res; return fail(ctx, BWB_ERR_CAPACITY, "hit output did not fit after retries"); }
+    if ((rc = seed_carry_update(ctx, p, R))) { delete res; return rc; }
     *out = res;
+    return BWB_OK;
+}
+
+int bwb_set_seed_carry(bwb_ctx *ctx, const uint8_t *read_seq, int len) {
+    if (!ctx || len < 0 || len > 255 || (len && !read_seq)) return fail(ctx, BWB_ERR_ARG, "bwb_set_seed_carry: a read of 0..255 bases");
+    ctx->carry_len = len;
+    memset(ctx->carry_seq, 0, sizeof ctx->carry_seq);
+    if (len) memcpy(ctx->carry_seq, read_seq, (size_t)len);
+    ctx->seed_carry = 1;
     return BWB_OK;
 }
 

@@ -157,7 +157,7 @@ struct CalcArgs {
     void *glists;            // [n_groups][2][list_cap] pairs (allocated 16 B each)
     int list_cap;
     int2 *d_main;            // per read (len+1) entries at offsets[r] + r
-    int2 *d_seed;            // per read (seed_len+1) entries at r*(seed_len+1); zeros if len <= seed_len (Q6)
+    int2 *d_seed;            // per read (seed_len+1) entries at r*(seed_len+1); reads with len <= seed_len: see seed_src
     uint16_t *pk_main, *pk_seed;   // same arrays packed for K4: num_diff | (width == previous width) << 15
     uint16_t *n_count;             // number of N bases per read (inexact_match.c:259-263)
     uint32_t *status;
@@ -167,7 +167,15 @@ struct CalcArgs {
     const unsigned long long *ktab_w;
     const uint32_t *ktab_off, *ktab_cnt;
     const void *ktab_iv;
+    // a read with len <= seed_len gets no D_seed of its own in the reference -- it consults the array the
+    // previous longer read of its thread left behind (inexact_match.c:36,62-64,121,141-143).  The host works out which
+    // read that is (seed_donors, bwb_abi.cu): seed_src[r] = offset in `seq` of that read's first base, SEED_SRC_EXT =
+    // the donor is not in this shard (its first seed_len bases are in seed_ext), SEED_SRC_NONE = none (the calloc'ed
+    // array: zeros).  Only looked at for reads with len <= seed_len; null = no such read has a donor.
+    const uint32_t *seed_src;
+    const uint8_t *seed_ext;
 };
+constexpr uint32_t SEED_SRC_NONE = 0xffffffffu, SEED_SRC_EXT = 0xfffffffeu;
 
 template <bool WIDE>
 __global__ void __launch_bounds__(256) k_calc_d_g(const __grid_constant__ CalcArgs a) {
@@ -351,13 +359,25 @@ __global__ void __launch_bounds__(256) k_calc_d_g(const __grid_constant__ CalcAr
                     i = dlen - 1; z = 0; st.cur = 0; st.n_cur = 1; fresh = true; prev_w = 0;
                     if (gl == 0) glset<T>(ls, 0, 0, (T)0, fullU);
                 } else {
-                    // Q6: the reference consults a stale per-thread D_seed for such reads; the defined
-                    // behaviour here is the freshly calloc'ed array (all zero)
-                    for (int k = gl; k <= a.seed_len; k += GL) {
-                        if (Ds) Ds[k] = make_int2(0, 0);
-                        if (PKs) PKs[k] = (uint16_t)(k ? 0x8000 : 0);
+                    // Q6: the array of the donor read (computed here from the donor's first seed_len bases, which
+                    // replace the finished read in the group's staging buffer), or the calloc'ed zeros
+                    const uint32_t src = a.seed_src ? a.seed_src[r] : SEED_SRC_NONE;
+                    if (src != SEED_SRC_NONE) {
+                        const uint8_t *g = src == SEED_SRC_EXT ? a.seed_ext : a.seq + src;
+                        for (int k = gl; k < a.seed_len; k += GL) {
+                            uint8_t cc = g[k];
+                            sseq[k] = cc > 4 ? (uint8_t)4 : cc;
+                        }
+                        phase = 1; dlen = a.seed_len; D = Ds; PK = PKs;
+                        i = dlen - 1; z = 0; st.cur = 0; st.n_cur = 1; fresh = true; prev_w = 0;
+                        if (gl == 0) glset<T>(ls, 0, 0, (T)0, fullU);
+                    } else {
+                        for (int k = gl; k <= a.seed_len; k += GL) {
+                            if (Ds) Ds[k] = make_int2(0, 0);
+                            if (PKs) PKs[k] = (uint16_t)(k ? 0x8000 : 0);
+                        }
+                        mode = NEED;
                     }
-                    mode = NEED;
                 }
             } else {
                 mode = NEED;

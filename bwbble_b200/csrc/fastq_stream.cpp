@@ -166,6 +166,11 @@ extern "C" long long bwb_align_fastq(bwb_ctx *ctx, const bwb_params *params, con
     if (!ctx || !params || !fastq_path || (!aln_path && !sam_path)) return BWB_ERR_ARG;
     if (sam_path && !ann_path) return BWB_ERR_ARG;
     if (batch_reads == 0) batch_reads = 1ull << 23;     // every launch ends in a ~0.35 s tail: amortise it
+    // SURVEY Q6 (which stale D_seed a read no longer than the seed consults, see bwb_align): the serial driver's chain
+    // runs through the whole file, so it is carried from launch to launch; the OpenMP driver restarts it per thread
+    // chunk of every 262144-read batch of the FILE, so launches must hold whole batches
+    if (params->n_threads > 1) batch_reads = (batch_reads + 0x3ffff) / 0x40000 * 0x40000;
+    bwb_set_option(ctx, "seed_carry", params->n_threads > 1 ? 0 : 1);
     FILE *f = fopen(fastq_path, "rb");
     if (!f) return BWB_ERR_IO;
     if (aln_path) remove(aln_path);                 // align.c:48
@@ -283,5 +288,6 @@ extern "C" long long bwb_align_fastq(bwb_ctx *ctx, const bwb_params *params, con
         if (aln_path) rename(aln_path, (std::string(aln_path) + ".partial").c_str());
         if (sam_path) rename(sam_path, (std::string(sam_path) + ".partial").c_str());
     }
+    bwb_set_option(ctx, "seed_carry", 0);
     return rc == BWB_OK ? total : (long long)rc;
 }

@@ -130,6 +130,10 @@ static int run(shim_bwt_t *BWT, shim_reads_t *reads, const shim_sa_intv_list_t *
         upload_precalc(ctx, precalc, params);
     }
 
+    /* a read no longer than the seed consults the D_seed of the last longer read before it.  The serial
+     * driver's chain runs through all reads (inexact_match.c:36), so it is carried across the launches below; the OpenMP
+     * driver's restarts per thread chunk of every 262144-read batch (:115-121) -- SHIM_READ_BATCH is a multiple. */
+    bwb_set_option(ctx, "seed_carry", params->n_threads > 1 ? 0 : 1);
     uint8_t *seq = NULL;
     uint64_t *off = NULL;
     size_t seq_cap = 0;
@@ -172,8 +176,10 @@ static int run(shim_bwt_t *BWT, shim_reads_t *reads, const shim_sa_intv_list_t *
 }
 
 int align_reads_inexact(void *BWT, void *reads, void *precalc_sa_intervals_table, void *params, char *alnFname) {
+    bwb_params p = *(const bwb_params *)params;
+    p.n_threads = 1;                         /* this entry point IS the serial driver, whatever -t says */
     return run((shim_bwt_t *)BWT, (shim_reads_t *)reads, (const shim_sa_intv_list_t *)precalc_sa_intervals_table,
-               (bwb_params *)params, alnFname, "BWBBLE Inexact Alignment...\n");
+               &p, alnFname, "BWBBLE Inexact Alignment...\n");
 }
 
 int align_reads_inexact_parallel(void *BWT, void *reads, void *precalc_sa_intervals_table, void *params, char *alnFname) {

@@ -40,9 +40,30 @@ def gather_bytes(blob: bytes, dst: int = 0, device: Optional[str] = None) -> Opt
     return [bytes(out[r][: int(sizes[r])].cpu().numpy().tobytes()) for r in range(world)]
 
 
-def align_sharded(align_fn, seq: np.ndarray, offsets: np.ndarray, dst: int = 0) -> Optional[bytes]:
+def seed_carry_read(seq: np.ndarray, offsets: np.ndarray, lo: int, seed_length: int,
+                    use_precalc: bool = False) -> Optional[np.ndarray]:
+    """The read whose D_seed the short reads at the start of shard [lo, ...) consult under the reference's SERIAL
+    driver (inexact_match.c:36,62-64): the last read before `lo` that is longer than the seed -- and, with
+    -P, was not skipped for an N among its first 12 bases (:50-57).  None if there is none.  Pass it to
+    Aligner.set_seed_carry() before aligning the shard; the OpenMP driver (-t > 1) has no chain across 262144-read
+    batches, so shards cut at multiples of that need nothing."""
+    if seed_length <= 0 or lo <= 0:
+        return None
+    lens = np.diff(np.asarray(offsets[:lo + 1]).astype(np.int64))
+    for r in np.nonzero(lens > seed_length)[0][::-1]:
+        o = int(offsets[r])
+        if use_precalc and (lens[r] < 12 or (np.asarray(seq[o:o + 12]) > 3).any()):
+            continue
+        return np.ascontiguousarray(seq[o:o + int(lens[r])], dtype=np.uint8)
+    return None
+
+
+def align_sharded(align_fn, seq: np.ndarray, offsets: np.ndarray, dst: int = 0, seed_length: int = 0,
+                  use_precalc: bool = False) -> Optional[bytes]:
     """Every rank aligns its shard with `align_fn(seq_shard, offsets_shard) -> .aln bytes`; rank `dst`
-    gets the whole batch's .aln stream in input order."""
+    gets the whole batch's .aln stream in input order.  With seed_length > 0 the call is
+    `align_fn(seq_shard, offsets_shard, carry)`, carry = seed_carry_read() of the shard (or None): what makes the
+    sharded stream equal the serial reference's when reads no longer than the seed are present."""
     import torch.distributed as dist
     world, rank = dist.get_world_size(), dist.get_rank()
     n = len(offsets) - 1
@@ -50,6 +71,9 @@ def align_sharded(align_fn, seq: np.ndarray, offsets: np.ndarray, dst: int = 0) 
     o = np.ascontiguousarray(offsets[lo:hi + 1])
     sub_seq = seq[int(o[0]):int(o[-1])]
     sub_off = (o - o[0]).astype(np.uint64)
-    blob = align_fn(sub_seq, sub_off)
+    if seed_length > 0:
+        blob = align_fn(sub_seq, sub_off, seed_carry_read(seq, offsets, lo, seed_length, use_precalc))
+    else:
+        blob = align_fn(sub_seq, sub_off)
     parts = gather_bytes(blob, dst)
     return None if parts is None else b"".join(parts)

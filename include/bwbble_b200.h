@@ -52,7 +52,7 @@ typedef struct {
     int32_t matched_Ncontig;  /* unused by the reference's hot path */
     int32_t use_precalc;      /* -P: BWB_ERR_UNSUPPORTED */
     int32_t is_multiref;      /* 0 = -S single-genome mode */
-    int32_t n_threads;        /* -t: ignored by the device path */
+    int32_t n_threads;        /* -t: only selects which driver's D_seed semantics short reads get (see bwb_align) */
 } bwb_params;
 
 /* set_default_aln_params, align.c:22-38 */
@@ -179,9 +179,31 @@ int bwb_lower_bounds(bwb_ctx *ctx, const uint8_t *seq, const uint64_t *offsets, 
                      int32_t *d_main, int32_t *d_seed);
 
 /* The hot path: calculate_d + inexact_match for every read (inexact_match.c:25-168), results in
- * input order.  Host buffers in, host-readable results out (H2D/D2H inside). */
+ * input order.  Host buffers in, host-readable results out (H2D/D2H inside).
+ *
+ * One call = one call of the reference's driver on these reads, including its one order-dependent
+ * behaviour: a read no longer than seed_length gets no D_seed of its own and consults
+ * the bounds of the last longer read its driver thread aligned before it (zeros if none).
+ * params->n_threads <= 1 follows align_reads_inexact (one array for the whole call,
+ * inexact_match.c:36,62-64); n_threads > 1 follows align_reads_inexact_parallel (a fresh array per
+ * thread and 262144-read batch, static chunks, :115-121,141-143).  Nothing else depends on
+ * n_threads; reads longer than the seed are unaffected. */
 int bwb_align(bwb_ctx *ctx, const bwb_params *params, const uint8_t *seq, const uint64_t *offsets,
               uint64_t n_reads, bwb_results **out);
+
+/* A run split over several bwb_align calls (serial driver only): the last read longer than the seed
+ * that the earlier calls saw, whose D_seed short reads at the start of the next call inherit.
+ * bwb_set_option(ctx, "seed_carry", 1) starts a run in which every call updates it by itself
+ * (what bwb_align_fastq and the drop-in shim do); this function sets it explicitly (len = 0: none)
+ * -- for callers that shard a read set over processes (bwbble_b200/dist.py).  Host only. */
+int bwb_set_seed_carry(bwb_ctx *ctx, const uint8_t *read_seq, int len);
+
+/* Which read's D_seed does read r consult in one bwb_align call with these parameters (see above)?
+ * donor_of[r] = r (its own: the read is longer than the seed), the index of an earlier read, -1 (none:
+ * zeros; also for reads -P skips) or -2 (the run's carry, when have_carry).  Host only: the plan the
+ * device path follows, exposed for tests and for callers that shard a run themselves. */
+int bwb_seed_donor_plan(const bwb_params *p, const uint8_t *seq, const uint64_t *offsets, uint64_t n_reads,
+                        int have_carry, int64_t *donor_of);
 
 /* Device-resident variant: upload once, align many times (bench `value`; no PCIe in the loop). */
 int bwb_reads_upload(bwb_ctx *ctx, const uint8_t *seq, const uint64_t *offsets, uint64_t n_reads,

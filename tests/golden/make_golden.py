@@ -13,7 +13,8 @@ seeded multi-genome + reads, and records what the real reference produces:
     manifest.json                   tag -> flags, md5 of every file
 `python tests/golden/make_golden.py --precalc-only` adds the PGRID files to an existing golden set;
 `--shipped-fastq` adds the reference's own test_data/sim_chr21_N100.fastq (BASELINE configs[0]) with the outputs
-the reference produces for it on a small multi-genome the reads' loci were planted into (g21.fa).
+the reference produces for it on a small multi-genome the reads' loci were planted into (g21.fa);
+`--mixed-lengths` adds mixed.fq (reads of 14..60 bases, many no longer than the seed: SURVEY Q6) and its .aln files.
 The reference repository ships no golden vectors of its own, so these ARE the pin.
 """
 import gzip
@@ -133,7 +134,50 @@ def add_shipped_fastq(ref, manifest):
             manifest["md5"][f] = md5(os.path.join(HERE, f))
 
 
+MIXED = {
+    "mixed_n3": ["-n", "3"],
+    "mixed_n3_t3": ["-n", "3", "-t", "3"],
+    "mixed_n2_k1_l40": ["-n", "2", "-k", "1", "-l", "40"],
+    "mixed_P_n3": ["-P", "-n", "3"],
+}
+
+
+def add_mixed_lengths(ref, manifest):
+    """reads no longer than the seed (-l, default 32) do not get a D_seed of their own -- they consult the
+    array the previous longer read of their thread left behind (inexact_match.c:36,62-64 serial; :121,141-143 OpenMP;
+    with -P a read skipped for an N in its 12-mer leaves it untouched, :50-57).  mixed.fq = 400 reads of 14..60 bases."""
+    import golden_util
+    from bwbble_b200 import synth
+    run = lambda *a: subprocess.run([ref, *a], check=True, stdout=subprocess.DEVNULL)
+    g = synth.make_genome(101, 24000, n_records=2, snp_rate=0.015, tri_frac=0.08, n_bubbles=16, n_frac=0.03,
+                          n_repeat_copies=8, repeat_len=200, n_microsats=3, lowercase_frac=0.01)      # = g.fa (checked below)
+    reads = synth.make_reads(g, 108, 400, 60, 2, n_base_frac=0.004, bubble_frac=0.1, ragged=(14, 60))    # (seed chosen so that the serial and the OpenMP driver disagree)
+    reads.names = ["m%d" % i for i in range(reads.n)]
+    manifest["mixed"] = MIXED
+    with tempfile.TemporaryDirectory() as d:
+        fa = golden_util.materialise_index(d)
+        chk = os.path.join(d, "chk.fa")
+        g.write_fasta(chk)
+        assert open(chk, "rb").read() == open(fa, "rb").read(), "synth.make_genome no longer reproduces g.fa"
+        fq = os.path.join(HERE, "mixed.fq")
+        reads.write_fastq(fq)
+        manifest["md5"]["mixed.fq"] = md5(fq)
+        for tag, flags in MIXED.items():
+            aln = os.path.join(d, "out.aln")
+            run("align", *flags, fa, fq, aln)              # -P: the reference first writes g.fa.pre (minutes)
+            shutil.copy(aln, os.path.join(HERE, "aln_%s.aln" % tag))
+            manifest["md5"]["aln_%s.aln" % tag] = md5(aln)
+
+
 def main():
+    if "--mixed-lengths" in sys.argv:
+        import oracle
+        ref = oracle.ensure_ref_binary()
+        assert ref, "/root/reference is required to (re)generate the golden files"
+        manifest = json.load(open(os.path.join(HERE, "manifest.json")))
+        add_mixed_lengths(ref, manifest)
+        json.dump(manifest, open(os.path.join(HERE, "manifest.json"), "w"), indent=1, sort_keys=True)
+        return
     if "--shipped-fastq" in sys.argv:
         import oracle
         ref = oracle.ensure_ref_binary()

@@ -19,6 +19,11 @@ def pgrid():
     return MANIFEST.get("pgrid", {})
 
 
+def mixed():
+    """mixed-length cases (reads of 14..60 bases on g.fa): tag -> flags"""
+    return MANIFEST.get("mixed", {})
+
+
 def flags_to_kwargs(flags):
     kw, i = {}, 0
     while i < len(flags):

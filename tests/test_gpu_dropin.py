@@ -35,6 +35,17 @@ def test_dropin_cli_writes_the_reference_aln_and_sam(tmp_path, tag):
         assert open(sam, "rb").read() == G.golden_bytes("sam_%s.sam" % tag)
 
 
+@pytest.mark.parametrize("tag", ["mixed_n3", "mixed_n3_t3"])
+def test_dropin_cli_on_reads_shorter_than_the_seed(tmp_path, tag):
+    """SURVEY Q6 through the reference's own main(): serial entry point and -t 3 (OpenMP entry point) on mixed.fq"""
+    fa = G.materialise_index(tmp_path)
+    aln = str(tmp_path / "out.aln")
+    r = subprocess.run([GPU_BIN, "align", *G.mixed()[tag], fa, os.path.join(G.GOLDEN, "mixed.fq"), aln],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert open(aln, "rb").read() == G.golden_bytes("aln_%s.aln" % tag)
+
+
 def test_dropin_single_genome_mode_equals_reference_binary(tmp_path):
     """-S through the drop-in CLI against the reference binary run on the same files."""
     fa = G.materialise_index(tmp_path)

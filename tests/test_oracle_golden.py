@@ -2,6 +2,7 @@
 This is what pins the oracle on a box without /root/reference."""
 import os
 
+import numpy as np
 import pytest
 
 import golden_util as G
@@ -40,6 +41,27 @@ def test_oracle_reproduces_reference_aln_with_precalc(case, tag):
     exp = G.golden_bytes("aln_%s.aln" % tag)
     assert got == exp, "first difference (read, oracle, reference): %s" % (first_difference(got, exp),)
     assert got != G.golden_bytes("aln_n3.aln")
+
+
+@pytest.mark.parametrize("tag", sorted(G.mixed()))
+def test_oracle_reproduces_reference_on_reads_shorter_than_the_seed(case, tag):
+    """reads no longer than the seed consult the D_seed the previous longer read of their driver thread
+    left behind -- serial driver, OpenMP driver (-t 3) and -P, as the reference wrote them for mixed.fq"""
+    fa, _, orc = case
+    reads = read_fastq(os.path.join(G.GOLDEN, "mixed.fq"))
+    kw = G.flags_to_kwargs(G.mixed()[tag])
+    threads = kw.pop("n_threads", 1)
+    p = default_params(**kw)
+    got, _ = orc.align(reads.seq, reads.offsets, p, threads=threads)
+    exp = G.golden_bytes("aln_%s.aln" % tag)
+    assert got == exp, "first difference (read, oracle, reference): %s" % (first_difference(got, exp),)
+    lens = np.diff(reads.offsets.astype(np.int64))
+    assert (lens <= p.seed_length).sum() > 50 and (lens > p.seed_length).sum() > 50
+
+
+def test_mixed_length_goldens_depend_on_the_driver():
+    """the fixture bites: serial and OpenMP drivers give different bytes for the same reads"""
+    assert G.golden_bytes("aln_mixed_n3.aln") != G.golden_bytes("aln_mixed_n3_t3.aln")
 
 
 def test_golden_fixture_exercises_the_hard_cases():

@@ -79,3 +79,33 @@ def test_oracle_150bp_gapped_reads_config5_shape(case, tmp_path):
 def _genome(case):
     return synth.make_genome(31, 120000, n_records=3, snp_rate=0.015, tri_frac=0.06, n_bubbles=40, n_frac=0.04,
                              n_repeat_copies=30, n_microsats=6, lowercase_frac=0.01)
+
+
+def mixed_length_reads(genome, seed=77, n=400):
+    """reads of 14..60 bases: about 40 % are no longer than the default seed (32) and consult whatever D_seed the
+    previous longer read of their thread left behind (inexact_match.c:36,62-64,121,141-143)"""
+    return synth.make_reads(genome, seed, n, 60, 2, n_base_frac=0.004, bubble_frac=0.1, ragged=(14, 60))
+
+
+@pytest.mark.parametrize("kw", [dict(n=3), dict(n=3, t=3), dict(n=2, k=1, l=40)],      # (-P: tests/golden/aln_mixed_P_n3.aln)
+                         ids=lambda k: "-".join("%s%d" % kv for kv in k.items()))
+def test_oracle_short_reads_inherit_the_previous_seed_bounds(case, kw, tmp_path):
+    """Q6: for reads with len <= seed_length the reference does not recompute D_seed; serial and OpenMP drivers differ
+    in which stale array such a read sees.  The oracle follows both, byte for byte."""
+    reads = mixed_length_reads(_genome(case))
+    fq = str(tmp_path / "mixed.fq")
+    reads.write_fastq(fq)
+    p = default_params(**kw)
+    fa = case["fasta"]
+    out = str(tmp_path / "ref.aln")
+    subprocess.run([REF, "align", *params_to_cli(p), fa, fq, out], check=True, stdout=subprocess.DEVNULL)
+    exp = open(out, "rb").read()
+    orc = oracle.Oracle(fa + ".bwt")
+    got, _ = orc.align(reads.seq, reads.offsets, p, threads=p.n_threads)
+    # the test bites: aligned one at a time (fresh, all-zero D_seed) some short read comes out differently
+    alone = b"".join(orc.align(reads.read(r), [0, len(reads.read(r))], p)[0] for r in range(reads.n))
+    orc.close()
+    assert got == exp, first_difference(got, exp)
+    lens = [len(reads.read(r)) for r in range(reads.n)]
+    assert min(lens) <= 20 and sum(1 for x in lens if x <= p.seed_length) > 50
+    assert alone != exp
