@@ -344,6 +344,11 @@ __device__ __forceinline__ void load_upper(UpperBlock &b, const uint4 *__restric
     b.q0 = __ldg(blk); b.q1 = __ldg(blk + 1); b.q2 = __ldg(blk + 2); b.q3 = __ldg(blk + 3);
 }
 
+// (A/B, round 2: fetching the 32 index blocks of a warp's tasks with the WHOLE warp -- 8 lanes per block, 16 bytes each, so
+// that one load instruction touches 4 cache lines instead of 32 -- and handing them to their owners through the warp's
+// columns of sLj / sUj, XOR-swizzled, conflict-free: bit-exact and 17 % SLOWER, 0.85 against 1.02 M reads/s at 3 and at
+// 4 blocks/SM.  The L1's tag stage is not what limits the rank stage; 16 shuffles, 16 shared-memory round trips and
+// three more warp barriers per task are worse than 2 x 8 divergent 16-byte loads.  profiles/r02_ab_log.md)
 template <class T, bool HOIST>
 __device__ __forceinline__ uint32_t rank_general(const IndexView &ix, T (*sLj)[128], T (*sUj)[128], uint32_t o,
                                                  const T L, const T iU, const bool trueq, const T lastrow,
@@ -438,6 +443,7 @@ static_assert(FREE_RING > 0 && FREE_RING < 256 && (FREE_RING & (FREE_RING - 1)) 
 #ifndef BWB_HOIST_NARROW
 #define BWB_HOIST_NARROW 1
 #endif
+
 #define BWB_LANE_MIN_BLOCKS(WIDE) ((WIDE) ? 3 : BWB_LANE_BLOCKS_NARROW)
 template <bool WIDE, bool PRE, bool RECYCLE>
 __global__ void __launch_bounds__(128, BWB_LANE_MIN_BLOCKS(WIDE)) k_search_l(const __grid_constant__ LaneArgs a) {
