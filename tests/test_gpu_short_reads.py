@@ -94,7 +94,7 @@ def test_streaming_entry_point(mixed, tmp_path, tag, batch):
 
 
 @pytest.mark.parametrize("threads", [1, 5])
-def test_larger_seeded_case_against_the_oracle(mixed, small_case, threads):
+def test_larger_seeded_case_against_the_oracle(small_case, threads):
     """20 000 reads of 12..70 bases with N bases, -l 32 and -l 40, serial and 5-thread chunking"""
     al = Aligner(heap_pool_mb=256)
     al.load_index(small_case["bwt"])
