@@ -170,11 +170,11 @@ extern "C" long long bwb_align_fastq(bwb_ctx *ctx, const bwb_params *params, con
     // runs through the whole file, so it is carried from launch to launch; the OpenMP driver restarts it per thread
     // chunk of every 262144-read batch of the FILE, so launches must hold whole batches
     if (params->n_threads > 1) batch_reads = (batch_reads + 0x3ffff) / 0x40000 * 0x40000;
-    bwb_set_option(ctx, "seed_carry", params->n_threads > 1 ? 0 : 1);
     FILE *f = fopen(fastq_path, "rb");
     if (!f) return BWB_ERR_IO;
+    bwb_set_option(ctx, "seed_carry", params->n_threads > 1 ? 0 : 1);
     if (aln_path) remove(aln_path);                 // align.c:48
-    if (aln_path) { FILE *t = fopen(aln_path, "wb"); if (!t) { fclose(f); return BWB_ERR_IO; } fclose(t); }
+    if (aln_path) { FILE *t = fopen(aln_path, "wb"); if (!t) { fclose(f); bwb_set_option(ctx, "seed_carry", 0); return BWB_ERR_IO; } fclose(t); }
     // producer: parses up to batch_reads reads per batch, at most two parsed batches waiting
     struct Parsed { Batch b; int status = BWB_OK; bool eof = false; };
     std::mutex mu;
